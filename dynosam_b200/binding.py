@@ -1,0 +1,237 @@
+"""ctypes binding of libdynoba.so (include/dynoba.h).  No CPU fallback: a missing library or a
+missing sm_100 device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .problem import ARITY, DIM, JCOLS, MEAS_DIM, Problem
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdynoba.so")
+
+POSE6, POINT3, FLOW2 = 0, 1, 2
+OK, ERR_BAD_ARG, ERR_STATE, ERR_CUDA, ERR_INDETERMINATE, ERR_UNSUPPORTED, ERR_COMM = 0, -1, -2, -3, -4, -5, -6
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_u64p = C.POINTER(C.c_uint64)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+EXPORTS = [
+    "dynoba_version", "dynoba_status_string", "dynoba_last_error", "dynoba_create", "dynoba_destroy",
+    "dynoba_lm_default_params", "dynoba_set_variables", "dynoba_set_aux_poses", "dynoba_set_calibration",
+    "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_finalize", "dynoba_error",
+    "dynoba_optimize", "dynoba_get_variables", "dynoba_get_keys", "dynoba_num_variables", "dynoba_problem_info",
+    "dynoba_linearize", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
+    "dynoba_get_reduced_system", "dynoba_retract",
+]
+
+
+class LmParams(C.Structure):
+    _fields_ = [("lambda_initial", C.c_double), ("lambda_factor", C.c_double), ("lambda_upper_bound", C.c_double),
+                ("lambda_lower_bound", C.c_double), ("min_model_fidelity", C.c_double),
+                ("relative_error_tol", C.c_double), ("absolute_error_tol", C.c_double), ("error_tol", C.c_double),
+                ("max_iterations", C.c_int32), ("verbosity", C.c_int32)]
+
+
+class LmStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("inner_iterations", C.c_int32), ("error_initial", C.c_double),
+                ("error_final", C.c_double), ("lambda_final", C.c_double), ("reduced_dim", C.c_int32),
+                ("bandwidth", C.c_int32), ("kernel_launches", C.c_int64), ("ms_linearize", C.c_double),
+                ("ms_schur", C.c_double), ("ms_factor", C.c_double), ("ms_backsub", C.c_double),
+                ("ms_error", C.c_double), ("ms_total", C.c_double)]
+
+    def as_dict(self):
+        return {f[0]: getattr(self, f[0]) for f in self._fields_}
+
+
+class DynobaError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"libdynoba status {status}: {msg}")
+        self.status = status
+
+
+_LIB = None
+
+
+def load():
+    """dlopen libdynoba.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build the CUDA library first (__graft_entry__.build()); "
+                              "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.dynoba_status_string.restype = C.c_char_p
+        L.dynoba_last_error.restype = C.c_char_p
+        L.dynoba_last_error.argtypes = [C.c_void_p]
+        L.dynoba_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.dynoba_destroy.argtypes = [C.c_void_p]
+        L.dynoba_lm_default_params.argtypes = [C.POINTER(LmParams)]
+        L.dynoba_set_variables.argtypes = [C.c_void_p, C.c_int, C.c_int64, c_u64p, c_dp]
+        L.dynoba_set_aux_poses.argtypes = [C.c_void_p, C.c_int64, c_dp]
+        L.dynoba_set_calibration.argtypes = [C.c_void_p, c_dp]
+        L.dynoba_add_factors.argtypes = [C.c_void_p, C.c_int, C.c_int64, c_ip, c_dp, c_dp, C.c_int, C.c_int64, C.c_double, c_ip]
+        L.dynoba_set_pose_order.argtypes = [C.c_void_p, C.c_int64, c_ip]
+        L.dynoba_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p, C.c_int]
+        L.dynoba_finalize.argtypes = [C.c_void_p]
+        L.dynoba_error.argtypes = [C.c_void_p, c_dp]
+        L.dynoba_optimize.argtypes = [C.c_void_p, C.POINTER(LmParams), C.POINTER(LmStats)]
+        L.dynoba_get_variables.argtypes = [C.c_void_p, C.c_int, C.c_int64, c_dp]
+        L.dynoba_get_keys.argtypes = [C.c_void_p, C.c_int, C.c_int64, c_u64p]
+        L.dynoba_num_variables.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.dynoba_problem_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+        L.dynoba_linearize.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.dynoba_get_linearization.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp]
+        L.dynoba_get_factor_errors.argtypes = [C.c_void_p, C.c_int, c_dp]
+        L.dynoba_solve.argtypes = [C.c_void_p, C.c_double, c_dp]
+        L.dynoba_get_reduced_system.argtypes = [C.c_void_p, C.c_double, c_dp, c_dp]
+        L.dynoba_retract.argtypes = [C.c_void_p, c_dp]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None and a.size else C.cast(None, c_dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip) if a is not None and a.size else C.cast(None, c_ip)
+
+
+def default_params(**kw) -> LmParams:
+    p = LmParams()
+    load().dynoba_lm_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Solver:
+    """One dynoba handle == one optimiser instance (not thread-safe, like the reference's call site)."""
+
+    def __init__(self, problem: Problem | None = None, device: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        st = self.lib.dynoba_create(device, C.byref(self.h))
+        if st != OK:
+            raise DynobaError(st, self.lib.dynoba_status_string(st).decode() + " (no sm_100 CUDA device: libdynoba has no CPU path)")
+        self.problem = None
+        self._cb = None
+        if problem is not None:
+            self.ingest(problem)
+
+    def _ck(self, st):
+        if st != OK:
+            raise DynobaError(st, f"{self.lib.dynoba_status_string(st).decode()}: {self.lib.dynoba_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.dynoba_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- ingest
+    def ingest(self, p: Problem):
+        self.problem = p
+        L = self.lib
+        kp = p.pose_keys.ctypes.data_as(c_u64p) if p.pose_keys is not None else C.cast(None, c_u64p)
+        kq = p.point_keys.ctypes.data_as(c_u64p) if p.point_keys is not None else C.cast(None, c_u64p)
+        self._ck(L.dynoba_set_variables(self.h, POSE6, p.n_pose, kp, _dp(p.pose)))
+        self._ck(L.dynoba_set_variables(self.h, POINT3, p.n_point, kq, _dp(p.point)))
+        if p.n_flow:
+            self._ck(L.dynoba_set_variables(self.h, FLOW2, p.n_flow, C.cast(None, c_u64p), _dp(p.flow)))
+        if p.aux_pose.shape[0]:
+            self._ck(L.dynoba_set_aux_poses(self.h, p.aux_pose.shape[0], _dp(p.aux_pose)))
+        self._ck(L.dynoba_set_calibration(self.h, _dp(p.calib)))
+        for b in p.blocks:
+            self.add_factors(b)
+        if p.pose_order is not None:
+            self._ck(L.dynoba_set_pose_order(self.h, p.n_pose, _ip(p.pose_order)))
+
+    def add_factors(self, b):
+        self._ck(self.lib.dynoba_add_factors(self.h, b.type, b.n, _ip(b.idx), _dp(b.meas) if b.meas is not None else C.cast(None, c_dp),
+                                             _dp(b.sigma), b.sigma_dim, 1 if b.sigma_bcast else b.n, float(b.robust_k),
+                                             _ip(b.aux_idx) if b.aux_idx is not None else C.cast(None, c_ip)))
+
+    def set_shard(self, rank, world, allreduce, min_bandwidth=0):
+        """allreduce(dev_ptr:int, n:int, stream:int) -> None sums n doubles in place across ranks."""
+        def _cb(ctx, dev, n, stream):
+            try:
+                allreduce(dev, n, stream)
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("all-reduce callback failed:", e)
+                return 1
+        self._cb = ALLREDUCE_FN(_cb)
+        self._ck(self.lib.dynoba_set_shard(self.h, rank, world, self._cb, None, min_bandwidth))
+
+    def finalize(self):
+        self._ck(self.lib.dynoba_finalize(self.h))
+
+    # ---- compute
+    def error(self) -> float:
+        out = C.c_double()
+        self._ck(self.lib.dynoba_error(self.h, C.byref(out)))
+        return out.value
+
+    def optimize(self, params: LmParams | None = None, **kw) -> dict:
+        prm = params if params is not None else default_params(**kw)
+        st = LmStats()
+        self._ck(self.lib.dynoba_optimize(self.h, C.byref(prm), C.byref(st)))
+        return st.as_dict()
+
+    def linearize(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.dynoba_linearize(self.h, C.byref(ms)))
+        return ms.value
+
+    def linearization(self, bi):
+        b = self.problem.blocks[bi]
+        A = np.zeros((b.n, DIM[b.type], JCOLS[b.type])); bv = np.zeros((b.n, DIM[b.type]))
+        self._ck(self.lib.dynoba_get_linearization(self.h, bi, _dp(A), _dp(bv)))
+        return A, bv
+
+    def factor_errors(self, bi):
+        e = np.zeros(self.problem.blocks[bi].n)
+        self._ck(self.lib.dynoba_get_factor_errors(self.h, bi, _dp(e)))
+        return e
+
+    def solve(self, lam):
+        p = self.problem
+        d = np.zeros(6*p.n_pose + 3*p.n_point + 2*p.n_flow)
+        self._ck(self.lib.dynoba_solve(self.h, float(lam), _dp(d)))
+        return d
+
+    def reduced_system(self, lam):
+        n = 6*self.problem.n_pose
+        S = np.zeros((n, n)); g = np.zeros(n)
+        self._ck(self.lib.dynoba_get_reduced_system(self.h, float(lam), _dp(S), _dp(g)))
+        return S, g
+
+    def retract(self, delta):
+        delta = np.ascontiguousarray(delta, dtype=np.float64)
+        self._ck(self.lib.dynoba_retract(self.h, _dp(delta)))
+
+    def info(self):
+        n = C.c_int32(); bw = C.c_int32(); jb = C.c_int64()
+        self._ck(self.lib.dynoba_problem_info(self.h, C.byref(n), C.byref(bw), C.byref(jb)))
+        return dict(reduced_dim=n.value, bandwidth=bw.value, jacobian_bytes=jb.value)
+
+    def values(self):
+        p = self.problem
+        pose = np.zeros((p.n_pose, 12)); point = np.zeros((p.n_point, 3)); flow = np.zeros((p.n_flow, 2))
+        self._ck(self.lib.dynoba_get_variables(self.h, POSE6, p.n_pose, _dp(pose)))
+        if p.n_point:
+            self._ck(self.lib.dynoba_get_variables(self.h, POINT3, p.n_point, _dp(point)))
+        if p.n_flow:
+            self._ck(self.lib.dynoba_get_variables(self.h, FLOW2, p.n_flow, _dp(flow)))
+        return pose, point, flow

@@ -1,0 +1,693 @@
+// api.cu -- host side of libdynoba: C-ABI entry points (include/dynoba.h), symbolic phase (ordering, landmark
+// grouping, band structure), device upload and the Levenberg-Marquardt control loop.
+//
+// The LM loop is a literal restatement of GTSAM 4.2.0's LevenbergMarquardtOptimizer::{iterate,tryLambda} and
+// NonlinearOptimizer::defaultOptimize [GTSAM-ext], which is what the reference runs at
+// dynosam/src/backend/RegularBackendModule.cc:405-428.  Control decisions need two scalars per trial step, so
+// the loop lives on the host and everything else stays on the device.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/dynoba.h"
+#include "internal.cuh"
+
+using namespace dynoba;
+
+namespace {
+
+struct HostBlock {
+  int type = 0; int64_t n = 0;
+  std::vector<int32_t> idx; std::vector<double> meas, sigma; int sigma_dim = 1; bool bcast = true;
+  double robust_k = 0; std::vector<int32_t> aux; bool has_aux = false;
+  // finalize products
+  std::vector<int32_t> perm;   // sorted position -> original factor index
+  DevBlock dev{};
+  bool simple = false, pose_only = false;
+  int part_off = 0, bs_off = 0;
+};
+
+}  // namespace
+
+struct dynoba_solver {
+  int device = 0; cudaStream_t stream = nullptr; std::string err;
+  std::vector<double> pose, point, flow, aux; std::vector<uint64_t> kpose, kpoint, kflow;
+  double calib[6] = { 721.5377, 721.5377, 0.0, 609.5593, 172.854, 0.5372 };
+  std::vector<int32_t> hint;
+  std::vector<HostBlock> blocks;
+  bool finalized = false, linearized = false, supported = true;
+  std::vector<int32_t> pos, pt_new, fl_new;
+  DevVars cur{}, cand{}; DevBand band{};
+  double *dl_point = nullptr, *dl_flow = nullptr, *partials = nullptr, *scalars = nullptr;
+  int* fail = nullptr; int n_partials = 0, n_lin_partials = 0, n_bs_partials = 0;
+  int rank = 0, world = 1; dynoba_allreduce_fn allreduce = nullptr; void* ar_ctx = nullptr; int min_bw = 0;
+  int64_t launches = 0; int64_t jac_bytes = 0;
+  std::vector<void*> allocs;
+  cudaEvent_t ev[8]{};
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DYNOBA_ERR_CUDA; } } while (0)
+#define ARG(cond, msg) do { if (!(cond)) { if (h) h->err = msg; return DYNOBA_ERR_BAD_ARG; } } while (0)
+
+static int pad32(int64_t n) { return (int)((n + 31)/32*32); }
+
+template <class T> static int dalloc(dynoba_solver* h, T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  CK(cudaMalloc((void**)p, count*sizeof(T)));
+  h->allocs.push_back((void*)*p);
+  return DYNOBA_OK;
+}
+static void free_device(dynoba_solver* h) {
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+  h->finalized = false; h->linearized = false;
+}
+
+extern "C" {
+
+int dynoba_version(void) { return 100; }
+
+const char* dynoba_status_string(int s) {
+  switch (s) {
+    case DYNOBA_OK: return "ok";
+    case DYNOBA_ERR_BAD_ARG: return "bad argument";
+    case DYNOBA_ERR_STATE: return "bad call order";
+    case DYNOBA_ERR_CUDA: return "CUDA error / no usable device";
+    case DYNOBA_ERR_INDETERMINATE: return "indeterminate linear system";
+    case DYNOBA_ERR_UNSUPPORTED: return "unsupported topology";
+    case DYNOBA_ERR_COMM: return "all-reduce callback failed";
+    default: return "unknown";
+  }
+}
+const char* dynoba_last_error(dynoba_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+void dynoba_lm_default_params(dynoba_lm_params* p) {
+  p->lambda_initial = 1e-5; p->lambda_factor = 10.0; p->lambda_upper_bound = 1e5; p->lambda_lower_bound = 0.0;
+  p->min_model_fidelity = 1e-3; p->relative_error_tol = 1e-5; p->absolute_error_tol = 1e-5; p->error_tol = 0.0;
+  p->max_iterations = 100; p->verbosity = 0;
+}
+
+int dynoba_create(int device, dynoba_handle* out) {
+  if (!out) return DYNOBA_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return DYNOBA_ERR_CUDA;  // no CPU fallback
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return DYNOBA_ERR_CUDA;
+  dynoba_solver* h = new dynoba_solver();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DYNOBA_ERR_CUDA; }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  *out = h;
+  return DYNOBA_OK;
+}
+
+int dynoba_destroy(dynoba_handle h) {
+  if (!h) return DYNOBA_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  free_device(h);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DYNOBA_OK;
+}
+
+int dynoba_set_variables(dynoba_handle h, int kind, int64_t n, const uint64_t* keys, const double* data) {
+  ARG(h, "null handle"); ARG(n >= 0 && (n == 0 || data), "null data");
+  const int w = kind == DYNOBA_POSE6 ? 12 : (kind == DYNOBA_POINT3 ? 3 : 2);
+  std::vector<double>* dst = kind == DYNOBA_POSE6 ? &h->pose : (kind == DYNOBA_POINT3 ? &h->point : (kind == DYNOBA_FLOW2 ? &h->flow : nullptr));
+  std::vector<uint64_t>* kd = kind == DYNOBA_POSE6 ? &h->kpose : (kind == DYNOBA_POINT3 ? &h->kpoint : &h->kflow);
+  ARG(dst, "bad variable kind");
+  const bool same_shape = dst->size() == (size_t)n*w;
+  dst->assign(data, data + (size_t)n*w);
+  if (keys) kd->assign(keys, keys + n); else kd->clear();
+  if (h->finalized && same_shape) {
+    // refresh device values only (layout unchanged)
+    cudaSetDevice(h->device);
+    std::vector<double> soa;
+    if (kind == DYNOBA_POSE6) {
+      soa.assign((size_t)12*h->cur.np_stride, 0.0);
+      for (int64_t i = 0; i < n; i++) for (int k = 0; k < 12; k++) soa[(size_t)k*h->cur.np_stride + h->pos[i]] = data[i*12 + k];
+      for (int p = (int)n; p < h->cur.np_stride; p++) { soa[(size_t)0*h->cur.np_stride + p] = soa[(size_t)4*h->cur.np_stride + p] = soa[(size_t)8*h->cur.np_stride + p] = 1.0; }
+      CK(cudaMemcpyAsync(h->cur.pose, soa.data(), soa.size()*8, cudaMemcpyHostToDevice, h->stream));
+    } else if (kind == DYNOBA_POINT3) {
+      soa.assign((size_t)3*h->cur.nl_stride, 0.0);
+      for (int64_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) soa[(size_t)k*h->cur.nl_stride + h->pt_new[i]] = data[i*3 + k];
+      CK(cudaMemcpyAsync(h->cur.point, soa.data(), soa.size()*8, cudaMemcpyHostToDevice, h->stream));
+    } else {
+      soa.assign((size_t)2*h->cur.nf_stride, 0.0);
+      for (int64_t i = 0; i < n; i++) for (int k = 0; k < 2; k++) soa[(size_t)k*h->cur.nf_stride + h->fl_new[i]] = data[i*2 + k];
+      CK(cudaMemcpyAsync(h->cur.flow, soa.data(), soa.size()*8, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->linearized = false;
+  } else if (h->finalized) {
+    free_device(h);
+  }
+  return DYNOBA_OK;
+}
+
+int dynoba_set_aux_poses(dynoba_handle h, int64_t n, const double* data) {
+  ARG(h, "null handle"); ARG(n >= 0 && (n == 0 || data), "null data");
+  h->aux.assign(data, data + (size_t)n*12);
+  if (h->finalized) free_device(h);
+  return DYNOBA_OK;
+}
+int dynoba_set_calibration(dynoba_handle h, const double calib[6]) {
+  ARG(h, "null handle"); ARG(calib, "null calib");
+  for (int i = 0; i < 6; i++) { h->calib[i] = calib[i]; h->cur.K[i] = calib[i]; h->cand.K[i] = calib[i]; }
+  h->linearized = false;
+  return DYNOBA_OK;
+}
+
+int dynoba_add_factors(dynoba_handle h, int type, int64_t n, const int32_t* idx, const double* meas, const double* sigma,
+                       int sigma_dim, int64_t sigma_count, double robust_k, const int32_t* aux_idx) {
+  ARG(h, "null handle"); ARG(type >= 0 && type < F_NUM_TYPES, "bad factor type");
+  const TypeInfo ti = type_info(type);
+  ARG(n >= 0 && (n == 0 || idx), "null idx"); ARG(ti.meas == 0 || n == 0 || meas, "factor type needs measurements");
+  ARG(sigma && (sigma_dim == 1 || sigma_dim == ti.dim), "sigma_dim must be 1 or the residual dimension");
+  ARG(sigma_count == 1 || sigma_count == n, "sigma_count must be 1 or n"); ARG(!ti.needs_aux || n == 0 || aux_idx, "factor type needs aux_idx");
+  HostBlock b; b.type = type; b.n = n;
+  b.idx.assign(idx, idx + (size_t)n*ti.arity);
+  if (ti.meas) b.meas.assign(meas, meas + (size_t)n*ti.meas);
+  b.sigma_dim = sigma_dim; b.bcast = sigma_count == 1 && n != 1;
+  b.sigma.assign(sigma, sigma + (size_t)sigma_count*sigma_dim);
+  for (double s : b.sigma) ARG(s > 0, "sigma must be positive");
+  b.robust_k = robust_k;
+  if (aux_idx) { b.aux.assign(aux_idx, aux_idx + n); b.has_aux = true; }
+  h->blocks.push_back(std::move(b));
+  if (h->finalized) free_device(h);
+  return DYNOBA_OK;
+}
+
+int dynoba_set_pose_order(dynoba_handle h, int64_t n, const int32_t* rank) {
+  ARG(h, "null handle"); ARG(n >= 0 && (n == 0 || rank), "null rank");
+  h->hint.assign(rank, rank + n);
+  if (h->finalized) free_device(h);
+  return DYNOBA_OK;
+}
+
+int dynoba_set_shard(dynoba_handle h, int rank, int world, dynoba_allreduce_fn fn, void* ctx, int min_bandwidth) {
+  ARG(h, "null handle"); ARG(world >= 1 && rank >= 0 && rank < world, "bad rank/world"); ARG(world == 1 || fn, "world > 1 needs an all-reduce");
+  h->rank = rank; h->world = world; h->allreduce = fn; h->ar_ctx = ctx; h->min_bw = min_bandwidth;
+  if (h->finalized) free_device(h);
+  return DYNOBA_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ finalize
+static int uf_find(std::vector<int32_t>& p, int x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
+
+static int finalize_impl(dynoba_solver* h) {
+  if (h->finalized) return DYNOBA_OK;
+  cudaSetDevice(h->device);
+  const int64_t np = (int64_t)h->pose.size()/12, npt = (int64_t)h->point.size()/3, nfl = (int64_t)h->flow.size()/2, naux = (int64_t)h->aux.size()/12;
+  ARG(h->hint.empty() || (int64_t)h->hint.size() == np, "pose order hint length != number of poses");
+  // ---- validate indices
+  for (auto& b : h->blocks) {
+    const TypeInfo ti = type_info(b.type);
+    for (int64_t i = 0; i < b.n; i++) for (int k = 0; k < ti.arity; k++) {
+      const int32_t ix = b.idx[i*ti.arity + k];
+      const int64_t lim = ti.cls[k] == VC_POSE ? np : (ti.cls[k] == VC_POINT ? npt : nfl);
+      ARG(ix >= 0 && ix < lim, "factor index out of range");
+    }
+    if (b.has_aux) for (int64_t i = 0; i < b.n; i++) ARG(b.aux[i] >= 0 && b.aux[i] < naux, "aux index out of range");
+  }
+  // ---- pose ordering
+  h->pos.resize(np);
+  {
+    std::vector<int32_t> ord(np); std::iota(ord.begin(), ord.end(), 0);
+    if (!h->hint.empty()) std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return h->hint[a] < h->hint[b]; });
+    for (int64_t i = 0; i < np; i++) h->pos[ord[i]] = (int32_t)i;
+  }
+  // ---- landmark groups (union-find across factors that touch two landmarks)
+  const int64_t nl = npt + nfl;
+  std::vector<int32_t> uf(nl); std::iota(uf.begin(), uf.end(), 0);
+  auto lmk_id = [&](int cls, int ix) { return cls == VC_POINT ? ix : (int)npt + ix; };
+  for (auto& b : h->blocks) {
+    const TypeInfo ti = type_info(b.type);
+    if (ti.nlmk < 2) continue;
+    for (int64_t i = 0; i < b.n; i++) {
+      int first = -1;
+      for (int k = 0; k < ti.arity; k++) if (ti.cls[k] != VC_POSE) {
+        const int l = lmk_id(ti.cls[k], b.idx[i*ti.arity + k]);
+        if (first < 0) first = l; else { const int a = uf_find(uf, first), c = uf_find(uf, l); if (a != c) uf[c] = a; }
+      }
+    }
+  }
+  std::vector<int32_t> root(nl); for (int64_t i = 0; i < nl; i++) root[i] = uf_find(uf, (int)i);
+  std::vector<int32_t> gmin(nl, INT32_MAX), gmax(nl, -1), gblk(nl, -1), gcount(nl, 0);
+  for (int64_t i = 0; i < nl; i++) gcount[root[i]]++;
+  int spread = 0;
+  for (size_t bi = 0; bi < h->blocks.size(); bi++) {
+    auto& b = h->blocks[bi]; const TypeInfo ti = type_info(b.type);
+    b.pose_only = ti.nlmk == 0;
+    int lslot = -1; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] != VC_POSE) { lslot = k; break; }
+    for (int64_t i = 0; i < b.n; i++) {
+      int lo = INT32_MAX, hi = -1;
+      for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE) { const int p = h->pos[b.idx[i*ti.arity + k]]; lo = std::min(lo, p); hi = std::max(hi, p); }
+      if (lslot < 0) { spread = std::max(spread, hi - lo); continue; }
+      const int g = root[lmk_id(ti.cls[lslot], b.idx[i*ti.arity + lslot])];
+      gmin[g] = std::min(gmin[g], lo); gmax[g] = std::max(gmax[g], hi);
+      if (gblk[g] == -1) gblk[g] = (int)bi; else if (gblk[g] != (int)bi) gblk[g] = -2;
+    }
+  }
+  for (int64_t g = 0; g < nl; g++) if (gmax[g] >= 0) spread = std::max(spread, gmax[g] - gmin[g]);
+  // group rank: by first pose position, then root id
+  std::vector<int32_t> gorder; gorder.reserve(nl);
+  for (int64_t g = 0; g < nl; g++) if (root[g] == g) gorder.push_back((int32_t)g);
+  std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return gmin[a] < gmin[b]; });
+  std::vector<int32_t> grank(nl, 0);
+  for (size_t r = 0; r < gorder.size(); r++) grank[gorder[r]] = (int32_t)r;
+  // landmark device indices
+  h->pt_new.assign(npt, 0); h->fl_new.assign(nfl, 0);
+  {
+    std::vector<int32_t> ord(npt); std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return grank[root[a]] < grank[root[b]]; });
+    for (int64_t i = 0; i < npt; i++) h->pt_new[ord[i]] = (int32_t)i;
+    std::vector<int32_t> of(nfl); std::iota(of.begin(), of.end(), 0);
+    std::stable_sort(of.begin(), of.end(), [&](int a, int b) { return grank[root[npt + a]] < grank[root[npt + b]]; });
+    for (int64_t i = 0; i < nfl; i++) h->fl_new[of[i]] = (int32_t)i;
+  }
+  // ---- band structure
+  DevBand& B = h->band;
+  B.n = (int)(6*np);
+  int bw = 6*spread + 5; if (bw < h->min_bw) bw = h->min_bw; if (bw > B.n - 1) bw = std::max(B.n - 1, 0);
+  B.bw = bw; B.NT = std::max((B.n + TILE - 1)/TILE, 1); B.n_pad = B.NT*TILE;
+  B.WB = (bw + TILE - 1)/TILE; if (B.NT > 1 && B.WB < 1) B.WB = 1; if (B.WB > B.NT - 1) B.WB = B.NT - 1;
+  B.tile_count = (size_t)B.NT*(B.WB + 1);
+  { // tiles and rhs contiguous so that one all-reduce covers both
+    double* buf; int rc = dalloc(h, &buf, B.tile_count*TILE2 + B.n_pad); if (rc) return rc;
+    B.tiles = buf; B.rhs = buf + B.tile_count*TILE2;
+  }
+  // ---- variables
+  DevVars& V = h->cur;
+  V.np = (int)np; V.np_stride = pad32(np); V.nl = (int)npt; V.nl_stride = pad32(npt); V.nf = (int)nfl; V.nf_stride = pad32(nfl);
+  V.naux = (int)naux; V.naux_stride = pad32(naux);
+  for (int i = 0; i < 6; i++) V.K[i] = h->calib[i];
+  h->cand = V;
+  {
+    std::vector<double> soa((size_t)12*V.np_stride, 0.0);
+    for (int p = 0; p < V.np_stride; p++) soa[(size_t)0*V.np_stride + p] = soa[(size_t)4*V.np_stride + p] = soa[(size_t)8*V.np_stride + p] = 1.0;
+    for (int64_t i = 0; i < np; i++) for (int k = 0; k < 12; k++) soa[(size_t)k*V.np_stride + h->pos[i]] = h->pose[i*12 + k];
+    int rc = dalloc(h, &h->cur.pose, soa.size()); if (rc) return rc; rc = dalloc(h, &h->cand.pose, soa.size()); if (rc) return rc;
+    CK(cudaMemcpy(h->cur.pose, soa.data(), soa.size()*8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->cand.pose, soa.data(), soa.size()*8, cudaMemcpyHostToDevice));
+    soa.assign((size_t)3*V.nl_stride, 0.0);
+    for (int64_t i = 0; i < npt; i++) for (int k = 0; k < 3; k++) soa[(size_t)k*V.nl_stride + h->pt_new[i]] = h->point[i*3 + k];
+    rc = dalloc(h, &h->cur.point, soa.size()); if (rc) return rc; rc = dalloc(h, &h->cand.point, soa.size()); if (rc) return rc;
+    rc = dalloc(h, &h->dl_point, soa.size()); if (rc) return rc;
+    CK(cudaMemcpy(h->cur.point, soa.data(), soa.size()*8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->dl_point, 0, std::max<size_t>(soa.size(), 1)*8));
+    soa.assign((size_t)2*V.nf_stride, 0.0);
+    for (int64_t i = 0; i < nfl; i++) for (int k = 0; k < 2; k++) soa[(size_t)k*V.nf_stride + h->fl_new[i]] = h->flow[i*2 + k];
+    rc = dalloc(h, &h->cur.flow, soa.size()); if (rc) return rc; rc = dalloc(h, &h->cand.flow, soa.size()); if (rc) return rc;
+    rc = dalloc(h, &h->dl_flow, soa.size()); if (rc) return rc;
+    CK(cudaMemcpy(h->cur.flow, soa.data(), soa.size()*8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->dl_flow, 0, std::max<size_t>(soa.size(), 1)*8));
+    soa.assign((size_t)12*V.naux_stride, 0.0);
+    for (int64_t i = 0; i < naux; i++) for (int k = 0; k < 12; k++) soa[(size_t)k*V.naux_stride + i] = h->aux[i*12 + k];
+    double* da; rc = dalloc(h, &da, soa.size()); if (rc) return rc;
+    CK(cudaMemcpy(da, soa.data(), soa.size()*8, cudaMemcpyHostToDevice));
+    h->cur.aux = da; h->cand.aux = da;
+  }
+  // ---- factor blocks
+  h->supported = true; h->jac_bytes = 96*(np + naux) + 24*npt + 16*nfl;
+  int part = 0, bs = 0;
+  for (size_t bi = 0; bi < h->blocks.size(); bi++) {
+    auto& b = h->blocks[bi]; const TypeInfo ti = type_info(b.type);
+    const int64_t n = b.n; const int stride = pad32(n);
+    int lslot = -1, pslot = -1;
+    for (int k = 0; k < ti.arity; k++) { if (ti.cls[k] != VC_POSE && lslot < 0) lslot = k; if (ti.cls[k] == VC_POSE && pslot < 0) pslot = k; }
+    b.perm.resize(n); std::iota(b.perm.begin(), b.perm.end(), 0);
+    std::vector<int32_t> frank;
+    if (lslot >= 0) {
+      frank.resize(n);
+      std::vector<int64_t> key(n);
+      for (int64_t i = 0; i < n; i++) {
+        frank[i] = grank[root[lmk_id(ti.cls[lslot], b.idx[i*ti.arity + lslot])]];
+        key[i] = ((int64_t)frank[i] << 32) | (uint32_t)h->pos[b.idx[i*ti.arity + pslot]];
+      }
+      std::stable_sort(b.perm.begin(), b.perm.end(), [&](int a, int c) { return key[a] < key[c]; });
+    }
+    // SoA host images
+    std::vector<int32_t> hidx((size_t)ti.arity*stride, 0);
+    std::vector<double> hmeas((size_t)std::max(ti.meas, 1)*stride, 0.0), hsig((size_t)b.sigma_dim*stride, 1.0);
+    std::vector<int32_t> haux(stride, 0);
+    for (int64_t s = 0; s < n; s++) {
+      const int64_t o = b.perm[s];
+      for (int k = 0; k < ti.arity; k++) {
+        const int32_t ix = b.idx[o*ti.arity + k];
+        hidx[(size_t)k*stride + s] = ti.cls[k] == VC_POSE ? h->pos[ix] : (ti.cls[k] == VC_POINT ? h->pt_new[ix] : h->fl_new[ix]);
+      }
+      for (int k = 0; k < ti.meas; k++) hmeas[(size_t)k*stride + s] = b.meas[o*ti.meas + k];
+      for (int k = 0; k < b.sigma_dim; k++) hsig[(size_t)k*stride + s] = 1.0/(b.bcast ? b.sigma[k] : b.sigma[o*b.sigma_dim + k]);
+      if (b.has_aux) haux[s] = b.aux[o];
+    }
+    DevBlock& d = b.dev; d = DevBlock{};
+    d.type = b.type; d.n = (int)n; d.stride = stride; d.sigma_dim = b.sigma_dim; d.robust_k = b.robust_k;
+    int* di; double* dm; double* ds; int* dax = nullptr; int rc;
+    if ((rc = dalloc(h, &di, hidx.size()))) return rc; CK(cudaMemcpy(di, hidx.data(), hidx.size()*4, cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &dm, hmeas.size()))) return rc; CK(cudaMemcpy(dm, hmeas.data(), hmeas.size()*8, cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &ds, hsig.size()))) return rc; CK(cudaMemcpy(ds, hsig.data(), hsig.size()*8, cudaMemcpyHostToDevice));
+    if (b.has_aux) { if ((rc = dalloc(h, &dax, haux.size()))) return rc; CK(cudaMemcpy(dax, haux.data(), haux.size()*4, cudaMemcpyHostToDevice)); }
+    d.idx = di; d.meas = dm; d.isig = ds; d.aux = dax;
+    if ((rc = dalloc(h, &d.J, (size_t)ti.dim*ti.jcols*stride))) return rc;
+    if ((rc = dalloc(h, &d.b, (size_t)ti.dim*stride))) return rc;
+    CK(cudaMemset(d.J, 0, (size_t)ti.dim*ti.jcols*stride*8)); CK(cudaMemset(d.b, 0, (size_t)ti.dim*stride*8));
+    // groups
+    b.simple = false;
+    if (lslot >= 0) {
+      std::vector<int32_t> gp, gl; bool simple = ti.nlmk == 1;
+      for (int64_t s = 0; s < n; s++) {
+        const int64_t o = b.perm[s];
+        if (s == 0 || frank[o] != frank[b.perm[s-1]]) {
+          gp.push_back((int32_t)s);
+          const int l = lmk_id(ti.cls[lslot], b.idx[o*ti.arity + lslot]);
+          gl.push_back(hidx[(size_t)lslot*stride + s]);
+          if (gblk[root[l]] != (int)bi || gcount[root[l]] != 1) simple = false;
+        }
+      }
+      gp.push_back((int32_t)n);
+      int* dgp; int* dgl;
+      if ((rc = dalloc(h, &dgp, gp.size()))) return rc; CK(cudaMemcpy(dgp, gp.data(), gp.size()*4, cudaMemcpyHostToDevice));
+      if ((rc = dalloc(h, &dgl, gl.size()))) return rc; if (!gl.empty()) CK(cudaMemcpy(dgl, gl.data(), gl.size()*4, cudaMemcpyHostToDevice));
+      d.n_groups = (int)gl.size(); d.grp_ptr = dgp; d.grp_lmk = dgl;
+      b.simple = simple;
+      if (!simple && n > 0) h->supported = false;
+    }
+    b.part_off = part; part += linearize_grid((int)n);
+    b.bs_off = bs; bs += b.pose_only ? (int)((n + 127)/128) : backsub_grid(d.n_groups);
+    const int64_t rd = 4*ti.arity + 8*ti.meas + 8*b.sigma_dim + (b.has_aux ? 4 : 0), wr = 8*(ti.dim*ti.jcols + ti.dim);
+    h->jac_bytes += n*(rd + wr);
+  }
+  h->n_lin_partials = part; h->n_bs_partials = bs + pose_norm_grid(B.n);
+  h->n_partials = std::max(std::max(h->n_lin_partials, h->n_bs_partials), 1);
+  { int rc; if ((rc = dalloc(h, &h->partials, (size_t)h->n_partials))) return rc; if ((rc = dalloc(h, &h->scalars, 8))) return rc; if ((rc = dalloc(h, &h->fail, 1))) return rc; }
+  CK(cudaMemset(h->scalars, 0, 64)); CK(cudaMemset(h->fail, 0, 4));
+  CK(cudaDeviceSynchronize());
+  h->finalized = true; h->linearized = false;
+  return DYNOBA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device steps
+__global__ void pack_fail_kernel(const int* fail, double* scalars) { scalars[3] = (double)(*fail); }
+
+static int allreduce_dev(dynoba_solver* h, double* p, size_t n) {
+  if (h->world <= 1) return DYNOBA_OK;
+  if (h->allreduce(h->ar_ctx, p, n, (void*)h->stream) != 0) { h->err = "all-reduce callback failed"; return DYNOBA_ERR_COMM; }
+  return DYNOBA_OK;
+}
+
+// graph.error(values) on the given variable set -> scalars[slot]
+static int eval_error(dynoba_solver* h, const DevVars& v, int slot) {
+  for (auto& b : h->blocks) h->launches += launch_error(b.dev, v, h->partials + b.part_off, nullptr, h->stream);
+  h->launches += launch_sum(h->partials, h->n_lin_partials, h->scalars + slot, h->stream);
+  return DYNOBA_OK;
+}
+static int do_linearize(dynoba_solver* h) {
+  for (auto& b : h->blocks) h->launches += launch_linearize(b.dev, h->cur, h->partials + b.part_off, h->stream);
+  h->launches += launch_sum(h->partials, h->n_lin_partials, h->scalars + 0, h->stream);
+  h->linearized = true;
+  return DYNOBA_OK;
+}
+// S, g_S at the current linearization
+static int build_reduced(dynoba_solver* h, double lambda) {
+  CK(cudaMemsetAsync(h->fail, 0, 4, h->stream));
+  h->launches += launch_band_clear(h->band, lambda, h->rank == 0, h->stream);
+  for (auto& b : h->blocks) {
+    if (b.pose_only) h->launches += launch_pose_factors(b.dev, h->band, h->stream);
+    else h->launches += launch_schur_simple(b.dev, h->band, lambda, h->fail, h->stream);
+  }
+  return allreduce_dev(h, h->band.tiles, h->band.tile_count*TILE2 + h->band.n_pad);
+}
+// factor + solve + back-substitute; scalars[1] = linearised cost decrease
+static int solve_step(dynoba_solver* h, double lambda) {
+  h->launches += launch_band_cholesky(h->band, h->fail, h->stream);
+  h->launches += launch_band_backsolve(h->band, h->stream);
+  int used = 0;
+  for (auto& b : h->blocks) {
+    if (b.pose_only) { h->launches += launch_pose_model(b.dev, h->band, h->partials + b.bs_off, h->stream); used = std::max(used, b.bs_off + (int)((b.n + 127)/128)); }
+    else { h->launches += launch_backsub_simple(b.dev, h->band, lambda, h->dl_point, h->cur.nl_stride, h->dl_flow, h->cur.nf_stride, h->partials + b.bs_off, h->stream);
+           used = std::max(used, b.bs_off + backsub_grid(b.dev.n_groups)); }
+  }
+  if (h->rank == 0) { h->launches += launch_pose_delta_norm(h->band, lambda, h->partials + used, h->stream); used += pose_norm_grid(h->band.n); }
+  h->launches += launch_sum(h->partials, used, h->scalars + 1, h->stream);
+  return DYNOBA_OK;
+}
+
+static int check_ready(dynoba_solver* h, bool need_supported) {
+  if (!h) return DYNOBA_ERR_BAD_ARG;
+  int rc = finalize_impl(h); if (rc) return rc;
+  cudaSetDevice(h->device);
+  if (need_supported && !h->supported) { h->err = "graph has landmark groups the Schur kernels do not handle yet (chains / landmarks spanning blocks)"; return DYNOBA_ERR_UNSUPPORTED; }
+  return DYNOBA_OK;
+}
+
+static int read_scalars(dynoba_solver* h, double* out4, bool reduce) {
+  pack_fail_kernel<<<1, 1, 0, h->stream>>>(h->fail, h->scalars); h->launches++;
+  if (reduce) { int rc = allreduce_dev(h, h->scalars, 4); if (rc) return rc; }
+  CK(cudaMemcpyAsync(out4, h->scalars, 32, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DYNOBA_OK;
+}
+
+extern "C" {
+
+int dynoba_finalize(dynoba_handle h) { if (!h) return DYNOBA_ERR_BAD_ARG; return finalize_impl(h); }
+
+int dynoba_num_variables(dynoba_handle h, int kind, int64_t* out) {
+  ARG(h && out, "null");
+  *out = kind == DYNOBA_POSE6 ? (int64_t)h->pose.size()/12 : (kind == DYNOBA_POINT3 ? (int64_t)h->point.size()/3 : (int64_t)h->flow.size()/2);
+  return DYNOBA_OK;
+}
+int dynoba_get_keys(dynoba_handle h, int kind, int64_t n, uint64_t* out) {
+  ARG(h && out, "null");
+  auto& k = kind == DYNOBA_POSE6 ? h->kpose : (kind == DYNOBA_POINT3 ? h->kpoint : h->kflow);
+  ARG((int64_t)k.size() == n, "no keys stored / size mismatch");
+  std::copy(k.begin(), k.end(), out);
+  return DYNOBA_OK;
+}
+int dynoba_problem_info(dynoba_handle h, int32_t* reduced_dim, int32_t* bandwidth, int64_t* jacobian_bytes) {
+  int rc = check_ready(h, false); if (rc) return rc;
+  if (reduced_dim) *reduced_dim = h->band.n; if (bandwidth) *bandwidth = h->band.bw; if (jacobian_bytes) *jacobian_bytes = h->jac_bytes;
+  return DYNOBA_OK;
+}
+
+int dynoba_error(dynoba_handle h, double* out) {
+  int rc = check_ready(h, false); if (rc) return rc;
+  ARG(out, "null out");
+  eval_error(h, h->cur, 2);
+  double s[4]; rc = read_scalars(h, s, true); if (rc) return rc;
+  *out = s[2];
+  return DYNOBA_OK;
+}
+
+int dynoba_linearize(dynoba_handle h, float* ms) {
+  int rc = check_ready(h, false); if (rc) return rc;
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  do_linearize(h);
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (ms) CK(cudaEventElapsedTime(ms, h->ev[0], h->ev[1]));
+  CK(cudaGetLastError());
+  return DYNOBA_OK;
+}
+
+int dynoba_get_linearization(dynoba_handle h, int bi, double* A, double* bv) {
+  int rc = check_ready(h, false); if (rc) return rc;
+  ARG(bi >= 0 && bi < (int)h->blocks.size(), "bad block index");
+  if (!h->linearized) { h->err = "call dynoba_linearize first"; return DYNOBA_ERR_STATE; }
+  auto& b = h->blocks[bi]; const TypeInfo ti = type_info(b.type); const int ne = ti.dim*ti.jcols, st = b.dev.stride;
+  std::vector<double> hj((size_t)ne*st), hb((size_t)ti.dim*st);
+  CK(cudaMemcpy(hj.data(), b.dev.J, hj.size()*8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hb.data(), b.dev.b, hb.size()*8, cudaMemcpyDeviceToHost));
+  for (int64_t s = 0; s < b.n; s++) {
+    const int64_t o = b.perm[s];
+    if (A) for (int e = 0; e < ne; e++) A[o*ne + e] = hj[(size_t)e*st + s];
+    if (bv) for (int r = 0; r < ti.dim; r++) bv[o*ti.dim + r] = hb[(size_t)r*st + s];
+  }
+  return DYNOBA_OK;
+}
+
+int dynoba_get_factor_errors(dynoba_handle h, int bi, double* err) {
+  int rc = check_ready(h, false); if (rc) return rc;
+  ARG(bi >= 0 && bi < (int)h->blocks.size() && err, "bad block index");
+  auto& b = h->blocks[bi];
+  double* d; rc = dalloc(h, &d, (size_t)b.dev.stride); if (rc) return rc;
+  h->launches += launch_error(b.dev, h->cur, h->partials + b.part_off, d, h->stream);
+  std::vector<double> he(b.dev.stride);
+  CK(cudaMemcpyAsync(he.data(), d, he.size()*8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int64_t s = 0; s < b.n; s++) err[b.perm[s]] = he[s];
+  cudaFree(d); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)d));
+  return DYNOBA_OK;
+}
+
+int dynoba_get_reduced_system(dynoba_handle h, double lambda, double* S, double* g) {
+  int rc = check_ready(h, true); if (rc) return rc;
+  if (!h->linearized) do_linearize(h);
+  rc = build_reduced(h, lambda); if (rc) return rc;
+  const DevBand& B = h->band;
+  std::vector<double> ht(B.tile_count*TILE2), hr(B.n_pad);
+  CK(cudaMemcpyAsync(ht.data(), B.tiles, ht.size()*8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(hr.data(), B.rhs, hr.size()*8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int n = B.n; const int64_t np = n/6;
+  std::vector<int32_t> inv(np); for (int64_t i = 0; i < np; i++) inv[h->pos[i]] = (int32_t)i;
+  auto user = [&](int s) { return 6*inv[s/6] + s%6; };
+  if (S) {
+    std::fill(S, S + (size_t)n*n, 0.0);
+    for (int j = 0; j < n; j++) for (int i = j; i < n && i <= j + (B.WB + 1)*TILE; i++) {
+      const int I = i >> 5, Jt = j >> 5; if (I - Jt > B.WB) break;
+      const double v = ht[band_index(B, i, j)];
+      S[(size_t)user(i)*n + user(j)] = v; S[(size_t)user(j)*n + user(i)] = v;
+    }
+  }
+  if (g) for (int i = 0; i < n; i++) g[user(i)] = hr[i];
+  return DYNOBA_OK;
+}
+
+static int download_delta(dynoba_solver* h, double* delta) {
+  const DevBand& B = h->band; const int64_t np = B.n/6, npt = h->cur.nl, nfl = h->cur.nf;
+  std::vector<double> hr(B.n_pad), hp((size_t)3*h->cur.nl_stride), hf((size_t)2*h->cur.nf_stride);
+  CK(cudaMemcpyAsync(hr.data(), B.rhs, hr.size()*8, cudaMemcpyDeviceToHost, h->stream));
+  if (npt) CK(cudaMemcpyAsync(hp.data(), h->dl_point, hp.size()*8, cudaMemcpyDeviceToHost, h->stream));
+  if (nfl) CK(cudaMemcpyAsync(hf.data(), h->dl_flow, hf.size()*8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < np; i++) for (int c = 0; c < 6; c++) delta[6*i + c] = hr[6*(size_t)h->pos[i] + c];
+  double* dp = delta + 6*np;
+  for (int64_t i = 0; i < npt; i++) for (int c = 0; c < 3; c++) dp[3*i + c] = hp[(size_t)c*h->cur.nl_stride + h->pt_new[i]];
+  double* df = dp + 3*npt;
+  for (int64_t i = 0; i < nfl; i++) for (int c = 0; c < 2; c++) df[2*i + c] = hf[(size_t)c*h->cur.nf_stride + h->fl_new[i]];
+  return DYNOBA_OK;
+}
+
+int dynoba_solve(dynoba_handle h, double lambda, double* delta) {
+  int rc = check_ready(h, true); if (rc) return rc;
+  ARG(delta, "null delta");
+  if (!h->linearized) do_linearize(h);
+  rc = build_reduced(h, lambda); if (rc) return rc;
+  solve_step(h, lambda);
+  double s[4]; rc = read_scalars(h, s, true); if (rc) return rc;
+  CK(cudaGetLastError());
+  if (s[3] != 0.0) { h->err = "reduced system not positive definite"; return DYNOBA_ERR_INDETERMINATE; }
+  return download_delta(h, delta);
+}
+
+int dynoba_retract(dynoba_handle h, const double* delta) {
+  int rc = check_ready(h, false); if (rc) return rc;
+  ARG(delta, "null delta");
+  const DevBand& B = h->band; const int64_t np = B.n/6, npt = h->cur.nl, nfl = h->cur.nf;
+  std::vector<double> hr(B.n_pad, 0.0), hp((size_t)3*h->cur.nl_stride, 0.0), hf((size_t)2*h->cur.nf_stride, 0.0);
+  for (int64_t i = 0; i < np; i++) for (int c = 0; c < 6; c++) hr[6*(size_t)h->pos[i] + c] = delta[6*i + c];
+  const double* dp = delta + 6*np;
+  for (int64_t i = 0; i < npt; i++) for (int c = 0; c < 3; c++) hp[(size_t)c*h->cur.nl_stride + h->pt_new[i]] = dp[3*i + c];
+  const double* df = dp + 3*npt;
+  for (int64_t i = 0; i < nfl; i++) for (int c = 0; c < 2; c++) hf[(size_t)c*h->cur.nf_stride + h->fl_new[i]] = df[2*i + c];
+  CK(cudaMemcpyAsync(B.rhs, hr.data(), hr.size()*8, cudaMemcpyHostToDevice, h->stream));
+  if (npt) CK(cudaMemcpyAsync(h->dl_point, hp.data(), hp.size()*8, cudaMemcpyHostToDevice, h->stream));
+  if (nfl) CK(cudaMemcpyAsync(h->dl_flow, hf.data(), hf.size()*8, cudaMemcpyHostToDevice, h->stream));
+  h->launches += launch_retract(h->cur, h->cand, h->band, h->dl_point, h->dl_flow, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  std::swap(h->cur, h->cand);
+  h->linearized = false;
+  return DYNOBA_OK;
+}
+
+int dynoba_get_variables(dynoba_handle h, int kind, int64_t n, double* out) {
+  int rc = check_ready(h, false); if (rc) return rc;
+  ARG(out, "null out");
+  const DevVars& V = h->cur;
+  if (kind == DYNOBA_POSE6) {
+    ARG(n == V.np, "size mismatch");
+    std::vector<double> soa((size_t)12*V.np_stride);
+    CK(cudaMemcpy(soa.data(), V.pose, soa.size()*8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; i++) for (int k = 0; k < 12; k++) out[i*12 + k] = soa[(size_t)k*V.np_stride + h->pos[i]];
+  } else if (kind == DYNOBA_POINT3) {
+    ARG(n == V.nl, "size mismatch");
+    std::vector<double> soa((size_t)3*V.nl_stride);
+    CK(cudaMemcpy(soa.data(), V.point, soa.size()*8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) out[i*3 + k] = soa[(size_t)k*V.nl_stride + h->pt_new[i]];
+  } else if (kind == DYNOBA_FLOW2) {
+    ARG(n == V.nf, "size mismatch");
+    std::vector<double> soa((size_t)2*V.nf_stride);
+    CK(cudaMemcpy(soa.data(), V.flow, soa.size()*8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; i++) for (int k = 0; k < 2; k++) out[i*2 + k] = soa[(size_t)k*V.nf_stride + h->fl_new[i]];
+  } else ARG(false, "bad kind");
+  return DYNOBA_OK;
+}
+
+// LevenbergMarquardtOptimizer::optimize()  [GTSAM-ext nonlinear/{NonlinearOptimizer,LevenbergMarquardtOptimizer}.cpp]
+int dynoba_optimize(dynoba_handle h, const dynoba_lm_params* prm, dynoba_lm_stats* st) {
+  int rc = check_ready(h, true); if (rc) return rc;
+  dynoba_lm_params P; if (prm) P = *prm; else dynoba_lm_default_params(&P);
+  dynoba_lm_stats S; std::memset(&S, 0, sizeof(S));
+  const int64_t launches0 = h->launches;
+  cudaEvent_t* ev = h->ev;
+  float ms;
+  auto tick = [&](int i) { cudaEventRecord(ev[i], h->stream); };
+  auto tock = [&](int a, int b, double& acc) { cudaEventElapsedTime(&ms, ev[a], ev[b]); acc += ms; };
+  double sc[4];
+  tick(6);
+  tick(0); eval_error(h, h->cur, 2); tick(1);
+  rc = read_scalars(h, sc, true); if (rc) return rc;
+  tock(0, 1, S.ms_error);
+  double err = sc[2], lambda = P.lambda_initial;
+  S.error_initial = err; S.reduced_dim = h->band.n; S.bandwidth = h->band.bw;
+  int iterations = 0, inner = 0;
+  if (!(err <= P.error_tol) && P.max_iterations > 0) {
+    double newError = err, currentError;
+    do {
+      currentError = newError;
+      tick(0); do_linearize(h); tick(1);
+      for (;;) {   // tryLambda
+        tick(2); rc = build_reduced(h, lambda); if (rc) return rc;
+        tick(3); solve_step(h, lambda);
+        tick(4);
+        h->launches += launch_retract(h->cur, h->cand, h->band, h->dl_point, h->dl_flow, h->stream);
+        eval_error(h, h->cand, 2);
+        tick(5);
+        rc = read_scalars(h, sc, true); if (rc) return rc;
+        if (iterations + inner >= 0) { tock(2, 3, S.ms_schur); tock(3, 4, S.ms_factor); tock(4, 5, S.ms_error); }
+        const bool solved = sc[3] == 0.0 && std::isfinite(sc[1]);
+        bool success = false, stop = false; double nerr = INFINITY;
+        if (solved) {
+          const double oldLin = sc[0], lin = sc[1];
+          if (lin >= 0) {
+            nerr = sc[2];
+            const double cost = err - nerr;
+            if (lin > DBL_EPSILON*oldLin) { const double fid = cost/lin; success = fid > P.min_model_fidelity; }
+            if (std::fabs(cost) < P.relative_error_tol*err) stop = true;
+          }
+          if (P.verbosity > 0) std::fprintf(stderr, "[dynoba-lm] it %d inner %d lambda %.3e err %.12e -> %.12e lin %.6e %s\n", iterations, inner, lambda, err, nerr, lin, success ? "ok" : "rej");
+        } else if (P.verbosity > 0) std::fprintf(stderr, "[dynoba-lm] it %d inner %d lambda %.3e solve failed (flag %.0f)\n", iterations, inner, lambda, sc[3]);
+        if (success) { std::swap(h->cur, h->cand); h->linearized = false; lambda = std::max(P.lambda_lower_bound, lambda/P.lambda_factor); err = nerr; iterations++; inner++; break; }
+        else if (!stop) { lambda *= P.lambda_factor; inner++; if (lambda >= P.lambda_upper_bound) break; }
+        else break;
+      }
+      { float m2; cudaEventElapsedTime(&m2, ev[0], ev[1]); S.ms_linearize += m2; }
+      newError = err;
+    } while (iterations < P.max_iterations &&
+             !((newError <= P.error_tol) ||
+               ((P.relative_error_tol != 0.0) && ((currentError - newError)/currentError <= P.relative_error_tol)) ||
+               ((currentError - newError) <= P.absolute_error_tol)) &&
+             std::isfinite(currentError));
+  }
+  tick(7); cudaEventSynchronize(ev[7]); cudaEventElapsedTime(&ms, ev[6], ev[7]); S.ms_total = ms;
+  S.iterations = iterations; S.inner_iterations = inner; S.error_final = err; S.lambda_final = lambda;
+  S.kernel_launches = h->launches - launches0;
+  if (st) *st = S;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return DYNOBA_ERR_CUDA; }
+  return DYNOBA_OK;
+}
+
+}  // extern "C"

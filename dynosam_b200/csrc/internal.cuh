@@ -1,0 +1,72 @@
+// internal.cuh -- device data model shared by the kernel translation units (DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "factors.cuh"
+
+namespace dynoba {
+
+constexpr int TILE = 32;           // band-Cholesky tile edge
+constexpr int TILE2 = TILE*TILE;
+
+// Variables, SoA, fp64.  Pose-like variables are stored in *solver order* (ordered by the frame hint),
+// landmarks in group order (sorted by the first pose they touch).  strides are padded to 32.
+struct DevVars {
+  int np, np_stride;   double* pose;   // [12][np_stride]  rows 0-8 R (row-major), 9-11 t
+  int nl, nl_stride;   double* point;  // [3][nl_stride]
+  int nf, nf_stride;   double* flow;   // [2][nf_stride]
+  int naux, naux_stride; const double* aux;  // [12][naux_stride]
+  double K[6];
+};
+
+// One homogeneous factor block, sorted by landmark group, SoA.
+struct DevBlock {
+  int type, n, stride;
+  const int* idx;       // [arity][stride]   pose slots: solver position; point/flow slots: device index
+  const double* meas;   // [meas][stride]
+  const double* isig;   // [sigma_dim][stride]  1/sigma
+  int sigma_dim;
+  const int* aux;       // [stride] or nullptr
+  double robust_k;
+  double* J;            // [dim*jcols][stride]  whitened, Huber-weighted Jacobian, element e = row*jcols + col
+  double* b;            // [dim][stride]        rhs = -sqrt(w) * r_w
+  // landmark groups (simple groups: exactly one landmark, all of its factors in this block)
+  int n_groups;
+  const int* grp_ptr;   // [n_groups+1] into the sorted factor range
+  const int* grp_lmk;   // [n_groups]   device landmark index
+};
+
+// Band storage of the reduced (camera + object-motion) system, lower triangle, TILE x TILE tiles:
+// tile (I,J), J <= I <= J+WB at tiles[(J*(WB+1) + (I-J))*TILE2], element (r,c) at c*TILE + r.
+struct DevBand {
+  int n, n_pad, NT, WB, bw;
+  double* tiles;        // [NT*(WB+1)*TILE2]
+  double* rhs;          // [n_pad]   g_S, then y = L^-1 g_S, then delta_p (solver order)
+  size_t tile_count;
+};
+__host__ __device__ __forceinline__ size_t band_index(const DevBand& B, int i, int j) {  // requires i >= j
+  const int I = i >> 5, Jt = j >> 5;
+  return ((size_t)Jt*(B.WB + 1) + (I - Jt))*TILE2 + (size_t)(j & 31)*TILE + (i & 31);
+}
+
+// ---- launchers (each returns the number of kernels it launched)
+int launch_linearize(const DevBlock& blk, const DevVars& v, double* partials, cudaStream_t s);
+int launch_error(const DevBlock& blk, const DevVars& v, double* partials, double* per_factor, cudaStream_t s);
+int launch_sum(const double* partials, int n, double* out, cudaStream_t s);
+int linearize_grid(int n);          // number of partial sums a linearize/error launch of n factors writes
+
+int launch_band_clear(const DevBand& B, double lambda, int add_damping, cudaStream_t s);
+int launch_schur_simple(const DevBlock& blk, const DevBand& B, double lambda, int* fail, cudaStream_t s);
+int launch_pose_factors(const DevBlock& blk, const DevBand& B, cudaStream_t s);
+int launch_band_cholesky(const DevBand& B, int* fail, cudaStream_t s);
+int launch_band_backsolve(const DevBand& B, cudaStream_t s);
+int launch_backsub_simple(const DevBlock& blk, const DevBand& B, double lambda, double* dl_point, int nl_stride,
+                          double* dl_flow, int nf_stride, double* partials, cudaStream_t s);
+int backsub_grid(int n_groups);
+int launch_pose_model(const DevBlock& blk, const DevBand& B, double* partials, cudaStream_t s);
+int launch_pose_delta_norm(const DevBand& B, double lambda, double* partials, cudaStream_t s);
+int pose_norm_grid(int n);
+int launch_retract(const DevVars& cur, const DevVars& cand, const DevBand& B, const double* dl_point,
+                   const double* dl_flow, cudaStream_t s);
+
+}  // namespace dynoba

@@ -1,0 +1,144 @@
+/*
+ * dynoba.h -- C ABI of libdynoba: B200-native (sm_100a) batch nonlinear-least-squares hot path for DynOSAM.
+ *
+ * This is the drop-in boundary for the reference's solver call
+ *     gtsam::LevenbergMarquardtOptimizer problem(graph, theta, params);
+ *     gtsam::Values v = problem.optimize();  problem.getInnerIterations();  problem.iterations();
+ * at /root/reference/dynosam/src/backend/RegularBackendModule.cc:405-428 (same shape at
+ * dynosam_opt/src/SlidingWindowOptimization.cc:67-77, dynosam/test/internal/backend_runners.hpp:187-193,
+ * dynosam/include/dynosam/frontend/vision/MotionSolver-inl.hpp:184-199).  The header-only C++ adapter
+ * include/dynoba_gtsam_adapter.hpp flattens a gtsam::NonlinearFactorGraph / Values into these calls.
+ *
+ * Plain C types only: no torch, no CUDA types (streams are void*).  All functions return a
+ * dynoba_status (0 = ok, < 0 = error); no exception crosses the ABI.  A handle is NOT thread-safe;
+ * use one handle per optimiser instance (the reference calls from exactly one backend thread,
+ * src/pipeline/PipelineManager.cc:175-250).  Host arrays are copied during the call; nothing is retained.
+ * There is no CPU fallback: every compute entry point fails with DYNOBA_ERR_CUDA when no sm_100 device works.
+ */
+#ifndef DYNOBA_H
+#define DYNOBA_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dynoba_solver* dynoba_handle;
+
+typedef enum {
+  DYNOBA_OK = 0,
+  DYNOBA_ERR_BAD_ARG = -1,
+  DYNOBA_ERR_STATE = -2,        /* call order violated (e.g. optimize before variables are set) */
+  DYNOBA_ERR_CUDA = -3,         /* CUDA runtime / no usable device */
+  DYNOBA_ERR_INDETERMINATE = -4,/* reduced system not SPD even at lambda upper bound
+                                   (adapter maps this to gtsam::IndeterminantLinearSystemException) */
+  DYNOBA_ERR_UNSUPPORTED = -5,  /* topology outside what the kernels handle */
+  DYNOBA_ERR_COMM = -6          /* user all-reduce callback failed */
+} dynoba_status;
+
+/* Variable kinds (reference value types: gtsam::Pose3, gtsam::Point3, gtsam::Point2 optical-flow variable
+ * of Pose3FlowProjectionFactor, dynosam/include/dynosam/factors/Pose3FlowProjectionFactor.h:45-71). */
+typedef enum { DYNOBA_POSE6 = 0, DYNOBA_POINT3 = 1, DYNOBA_FLOW2 = 2 } dynoba_var_kind;
+
+/* Factor types.  idx columns are the factor's keys in the reference's constructor order.
+ *  type               reference factor (file:line)                                           keys (idx columns)            meas            */
+typedef enum {
+  DYNOBA_PRIOR6 = 0,        /* gtsam::PriorFactor<Pose3>   (Formulation-impl.hpp:523-533)              pose                 prior pose (12)   */
+  DYNOBA_BETWEEN6 = 1,      /* gtsam::BetweenFactor<Pose3> (dynosam_opt/src/FactorGraphTools.cc:53-63) pose1, pose2         measured (12)     */
+  DYNOBA_POSE2POINT3 = 2,   /* gtsam::PoseToPointFactor    (Formulation-impl.hpp:169-172)              pose, point          z (3)             */
+  DYNOBA_STEREO3 = 3,       /* gtsam::GenericStereoFactor  (Formulation-impl.hpp:292-293)              pose, point          uL,uR,v (3)       */
+  DYNOBA_TERNARY3 = 4,      /* LandmarkMotionTernaryFactor (src/factors/LandmarkMotionTernaryFactor.cc:41-72) prev pt, cur pt, motion   -      */
+  DYNOBA_HYBRID3 = 5,       /* HybridMotionFactor          (src/factors/HybridFormulationFactors.cc:137-187) X_k, e_H_k, m_L   z (3) + aux L_e */
+  DYNOBA_HYBRID_STEREO3 = 6,/* StereoHybridMotionFactor    (HybridFormulationFactors.cc:213-261)       X_k, e_H_k, m_L      uL,uR,v + aux L_e */
+  DYNOBA_MOTIONPOSE3 = 7,   /* LandmarkMotionPoseFactor    (src/factors/LandmarkMotionPoseFactor.cc:42-105) prev pt, cur pt, prev L, cur L  - */
+  DYNOBA_SMOOTH_HYBRID6 = 8,/* HybridSmoothingFactor       (HybridFormulationFactors.cc:274-322)       H_k-2, H_k-1, H_k    aux L_e           */
+  DYNOBA_SMOOTH_POSE6 = 9,  /* LandmarkPoseSmoothingFactor (src/factors/LandmarkPoseSmoothingFactor.cc:37-95) L_k-2, L_k-1, L_k   -            */
+  DYNOBA_FLOWPROJ2 = 10,    /* Pose3FlowProjectionFactor   (factors/Pose3FlowProjectionFactor.h:73-133) flow, pose          kp(2),depth,X_prev(12) */
+  DYNOBA_NUM_FACTOR_TYPES = 11
+} dynoba_factor_type;
+
+/* gtsam::LevenbergMarquardtParams (defaults = GTSAM 4.2.0, see dynoba_lm_default_params) */
+typedef struct {
+  double lambda_initial, lambda_factor, lambda_upper_bound, lambda_lower_bound;
+  double min_model_fidelity;
+  double relative_error_tol, absolute_error_tol, error_tol;
+  int32_t max_iterations;
+  int32_t verbosity;            /* 0 silent, 1 per-iteration line on stderr */
+} dynoba_lm_params;
+
+typedef struct {
+  int32_t iterations;           /* LevenbergMarquardtOptimizer::iterations()        */
+  int32_t inner_iterations;     /* LevenbergMarquardtOptimizer::getInnerIterations() */
+  double error_initial, error_final, lambda_final;
+  int32_t reduced_dim, bandwidth;
+  int64_t kernel_launches;      /* libdynoba kernels launched by this optimize() call */
+  double ms_linearize, ms_schur, ms_factor, ms_backsub, ms_error, ms_total; /* CUDA-event timings */
+} dynoba_lm_stats;
+
+/* Sum-all-reduce of n doubles at device pointer `dev` on CUDA stream `stream`, in place.  Supplied by the
+ * multi-GPU host (bench.py passes torch.distributed.all_reduce over NCCL).  Return 0 on success. */
+typedef int (*dynoba_allreduce_fn)(void* ctx, double* dev, size_t n, void* stream);
+
+/* ---- lifecycle */
+int dynoba_version(void);
+const char* dynoba_status_string(int status);
+const char* dynoba_last_error(dynoba_handle h);
+int dynoba_create(int device, dynoba_handle* out);
+int dynoba_destroy(dynoba_handle h);
+void dynoba_lm_default_params(dynoba_lm_params* p);
+
+/* ---- problem ingest (gtsam::Values / NonlinearFactorGraph equivalents) */
+/* kind POSE6: data[n][12] = R row-major (9) | t (3);  POINT3: data[n][3];  FLOW2: data[n][2].
+ * keys (optional, may be NULL): opaque gtsam::Key values, round-tripped by dynoba_get_keys. */
+int dynoba_set_variables(dynoba_handle h, int kind, int64_t n, const uint64_t* keys, const double* data);
+/* Fixed poses referenced through aux_idx (HybridMotionFactor's L_e): data[n][12]. */
+int dynoba_set_aux_poses(dynoba_handle h, int64_t n, const double* data);
+/* Cal3_S2Stereo: fx, fy, skew, u0, v0, baseline (also Cal3_S2 for FLOWPROJ2, baseline ignored). */
+int dynoba_set_calibration(dynoba_handle h, const double calib[6]);
+/* idx[n][arity] (int32 indices into the variable arrays of the slot's kind), meas[n][meas_dim] or NULL,
+ * sigma: sigma_count == 1 -> one row [sigma_dim] shared by all n factors, else [n][sigma_dim];
+ * sigma_dim is 1 (Isotropic) or the residual dimension (Diagonal); robust_k > 0 wraps the noise model in
+ * noiseModel::Robust(mEstimator::Huber(k)) (BackendDefinitions.cc:170-193), <= 0 = Gaussian;
+ * aux_idx[n] or NULL. */
+int dynoba_add_factors(dynoba_handle h, int type, int64_t n, const int32_t* idx, const double* meas,
+                       const double* sigma, int sigma_dim, int64_t sigma_count, double robust_k,
+                       const int32_t* aux_idx);
+/* Optional elimination-order hint for pose-like variables (e.g. the frame id encoded in the key):
+ * variables are ordered by (rank, index).  Without it the given order is used. */
+int dynoba_set_pose_order(dynoba_handle h, int64_t n, const int32_t* rank);
+/* Multi-GPU: rank/world of the landmark shard held by this handle and the all-reduce used for the reduced
+ * system and the scalar sums.  min_bandwidth forces a common band layout on all ranks (0 = local). */
+int dynoba_set_shard(dynoba_handle h, int rank, int world, dynoba_allreduce_fn fn, void* ctx, int min_bandwidth);
+/* Builds the device layout (sorting, CSR, band structure) and uploads.  Called implicitly by the
+ * compute entry points; exposed so that uploads can be timed separately. */
+int dynoba_finalize(dynoba_handle h);
+
+/* ---- compute */
+int dynoba_error(dynoba_handle h, double* out);                       /* graph.error(values) */
+int dynoba_optimize(dynoba_handle h, const dynoba_lm_params* p, dynoba_lm_stats* stats);
+int dynoba_get_variables(dynoba_handle h, int kind, int64_t n, double* out);
+int dynoba_get_keys(dynoba_handle h, int kind, int64_t n, uint64_t* out);
+int dynoba_num_variables(dynoba_handle h, int kind, int64_t* out);
+int dynoba_problem_info(dynoba_handle h, int32_t* reduced_dim, int32_t* bandwidth, int64_t* jacobian_bytes);
+
+/* ---- stepwise / parity hooks (what gtsam exposes as graph.linearize(values)) */
+/* Materialising linearize of every factor at the current values (the roofline kernel).  Returns the
+ * CUDA-event time of the linearize kernels alone in *ms (may be NULL). */
+int dynoba_linearize(dynoba_handle h, float* ms);
+/* Whitened Jacobian A[n][dim][jcols] and rhs b[n][dim] of the block_index-th dynoba_add_factors call,
+ * in the caller's factor order (valid after dynoba_linearize / dynoba_optimize). */
+int dynoba_get_linearization(dynoba_handle h, int block_index, double* A, double* b);
+/* Per-factor nonlinear error of one block (0.5|r_w|^2 or Huber rho). */
+int dynoba_get_factor_errors(dynoba_handle h, int block_index, double* err);
+/* One damped solve (J^T J + lambda I) delta = J^T b through Schur + band Cholesky at the current
+ * linearization; delta laid out [poses(6) in caller order | points(3) | flows(2)]. */
+int dynoba_solve(dynoba_handle h, double lambda, double* delta);
+/* Dense copy of the reduced camera/motion system S (dim x dim, row-major, caller pose order) and g_S. */
+int dynoba_get_reduced_system(dynoba_handle h, double lambda, double* S, double* g);
+/* values.retract(delta), same layout as dynoba_solve */
+int dynoba_retract(dynoba_handle h, const double* delta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNOBA_H */
