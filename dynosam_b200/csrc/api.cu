@@ -44,7 +44,7 @@ struct dynoba_solver {
   std::vector<int32_t> pos, pt_new, fl_new;
   DevVars cur{}, cand{}; DevBand band{};
   double *dl_point = nullptr, *dl_flow = nullptr, *partials = nullptr, *scalars = nullptr;
-  int* fail = nullptr; int n_partials = 0, n_lin_partials = 0, n_bs_partials = 0;
+  int* fail = nullptr; int* chol_flags = nullptr; double* linv = nullptr; int n_partials = 0, n_lin_partials = 0, n_bs_partials = 0;
   int rank = 0, world = 1; dynoba_allreduce_fn allreduce = nullptr; void* ar_ctx = nullptr; int min_bw = 0;
   int64_t launches = 0; int64_t jac_bytes = 0;
   std::vector<void*> allocs;
@@ -286,6 +286,8 @@ static int finalize_impl(dynoba_solver* h) {
   { // tiles and rhs contiguous so that one all-reduce covers both
     double* buf; int rc = dalloc(h, &buf, B.tile_count*TILE2 + B.n_pad); if (rc) return rc;
     B.tiles = buf; B.rhs = buf + B.tile_count*TILE2;
+    if ((rc = dalloc(h, &h->chol_flags, 2*B.tile_count + B.NT))) return rc;
+    if ((rc = dalloc(h, &h->linv, (size_t)B.NT*TILE2))) return rc;
   }
   // ---- variables
   DevVars& V = h->cur;
@@ -430,8 +432,8 @@ static int build_reduced(dynoba_solver* h, double lambda) {
 }
 // factor + solve + back-substitute; scalars[1] = linearised cost decrease
 static int solve_step(dynoba_solver* h, double lambda) {
-  h->launches += launch_band_cholesky(h->band, h->fail, h->stream);
-  h->launches += launch_band_backsolve(h->band, h->stream);
+  h->launches += launch_band_cholesky(h->band, h->chol_flags, h->linv, h->fail, h->stream);
+  h->launches += launch_band_solve(h->band, h->linv, h->stream);
   int used = 0;
   for (auto& b : h->blocks) {
     if (b.pose_only) { h->launches += launch_pose_model(b.dev, h->band, h->partials + b.bs_off, h->stream); used = std::max(used, b.bs_off + (int)((b.n + 127)/128)); }

@@ -58,8 +58,8 @@ int linearize_grid(int n);          // number of partial sums a linearize/error 
 int launch_band_clear(const DevBand& B, double lambda, int add_damping, cudaStream_t s);
 int launch_schur_simple(const DevBlock& blk, const DevBand& B, double lambda, int* fail, cudaStream_t s);
 int launch_pose_factors(const DevBlock& blk, const DevBand& B, cudaStream_t s);
-int launch_band_cholesky(const DevBand& B, int* fail, cudaStream_t s);
-int launch_band_backsolve(const DevBand& B, cudaStream_t s);
+int launch_band_cholesky(const DevBand& B, int* flags /*[2*NT*(WB+1) + NT]*/, double* linv /*[NT*TILE2]*/, int* fail, cudaStream_t s);
+int launch_band_solve(const DevBand& B, const double* linv, cudaStream_t s);
 int launch_backsub_simple(const DevBlock& blk, const DevBand& B, double lambda, double* dl_point, int nl_stride,
                           double* dl_flow, int nf_stride, double* partials, cudaStream_t s);
 int backsub_grid(int n_groups);

@@ -3,16 +3,44 @@
 // Replaces GTSAM's multifrontal Cholesky on the COLAMD ordering ([GTSAM-ext]) for the
 // reduced system that is left after the landmarks are eliminated.  With pose-like variables ordered by frame
 // the system is banded (half-width = the co-visibility window, <= max track age), stored as 32x32 tiles.
-// tcgen05/UMMA has no fp64 path, so the tile kernels are fp64 FMA code; one persistent cooperative kernel
-// walks the tile columns (right-looking), with the forward substitution of g_S folded in as an extra row.
-#include <cooperative_groups.h>
+// tcgen05/UMMA has no fp64 path, so the tile kernels are fp64 FMA code.
+//
+// Factorisation = one persistent DATAFLOW kernel (no grid-wide barriers):
+//   * worker warps take tiles in column-major order and apply, in registers, every left-looking update
+//     T_IK -= L_IJ L_KJ^T as soon as the per-tile "done" flags of the two operand tiles are released;
+//   * one spine warp owns the sequential dependency chain  potrf(K,K) -> trsm(K+1,K) -> update+potrf(K+1,K+1)
+//     and keeps those tiles in registers / shared memory, so the chain never waits on an L2 round trip.
+// Solve = explicit inverses of the diagonal tiles (one warp each, fully parallel) followed by single-CTA
+// forward / backward sweeps in which 31 warps do the off-diagonal tile GEMVs of a column concurrently.
+#include <algorithm>
+#include <cstdlib>
+#include <cstdio>
 #include "internal.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace dynoba {
 
 constexpr int CH_WARPS = 4;
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_flag(const int* f, int lane) {
+  if (lane == 0) {
+    int spins = 0;
+    while (ld_acquire(f) == 0) { if (++spins > 8) __nanosleep(64); }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void set_flag(int* f, int lane) {
+  __threadfence();      // every lane's tile stores are performed at gpu scope before the flag is released
+  __syncwarp();
+  if (lane == 0) st_release(f, 1);
+}
 
 // warp-level Cholesky of a 32x32 tile held one row per lane; returns false when a pivot is not positive
 __device__ __forceinline__ bool warp_potrf(double (&row)[TILE], int lane) {
@@ -20,9 +48,9 @@ __device__ __forceinline__ bool warp_potrf(double (&row)[TILE], int lane) {
 #pragma unroll
   for (int k = 0; k < TILE; k++) {
     const double d = __shfl_sync(0xffffffffu, row[k], k);
-    if (!(d > 0.0)) { ok = false; }
-    const double s = sqrt(d), inv = 1.0/s;
-    const double l = (lane == k) ? s : row[k]*inv;   // column k of L, valid for lane >= k
+    if (!(d > 0.0)) ok = false;
+    const double inv = rsqrt(d);
+    const double l = (lane == k) ? d*inv : row[k]*inv;   // column k of L, valid for lane >= k
     row[k] = l;
 #pragma unroll
     for (int c = k + 1; c < TILE; c++) {
@@ -33,165 +61,490 @@ __device__ __forceinline__ bool warp_potrf(double (&row)[TILE], int lane) {
   return ok;
 }
 
-__global__ void __launch_bounds__(CH_WARPS*32) band_cholesky_kernel(DevBand B, int* __restrict__ fail) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ double sD[TILE2];                 // L_JJ (diagonal tile of the current column)
-  __shared__ double sK[CH_WARPS][TILE2];       // per-warp staging of L_KJ
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x*CH_WARPS + warp, nw = gridDim.x*CH_WARPS;
-  const int NT = B.NT, WB = B.WB;
-  const size_t cs = (size_t)(WB + 1)*TILE2;    // tile-column stride
-
-  if (gw == 0) {   // prologue: factor the first diagonal tile
-    double row[TILE];
-    double* t = B.tiles;
+// acc(row = lane, 32 cols) -= A(row = lane, 32 k) * B^T with B staged in shared memory as sB[k*32 + c] = B[c][k]
+__device__ __forceinline__ void tile_gemm_sub(double (&acc)[TILE], const double (&a)[TILE], const double* sB) {
 #pragma unroll
-    for (int c = 0; c < TILE; c++) row[c] = t[c*TILE + lane];
-    if (!warp_potrf(row, lane) && lane == 0) atomicOr(fail, 2);
+  for (int k = 0; k < TILE; k++) {
 #pragma unroll
-    for (int c = 0; c < TILE; c++) t[c*TILE + lane] = row[c];
+    for (int c = 0; c < TILE; c += 2) {
+      const double2 b = *reinterpret_cast<const double2*>(sB + k*TILE + c);
+      acc[c] -= a[k]*b.x; acc[c + 1] -= a[k]*b.y;
+    }
   }
-  grid.sync();
+}
+// x(row = lane) <- x * L^-T with L staged as sL[k*32 + c] = L[c][k]; sinv[c] = 1 / L[c][c]
+__device__ __forceinline__ void tile_trsm(double (&x)[TILE], const double* sL, const double* sinv) {
+#pragma unroll
+  for (int c = 0; c < TILE; c++) {
+    double s = x[c];
+#pragma unroll
+    for (int k = 0; k < c; k++) s -= x[k]*sL[k*TILE + c];
+    x[c] = s*sinv[c];
+  }
+}
+__device__ __forceinline__ void tile_load(const double* t, double (&r)[TILE], int lane) {
+#pragma unroll
+  for (int c = 0; c < TILE; c++) r[c] = __ldcg(t + c*TILE + lane);
+}
+__device__ __forceinline__ void tile_store(double* t, const double (&r)[TILE], int lane) {
+#pragma unroll
+  for (int c = 0; c < TILE; c++) t[c*TILE + lane] = r[c];
+}
+// stage a tile held one row per lane into shared memory (s[c*32 + row]) + reciprocals of its diagonal
+__device__ __forceinline__ void tile_stage(double* s, const double (&r)[TILE], int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < TILE; c++) s[c*TILE + lane] = r[c];
+  __syncwarp();
+}
 
-  for (int J = 0; J < NT; J++) {
-    double* colJ = B.tiles + (size_t)J*cs;
-    const int nbelow = min(WB, NT - 1 - J);
-    // ---- phase 1: L_IJ = T_IJ L_JJ^-T for the tiles below the diagonal, and y_J = L_JJ^-1 y_J
-    for (int i = threadIdx.x; i < TILE2; i += blockDim.x) sD[i] = colJ[i];
-    __syncthreads();
-    for (int task = gw; task <= nbelow; task += nw) {
-      if (task == nbelow) {   // rhs "row"
-        double x = 0.0;
-        // forward substitution done by the whole warp: lane c finalises y[c] in turn
-        double yv = B.rhs[J*TILE + lane];
+
+// Blocked variant for the spine: 4 panels of 8 columns.  Inside a panel the right-looking updates only touch the
+// panel's columns (<= 7 shuffles per step); the rank-8 update of the trailing columns reads the panel from
+// shared memory (sP[row*8 + j], 4 x LDS.128 per trailing column) instead of 8 shuffles per column.
+__device__ __forceinline__ bool warp_potrf_blocked(double (&row)[TILE], int lane, double* sP) {
+  bool ok = true;
 #pragma unroll
-        for (int c = 0; c < TILE; c++) {
-          const double yc = __shfl_sync(0xffffffffu, yv, c)/sD[c*TILE + c];
-          if (lane == c) x = yc;
-          if (lane > c) yv -= sD[c*TILE + lane]*yc;
+  for (int p = 0; p < 4; p++) {
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+      const int k = 8*p + kk;
+      const double d = __shfl_sync(0xffffffffu, row[k], k);
+      if (!(d > 0.0)) ok = false;
+      const double inv = rsqrt(d);
+      const double l = (lane == k) ? d*inv : row[k]*inv;
+      row[k] = l;
+#pragma unroll
+      for (int c = k + 1; c < 8*p + 8; c++) {
+        const double lc = __shfl_sync(0xffffffffu, l, c);
+        row[c] -= l*lc;
+      }
+    }
+    if (p < 3) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sP + lane*8 + j) = make_double2(row[8*p + j], row[8*p + j + 1]);
+      __syncwarp();
+#pragma unroll
+      for (int c = 8*p + 8; c < TILE; c++) {
+        double acc = row[c];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const double2 b = *reinterpret_cast<const double2*>(sP + c*8 + j);
+          acc -= row[8*p + j]*b.x; acc -= row[8*p + j + 1]*b.y;
         }
-        B.rhs[J*TILE + lane] = x;
+        row[c] = acc;
+      }
+    }
+  }
+  return ok;
+}
+constexpr int LT_STRIDE = 34;   // padded row stride of the row-major copy of L_KK used by the spine TRSM
+// x(row = lane) <- x * L^-T with L staged row-major: sLt[c*LT_STRIDE + k] = L[c][k]; sinv[c] = 1 / L[c][c]
+__device__ __forceinline__ void tile_trsm_rm(double (&x)[TILE], const double* sLt, const double* sinv) {
+#pragma unroll
+  for (int c = 0; c < TILE; c++) {
+    double s = x[c];
+#pragma unroll
+    for (int k = 0; k + 1 < c; k += 2) {
+      const double2 l = *reinterpret_cast<const double2*>(sLt + c*LT_STRIDE + k);
+      s -= x[k]*l.x; s -= x[k + 1]*l.y;
+    }
+    if (c & 1) s -= x[c - 1]*sLt[c*LT_STRIDE + c - 1];
+    x[c] = s*sinv[c];
+  }
+}
+// acc[j] (16 columns c0..c0+15 of row = lane) -= sum_k a[k] * B[c0+j][k], B staged as sB[k*32 + c]
+__device__ __forceinline__ void tile_gemm_sub_half(double (&acc)[16], const double (&a)[TILE], const double* sB, int c0) {
+#pragma unroll
+  for (int k = 0; k < TILE; k++) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const double2 b = *reinterpret_cast<const double2*>(sB + k*TILE + c0 + j);
+      acc[j] -= a[k]*b.x; acc[j + 1] -= a[k]*b.y;
+    }
+  }
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ long long g_spine_dbg[16];
+#define TS(i) do { const long long t_ = clock64(); if (lane == 0) dbgacc[i] += t_ - tlast; tlast = t_; } while (0)
+
+// Tile roles (dd = I - K):
+//   dd == 0, 1 : workers apply the updates from columns J <= K-2 ("pre"), the spine applies J = K-1 and finishes
+//   dd == 2    : workers apply J <= K-1 ("pre"), the spine does the TRSM
+//   dd >= 3    : workers apply J <= K-1 and do the TRSM once done(K,K) is released
+// plus one "rhs" task per column that folds the forward substitution y_K = L_KK^-1 (g_K - sum_J L_KJ y_J) in.
+// flags: done[o], pre[o] for tile o = K*(WB+1) + dd;  ydone[K]
+__global__ void __launch_bounds__(CH_WARPS*32)
+band_cholesky_dataflow_kernel(DevBand B, int* __restrict__ done, int* __restrict__ pre, int* __restrict__ ydone,
+                              int* __restrict__ fail) {
+  extern __shared__ __align__(16) double chol_smem[];   // [CH_WARPS + 1][TILE2] + [CH_WARPS][32] (+ padding that pins CTAs/SM)
+  double* sspine = chol_smem + (size_t)CH_WARPS*TILE2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NT = B.NT, WB = B.WB, W1 = WB + 1;
+  double* sb = chol_smem + (size_t)warp*TILE2;
+  double* sinv = chol_smem + (size_t)(CH_WARPS + 1)*TILE2 + warp*TILE;
+
+  if (blockIdx.x == 0) {
+    // ------------------------------------------------------------------ spine CTA (4 warps, block-wide barriers)
+    //   warp 0: potrf(K,K);  warp 1: TRSM (K+1,K);  warp 2: TRSM (K+2,K);  then all four warps split the two
+    //   tile updates T(K+1,K+1) -= L(K+1,K) L(K+1,K)^T and T(K+2,K+1) -= L(K+2,K) L(K+1,K)^T by column halves.
+    double* sLt  = chol_smem;                       // [32*LT_STRIDE] row-major L_KK
+    double* sX1  = chol_smem + 1152;                // [1024] L(K+1,K), sX1[k*32 + r]
+    double* sX2  = sX1 + TILE2;                     // [1024] L(K+2,K)
+    double* sD   = sX2 + TILE2;                     // [1024] next diagonal tile hand-off
+    double* sXn  = sD + TILE2;                      // [1024] next x1 hand-off
+    double* sP   = sXn + TILE2;                     // [256]  potrf panel
+    double* sIv  = sP + 256;                        // [32]   1 / diag(L_KK)
+    double r[TILE];                                 // warp 0: diagonal tile row; warp 1: x1 row; warp 2: x2 row
+    long long dbgacc[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long tlast = clock64();
+    if (warp == 0) { wait_flag(pre + 0, lane); tile_load(B.tiles, r, lane); }
+    if (warp == 1 && NT > 1) { wait_flag(pre + 1, lane); tile_load(B.tiles + TILE2, r, lane); }
+    for (int K = 0; K < NT; K++) {
+      const size_t oD = (size_t)K*W1;
+      if (warp == 0) {
+        TS(11);
+        if (!warp_potrf_blocked(r, lane, sP) && lane == 0) atomicOr(fail, 2);
+        TS(0);
+        tile_store(B.tiles + oD*TILE2, r, lane);
+#pragma unroll
+        for (int c = 0; c < TILE; c += 2) *reinterpret_cast<double2*>(sLt + lane*LT_STRIDE + c) = make_double2(r[c], r[c + 1]);
+        double dg = 1.0;
+#pragma unroll
+        for (int c = 0; c < TILE; c++) if (lane == c) dg = r[c];
+        sIv[lane] = 1.0/dg;
+        set_flag(done + oD, lane);
+        TS(1);
+      }
+      if (K + 1 >= NT) break;
+      named_bar(1, 128);
+      const bool has2 = (K + 2 < NT) && (WB >= 2), hasn = (K + 2 < NT);
+      double h[16];
+      if (warp == 1) {
+        tile_trsm_rm(r, sLt, sIv);
+        tile_store(B.tiles + (oD + 1)*TILE2, r, lane);
+        tile_stage(sX1, r, lane);
+        set_flag(done + oD + 1, lane);
+      } else if (warp == 2) {
+        if (has2) {
+          wait_flag(pre + oD + 2, lane);
+          tile_load(B.tiles + (oD + 2)*TILE2, r, lane);
+          tile_trsm_rm(r, sLt, sIv);
+          tile_store(B.tiles + (oD + 2)*TILE2, r, lane);
+          tile_stage(sX2, r, lane);
+          set_flag(done + oD + 2, lane);
+        }
       } else {
-        double* t = colJ + (size_t)(task + 1)*TILE2;
-        double x[TILE];
+        TS(2);
+        const int c0 = warp == 0 ? 16 : 0;
+        wait_flag(pre + oD + W1, lane);
+        const double* t = B.tiles + (oD + W1)*TILE2;
 #pragma unroll
-        for (int c = 0; c < TILE; c++) x[c] = t[c*TILE + lane];
+        for (int j = 0; j < 16; j++) h[j] = __ldcg(t + (c0 + j)*TILE + lane);
+        TS(3);
+      }
+      named_bar(2, 128);
+      if (warp == 0) TS(4);
+      if (warp == 0 || warp == 3) {
+        const int c0 = warp == 0 ? 16 : 0;
+        double a[TILE];
 #pragma unroll
-        for (int c = 0; c < TILE; c++) {
-          double s = x[c];
+        for (int k = 0; k < TILE; k++) a[k] = sX1[k*TILE + lane];
+        tile_gemm_sub_half(h, a, sX1, c0);
 #pragma unroll
-          for (int k = 0; k < c; k++) s -= x[k]*sD[k*TILE + c];   // L_JJ[c][k]
-          x[c] = s/sD[c*TILE + c];
+        for (int j = 0; j < 16; j++) sD[(c0 + j)*TILE + lane] = h[j];
+      } else if (hasn) {
+        const int c0 = warp == 1 ? 16 : 0;
+        wait_flag(pre + oD + W1 + 1, lane);
+        const double* t = B.tiles + (oD + W1 + 1)*TILE2;
+#pragma unroll
+        for (int j = 0; j < 16; j++) h[j] = __ldcg(t + (c0 + j)*TILE + lane);
+        if (has2) {
+          double a[TILE];
+#pragma unroll
+          for (int k = 0; k < TILE; k++) a[k] = sX2[k*TILE + lane];
+          tile_gemm_sub_half(h, a, sX1, c0);
         }
 #pragma unroll
-        for (int c = 0; c < TILE; c++) t[c*TILE + lane] = x[c];
+        for (int j = 0; j < 16; j++) sXn[(c0 + j)*TILE + lane] = h[j];
+      }
+      if (warp == 0) TS(5);
+      named_bar(3, 128);
+      if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < TILE; c++) r[c] = sD[c*TILE + lane];
+        TS(6);
+      } else if (warp == 1 && hasn) {
+#pragma unroll
+        for (int c = 0; c < TILE; c++) r[c] = sXn[c*TILE + lane];
       }
     }
-    grid.sync();
-    // ---- phase 2: trailing update T_IK -= L_IJ L_KJ^T (J < K <= I <= J+nbelow), y_K -= L_KJ y_J
-    const int ntile = nbelow*(nbelow + 1)/2;
-    for (int task = gw; task < ntile + nbelow; task += nw) {
-      if (task >= ntile) {   // rhs update for K = J + 1 + (task - ntile)
-        const int kk = task - ntile + 1;
-        const double* lk = colJ + (size_t)kk*TILE2;
-        double s = 0;
-#pragma unroll 8
-        for (int k = 0; k < TILE; k++) s += lk[k*TILE + lane]*B.rhs[J*TILE + k];
-        B.rhs[(J + kk)*TILE + lane] -= s;
-        continue;
+    if (warp == 0 && lane == 0) for (int i = 0; i < 12; i++) g_spine_dbg[i] = dbgacc[i];
+    return;
+  }
+  // -------------------------------------------------------------------- workers
+  const int nworkers = (gridDim.x - 1)*CH_WARPS;
+  const int wid = (blockIdx.x - 1)*CH_WARPS + warp;
+  const int W2 = W1 + 1;                                 // tile tasks + the rhs task of the column
+  const long long ntasks = (long long)NT*W2;
+  for (long long o2 = wid; o2 < ntasks; o2 += nworkers) {
+    const int K = (int)(o2/W2), dd = (int)(o2 - (long long)K*W2), I = K + dd;
+    if (dd == W1) {
+      // ---- rhs task: y_K = L_KK^-1 (g_K - sum_{J<K} L_KJ y_J)
+      double v = B.rhs[(size_t)K*TILE + lane];
+      for (int J = max(0, K - WB); J < K; J++) {
+        const size_t oK = (size_t)J*W1 + (K - J);
+        wait_flag(done + oK, lane);
+        double a[TILE];
+        tile_load(B.tiles + oK*TILE2, a, lane);
+        wait_flag(ydone + J, lane);
+        const double yj = __ldcg(B.rhs + (size_t)J*TILE + lane);
+#pragma unroll
+        for (int k = 0; k < TILE; k++) v -= a[k]*__shfl_sync(0xffffffffu, yj, k);
       }
-      // decode (ii >= kk) in 1..nbelow from the triangular index
-      int ii = (int)((sqrt(8.0*task + 1.0) - 1.0)*0.5);
-      while (ii*(ii + 1)/2 > task) ii--;
-      while ((ii + 1)*(ii + 2)/2 <= task) ii++;
-      const int kk = task - ii*(ii + 1)/2 + 1;
-      ii += 1;
-      const double* li = colJ + (size_t)ii*TILE2;
-      const double* lk = colJ + (size_t)kk*TILE2;
-      double* dst = B.tiles + (size_t)(J + kk)*cs + (size_t)(ii - kk)*TILE2;
-      double* sk = sK[warp];
-      __syncwarp();
+      wait_flag(done + (size_t)K*W1, lane);
+      double l[TILE];
+      tile_load(B.tiles + (size_t)K*W1*TILE2, l, lane);
+      double y = 0.0, mydiag = 1.0;
 #pragma unroll
-      for (int c = 0; c < TILE; c++) sk[c*TILE + lane] = lk[c*TILE + lane];
-      __syncwarp();
-      double a[TILE], acc[TILE];
+      for (int c = 0; c < TILE; c++) if (lane == c) mydiag = l[c];
+      const double rinv = 1.0/mydiag;
 #pragma unroll
-      for (int k = 0; k < TILE; k++) a[k] = li[k*TILE + lane];       // row `lane` of L_IJ
-#pragma unroll
-      for (int c = 0; c < TILE; c++) acc[c] = dst[c*TILE + lane];
-#pragma unroll
-      for (int k = 0; k < TILE; k++) {
-#pragma unroll
-        for (int c = 0; c < TILE; c++) acc[c] -= a[k]*sk[k*TILE + c];  // L_KJ[c][k], broadcast read
+      for (int c = 0; c < TILE; c++) {
+        const double yc = __shfl_sync(0xffffffffu, v, c)*__shfl_sync(0xffffffffu, rinv, c);
+        if (lane == c) y = yc;
+        if (lane > c) v -= l[c]*yc;
       }
-      if (ii == 1 && kk == 1) {   // next diagonal tile is complete: factor it now
-        if (!warp_potrf(acc, lane) && lane == 0) atomicOr(fail, 2);
-      }
-#pragma unroll
-      for (int c = 0; c < TILE; c++) dst[c*TILE + lane] = acc[c];
+      B.rhs[(size_t)K*TILE + lane] = y;
+      set_flag(ydone + K, lane);
+      continue;
     }
-    grid.sync();
+    if (I >= NT) continue;
+    const size_t o = (size_t)K*W1 + dd;
+    double acc[TILE];
+    double* t = B.tiles + o*TILE2;
+    tile_load(t, acc, lane);
+    const int Jlo = max(0, I - WB), Jhi = (dd <= 1) ? K - 2 : K - 1;
+    for (int J = Jlo; J <= Jhi; J++) {
+      const size_t oI = (size_t)J*W1 + (I - J), oK = (size_t)J*W1 + (K - J);
+      wait_flag(done + oK, lane);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < TILE; c++) sb[c*TILE + lane] = __ldcg(B.tiles + oK*TILE2 + c*TILE + lane);
+      wait_flag(done + oI, lane);
+      double a[TILE];
+      tile_load(B.tiles + oI*TILE2, a, lane);
+      __syncwarp();
+      tile_gemm_sub(acc, a, sb);
+    }
+    if (dd <= 2) {
+      tile_store(t, acc, lane);
+      set_flag(pre + o, lane);
+    } else {
+      const size_t oD = (size_t)K*W1;
+      wait_flag(done + oD, lane);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < TILE; c++) sb[c*TILE + lane] = __ldcg(B.tiles + oD*TILE2 + c*TILE + lane);
+      __syncwarp();
+      sinv[lane] = 1.0/sb[lane*TILE + lane];
+      __syncwarp();
+      tile_trsm(acc, sb, sinv);
+      tile_store(t, acc, lane);
+      set_flag(done + o, lane);
+    }
   }
 }
 
-int launch_band_cholesky(const DevBand& B, int* fail, cudaStream_t s) {
-  static int max_blocks = 0;
-  if (!max_blocks) {
+// explicit inverse of every diagonal tile: Linv[K] = L_KK^-1 (lower triangular), one warp per tile
+__global__ void __launch_bounds__(128) diag_inverse_kernel(DevBand B, double* __restrict__ linv) {
+  __shared__ double sL[4][TILE2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = blockIdx.x*4 + warp;
+  if (K >= B.NT) return;
+  const double* t = B.tiles + (size_t)K*(B.WB + 1)*TILE2;
+  double* s = sL[warp];
+#pragma unroll
+  for (int c = 0; c < TILE; c++) s[c*TILE + lane] = t[c*TILE + lane];
+  __syncwarp();
+  // lane j solves L x = e_j  -> column j of L^-1
+  double x[TILE];
+#pragma unroll
+  for (int r = 0; r < TILE; r++) {
+    double v = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < r; k++) v -= s[k*TILE + r]*x[k];      // L[r][k]
+    x[r] = v/s[r*TILE + r];
+  }
+  double* o = linv + (size_t)K*TILE2;
+#pragma unroll
+  for (int r = 0; r < TILE; r++) o[lane*TILE + r] = (r >= lane) ? x[r] : 0.0;   // element (r, j=lane) at j*32 + r
+}
+
+// butterfly: on entry lane r holds v[c] (c = 0..31); on exit every lane c returns sum over r of v_r[c]
+__device__ __forceinline__ double warp_transpose_sum(double (&v)[TILE], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; i++) {
+      const double send = up ? v[i] : v[i + o];
+      const double recv = __shfl_xor_sync(0xffffffffu, send, o);
+      v[i] = (up ? v[i + o] : v[i]) + recv;
+    }
+  }
+  return v[0];
+}
+
+constexpr int SV_WARPS = 16;
+// forward sweep  y_K = Linv_KK (g_K - sum_{J<K} L_KJ y_J); rhs overwritten
+__global__ void __launch_bounds__(SV_WARPS*32) band_forward_kernel(DevBand B, const double* __restrict__ linv) {
+  extern __shared__ double sm[];
+  const int NT = B.NT, WB = B.WB, W1 = WB + 1, ring = WB + 1;
+  double* xs = sm;                      // ring buffer of solved blocks: [ring][32]
+  double* part = sm + (size_t)ring*TILE; // [SV_WARPS][32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int K = 0; K < NT; K++) {
+    const int nleft = min(WB, K);
+    double s = 0.0;
+    // tiles (K, J = K-1-q), q = warp-1, warp-1+31, ...
+    double t[TILE]; int q = warp - 1; bool have = false;
+    if (warp > 0 && q < nleft) {
+      const int J = K - 1 - q;
+      const double* tp = B.tiles + ((size_t)J*W1 + (K - J))*TILE2;
+#pragma unroll
+      for (int k = 0; k < TILE; k++) t[k] = tp[k*TILE + lane];
+      have = true;
+    }
+    __syncthreads();                    // y_{K-1} visible in the ring
+    if (warp > 0) {
+      while (have) {
+        const int J = K - 1 - q;
+        const double* y = xs + (size_t)(J % ring)*TILE;
+#pragma unroll
+        for (int k = 0; k < TILE; k++) s += t[k]*y[k];
+        q += SV_WARPS - 1; have = q < nleft;
+        if (have) {
+          const int J2 = K - 1 - q;
+          const double* tp = B.tiles + ((size_t)J2*W1 + (K - J2))*TILE2;
+#pragma unroll
+          for (int k = 0; k < TILE; k++) t[k] = tp[k*TILE + lane];
+        }
+      }
+      part[warp*TILE + lane] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double v = B.rhs[(size_t)K*TILE + lane];
+      const int nw = min(nleft, SV_WARPS - 1);
+      for (int w = 1; w <= nw; w++) v -= part[w*TILE + lane];
+      const double* li = linv + (size_t)K*TILE2;
+      double y = 0.0;
+#pragma unroll
+      for (int k = 0; k < TILE; k++) y += li[k*TILE + lane]*__shfl_sync(0xffffffffu, v, k);   // Linv[lane][k] v[k]
+      xs[(size_t)(K % ring)*TILE + lane] = y;
+      B.rhs[(size_t)K*TILE + lane] = y;
+    }
+  }
+}
+
+// backward sweep  x_J = Linv_JJ^T (y_J - sum_{I>J} L_IJ^T x_I); rhs overwritten
+__global__ void __launch_bounds__(SV_WARPS*32) band_backward_kernel(DevBand B, const double* __restrict__ linv) {
+  extern __shared__ double sm[];
+  const int NT = B.NT, WB = B.WB, W1 = WB + 1, ring = WB + 1;
+  double* xs = sm; double* part = sm + (size_t)ring*TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int J = NT - 1; J >= 0; J--) {
+    const int nbelow = min(WB, NT - 1 - J);
+    const double* colJ = B.tiles + (size_t)J*W1*TILE2;
+    double t[TILE]; int q = warp - 1; bool have = false;
+    if (warp > 0 && q < nbelow) {
+      const double* tp = colJ + (size_t)(q + 1)*TILE2;
+#pragma unroll
+      for (int c = 0; c < TILE; c++) t[c] = tp[c*TILE + lane];     // row `lane` of L_IJ
+      have = true;
+    }
+    __syncthreads();
+    if (warp > 0) {
+      double s = 0.0;
+      while (have) {
+        const int I = J + 1 + q;
+        const double xr = xs[(size_t)(I % ring)*TILE + lane];
+#pragma unroll
+        for (int c = 0; c < TILE; c++) t[c] *= xr;
+        s += warp_transpose_sum(t, lane);                           // lane c: sum_r L[r][c] x[r]
+        q += SV_WARPS - 1; have = q < nbelow;
+        if (have) {
+          const double* tp = colJ + (size_t)(q + 1)*TILE2;
+#pragma unroll
+          for (int c = 0; c < TILE; c++) t[c] = tp[c*TILE + lane];
+        }
+      }
+      part[warp*TILE + lane] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double v = B.rhs[(size_t)J*TILE + lane];
+      const int nw = min(nbelow, SV_WARPS - 1);
+      for (int w = 1; w <= nw; w++) v -= part[w*TILE + lane];
+      const double* li = linv + (size_t)J*TILE2;
+      double p[TILE];
+#pragma unroll
+      for (int c = 0; c < TILE; c++) p[c] = li[c*TILE + lane]*v;    // Linv[lane][c] * v[lane]
+      const double x = warp_transpose_sum(p, lane);                  // lane c: sum_r Linv[r][c] v[r]
+      xs[(size_t)(J % ring)*TILE + lane] = x;
+      B.rhs[(size_t)J*TILE + lane] = x;
+    }
+  }
+}
+
+static int g_max_blocks = 0;
+static size_t g_chol_smem = 0;
+
+int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, cudaStream_t s) {
+  if (!g_max_blocks) {
     int dev = 0, sms = 0, per = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, band_cholesky_kernel, CH_WARPS*32, 0);
-    max_blocks = sms*(per > 0 ? per : 1);
+    // CTAs per SM: 1 keeps the spine warp alone on its scheduler (DYNOBA_CHOL_BPS overrides for experiments)
+    int bps = 1; if (const char* e = getenv("DYNOBA_CHOL_BPS")) bps = atoi(e) > 0 ? atoi(e) : 1;
+    const size_t need = (size_t)(1152 + 4*TILE2 + 256 + 64)*sizeof(double);
+    g_chol_smem = std::max(need, (size_t)(220*1024)/bps - 2048);
+    cudaFuncSetAttribute(band_cholesky_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_chol_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, band_cholesky_dataflow_kernel, CH_WARPS*32, g_chol_smem);
+    g_max_blocks = sms*(per > 0 ? per : 1);
   }
-  const int ntask = B.WB*(B.WB + 1)/2 + B.WB + 1;
-  int grid = (ntask + CH_WARPS - 1)/CH_WARPS;
-  if (grid > max_blocks) grid = max_blocks;
-  if (grid < 1) grid = 1;
-  DevBand Bc = B;
-  void* args[] = { (void*)&Bc, (void*)&fail };
-  cudaLaunchCooperativeKernel((void*)band_cholesky_kernel, dim3(grid), dim3(CH_WARPS*32), args, 0, s);
-  return 1;
+  const size_t nflags = (size_t)B.NT*(B.WB + 1);
+  cudaMemsetAsync(flags, 0, (2*nflags + B.NT)*sizeof(int), s);
+  int grid = g_max_blocks;
+  const long long want = ((long long)nflags + B.NT + 1 + CH_WARPS - 1)/CH_WARPS + 1;
+  if (grid > want) grid = (int)want;
+  if (grid < 2) grid = 2;
+  DevBand Bc = B; int* done = flags; int* pre = flags + nflags; int* ydone = flags + 2*nflags;
+  void* args[] = { (void*)&Bc, (void*)&done, (void*)&pre, (void*)&ydone, (void*)&fail };
+  // cooperative launch only for its co-residency guarantee (the flag waits need every warp resident)
+  cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel, dim3(grid), dim3(CH_WARPS*32), args, g_chol_smem, s);
+  diag_inverse_kernel<<<(B.NT + 3)/4, 128, 0, s>>>(B, linv);
+  if (getenv("DYNOBA_SPINE_DBG")) {
+    long long hd[16]; cudaStreamSynchronize(s); cudaMemcpyFromSymbol(hd, g_spine_dbg, sizeof(hd));
+    const char* nm[12] = {"potrf", "store+stage+flag D", "barA", "wait+load Dnext half", "barB (trsm)", "gemm half + stage", "barC + reload", "-", "-", "-", "-", "loop"};
+    for (int i = 0; i < 12; i++) fprintf(stderr, "[spine] %-22s %10.3f ms  (%.0f cyc/col)\n", nm[i], hd[i]/1.965e6, (double)hd[i]/B.NT);
+  }
+  return 3;
 }
 
-// ---- backward substitution  L^T x = y  (single CTA; x overwrites rhs)
-constexpr int BS_WARPS = 16;
-__global__ void __launch_bounds__(BS_WARPS*32) band_backsolve_kernel(DevBand B) {
-  __shared__ double part[BS_WARPS][TILE];
-  __shared__ double sD[TILE2];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NT = B.NT, WB = B.WB;
-  const size_t cs = (size_t)(WB + 1)*TILE2;
-  for (int J = NT - 1; J >= 0; J--) {
-    const double* colJ = B.tiles + (size_t)J*cs;
-    const int nbelow = min(WB, NT - 1 - J);
-    double s = 0;
-    for (int ii = 1 + warp; ii <= nbelow; ii += BS_WARPS) {
-      const double* t = colJ + (size_t)ii*TILE2 + (size_t)lane*TILE;   // column `lane` of L_IJ
-      const double* x = B.rhs + (size_t)(J + ii)*TILE;
-#pragma unroll 8
-      for (int r = 0; r < TILE; r++) s += t[r]*x[r];
-    }
-    part[warp][lane] = s;
-    for (int i = threadIdx.x; i < TILE2; i += blockDim.x) sD[i] = colJ[i];
-    __syncthreads();
-    if (warp == 0) {
-      double acc = B.rhs[J*TILE + lane];
-#pragma unroll
-      for (int w = 0; w < BS_WARPS; w++) acc -= part[w][lane];
-      double x = 0;
-#pragma unroll
-      for (int c = TILE - 1; c >= 0; c--) {
-        const double xc = __shfl_sync(0xffffffffu, acc, c)/sD[c*TILE + c];
-        if (lane == c) x = xc;
-        if (lane < c) acc -= sD[lane*TILE + c]*xc;     // L_JJ[c][lane]
-      }
-      B.rhs[J*TILE + lane] = x;
-    }
-    __syncthreads();
+int launch_band_solve(const DevBand& B, const double* linv, cudaStream_t s) {
+  const size_t smem = ((size_t)(B.WB + 1)*TILE + (size_t)SV_WARPS*TILE)*sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(band_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
+    cudaFuncSetAttribute(band_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
+    attr = true;
   }
-}
-int launch_band_backsolve(const DevBand& B, cudaStream_t s) {
-  band_backsolve_kernel<<<1, BS_WARPS*32, 0, s>>>(B);
+  band_backward_kernel<<<1, SV_WARPS*32, smem, s>>>(B, linv);   // the forward sweep is folded into the factorisation
   return 1;
 }
 
