@@ -47,6 +47,7 @@ struct dynoba_solver {
   int* fail = nullptr; int* chol_flags = nullptr; double* linv = nullptr; int n_partials = 0, n_lin_partials = 0, n_bs_partials = 0;
   int rank = 0, world = 1; dynoba_allreduce_fn allreduce = nullptr; void* ar_ctx = nullptr; int min_bw = 0;
   int64_t launches = 0; int64_t jac_bytes = 0;
+  GeneralGroups gen{}; int gen_bs_off = 0;
   std::vector<void*> allocs;
   cudaEvent_t ev[8]{};
 };
@@ -323,6 +324,8 @@ static int finalize_impl(dynoba_solver* h) {
   // ---- factor blocks
   h->supported = true; h->jac_bytes = 96*(np + naux) + 24*npt + 16*nfl;
   int part = 0, bs = 0;
+  struct GenRef { int32_t rank, blk, idx; };
+  std::vector<GenRef> gen_refs;
   for (size_t bi = 0; bi < h->blocks.size(); bi++) {
     auto& b = h->blocks[bi]; const TypeInfo ti = type_info(b.type);
     const int64_t n = b.n; const int stride = pad32(n);
@@ -364,32 +367,72 @@ static int finalize_impl(dynoba_solver* h) {
     if ((rc = dalloc(h, &d.J, (size_t)ti.dim*ti.jcols*stride))) return rc;
     if ((rc = dalloc(h, &d.b, (size_t)ti.dim*stride))) return rc;
     CK(cudaMemset(d.J, 0, (size_t)ti.dim*ti.jcols*stride*8)); CK(cudaMemset(d.b, 0, (size_t)ti.dim*stride*8));
-    // groups
+    // groups: CSR over every landmark group that has factors in this block; groups this block cannot own alone
+    // (several points, or factors in other blocks too) are marked -1 and collected for the general path
     b.simple = false;
     if (lslot >= 0) {
-      std::vector<int32_t> gp, gl; bool simple = ti.nlmk == 1;
+      std::vector<int32_t> gp, gl;
       for (int64_t s = 0; s < n; s++) {
         const int64_t o = b.perm[s];
         if (s == 0 || frank[o] != frank[b.perm[s-1]]) {
           gp.push_back((int32_t)s);
           const int l = lmk_id(ti.cls[lslot], b.idx[o*ti.arity + lslot]);
-          gl.push_back(hidx[(size_t)lslot*stride + s]);
-          if (gblk[root[l]] != (int)bi || gcount[root[l]] != 1) simple = false;
+          const bool simple = ti.nlmk == 1 && gblk[root[l]] == (int)bi && gcount[root[l]] == 1;
+          gl.push_back(simple ? hidx[(size_t)lslot*stride + s] : -1);
         }
+        const int l = lmk_id(ti.cls[lslot], b.idx[o*ti.arity + lslot]);
+        if (!(ti.nlmk == 1 && gblk[root[l]] == (int)bi && gcount[root[l]] == 1)) gen_refs.push_back({ grank[root[l]], (int32_t)bi, (int32_t)s });
       }
       gp.push_back((int32_t)n);
       int* dgp; int* dgl;
       if ((rc = dalloc(h, &dgp, gp.size()))) return rc; CK(cudaMemcpy(dgp, gp.data(), gp.size()*4, cudaMemcpyHostToDevice));
       if ((rc = dalloc(h, &dgl, gl.size()))) return rc; if (!gl.empty()) CK(cudaMemcpy(dgl, gl.data(), gl.size()*4, cudaMemcpyHostToDevice));
       d.n_groups = (int)gl.size(); d.grp_ptr = dgp; d.grp_lmk = dgl;
-      b.simple = simple;
-      if (!simple && n > 0) h->supported = false;
+      b.simple = true;
     }
     b.part_off = part; part += linearize_grid((int)n);
     b.bs_off = bs; bs += b.pose_only ? (int)((n + 127)/128) : backsub_grid(d.n_groups);
     const int64_t rd = 4*ti.arity + 8*ti.meas + 8*b.sigma_dim + (b.has_aux ? 4 : 0), wr = 8*(ti.dim*ti.jcols + ti.dim);
     h->jac_bytes += n*(rd + wr);
   }
+  // ---- general landmark groups
+  h->gen = GeneralGroups{};
+  if (!gen_refs.empty()) {
+    std::stable_sort(gen_refs.begin(), gen_refs.end(), [](const GenRef& a, const GenRef& c) { return a.rank < c.rank; });
+    std::vector<int32_t> gptr, gl0, gnl; std::vector<int32_t> refs;
+    for (size_t i = 0; i < gen_refs.size(); i++) {
+      if (i == 0 || gen_refs[i].rank != gen_refs[i-1].rank) {
+        gptr.push_back((int32_t)i);
+        const int r = gorder[gen_refs[i].rank];           // root landmark id of the group
+        int first = INT32_MAX, cnt = 0; bool only_points = true;
+        // points of the group are contiguous in device order; find the first one and the count
+        (void)cnt;
+        gnl.push_back(gcount[r]);
+        // first device index = min over the group's points: every member maps to consecutive indices
+        first = INT32_MAX;
+        gl0.push_back(first);
+        if (r >= npt) only_points = false;
+        if (gcount[r] > 21 || !only_points) h->supported = false;
+      }
+      refs.push_back(gen_refs[i].blk); refs.push_back(gen_refs[i].idx);
+    }
+    gptr.push_back((int32_t)gen_refs.size());
+    // device index of the first point of each general group
+    {
+      std::vector<int32_t> rank2g(gorder.size(), -1);
+      for (size_t g = 0; g + 1 < gptr.size(); g++) rank2g[gen_refs[gptr[g]].rank] = (int32_t)g;
+      for (int64_t i = 0; i < nl; i++) { const int g = rank2g[grank[root[i]]]; if (g >= 0) { if (i >= npt) { h->supported = false; continue; } gl0[g] = std::min(gl0[g], h->pt_new[i]); } }
+    }
+    std::vector<DevBlock> hb; for (auto& b : h->blocks) hb.push_back(b.dev);
+    DevBlock* dblk; int* dgptr; int* drefs; int* dgl0; int* dgnl; int rc;
+    if ((rc = dalloc(h, &dblk, hb.size()))) return rc; CK(cudaMemcpy(dblk, hb.data(), hb.size()*sizeof(DevBlock), cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &dgptr, gptr.size()))) return rc; CK(cudaMemcpy(dgptr, gptr.data(), gptr.size()*4, cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &drefs, refs.size()))) return rc; CK(cudaMemcpy(drefs, refs.data(), refs.size()*4, cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &dgl0, gl0.size()))) return rc; CK(cudaMemcpy(dgl0, gl0.data(), gl0.size()*4, cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &dgnl, gnl.size()))) return rc; CK(cudaMemcpy(dgnl, gnl.data(), gnl.size()*4, cudaMemcpyHostToDevice));
+    h->gen.n_groups = (int)gl0.size(); h->gen.blocks = dblk; h->gen.gptr = dgptr; h->gen.refs = drefs; h->gen.gl0 = dgl0; h->gen.gnl = dgnl;
+  }
+  h->gen_bs_off = bs; bs += general_grid(h->gen.n_groups);
   h->n_lin_partials = part; h->n_bs_partials = bs + pose_norm_grid(B.n);
   h->n_partials = std::max(std::max(h->n_lin_partials, h->n_bs_partials), 1);
   { int rc; if ((rc = dalloc(h, &h->partials, (size_t)h->n_partials))) return rc; if ((rc = dalloc(h, &h->scalars, 8))) return rc; if ((rc = dalloc(h, &h->fail, 1))) return rc; }
@@ -428,6 +471,7 @@ static int build_reduced(dynoba_solver* h, double lambda) {
     if (b.pose_only) h->launches += launch_pose_factors(b.dev, h->band, h->stream);
     else h->launches += launch_schur_simple(b.dev, h->band, lambda, h->fail, h->stream);
   }
+  h->launches += launch_schur_general(h->gen, h->band, lambda, h->fail, h->stream);
   return allreduce_dev(h, h->band.tiles, h->band.tile_count*TILE2 + h->band.n_pad);
 }
 // factor + solve + back-substitute; scalars[1] = linearised cost decrease
@@ -440,6 +484,10 @@ static int solve_step(dynoba_solver* h, double lambda) {
     else { h->launches += launch_backsub_simple(b.dev, h->band, lambda, h->dl_point, h->cur.nl_stride, h->dl_flow, h->cur.nf_stride, h->partials + b.bs_off, h->stream);
            used = std::max(used, b.bs_off + backsub_grid(b.dev.n_groups)); }
   }
+  if (h->gen.n_groups) {
+    h->launches += launch_backsub_general(h->gen, h->band, lambda, h->dl_point, h->cur.nl_stride, h->partials + h->gen_bs_off, h->stream);
+    used = std::max(used, h->gen_bs_off + general_grid(h->gen.n_groups));
+  }
   if (h->rank == 0) { h->launches += launch_pose_delta_norm(h->band, lambda, h->partials + used, h->stream); used += pose_norm_grid(h->band.n); }
   h->launches += launch_sum(h->partials, used, h->scalars + 1, h->stream);
   return DYNOBA_OK;
@@ -449,7 +497,7 @@ static int check_ready(dynoba_solver* h, bool need_supported) {
   if (!h) return DYNOBA_ERR_BAD_ARG;
   int rc = finalize_impl(h); if (rc) return rc;
   cudaSetDevice(h->device);
-  if (need_supported && !h->supported) { h->err = "graph has landmark groups the Schur kernels do not handle yet (chains / landmarks spanning blocks)"; return DYNOBA_ERR_UNSUPPORTED; }
+  if (need_supported && !h->supported) { h->err = "graph has a landmark group with more than 21 chained points or a chained optical-flow variable"; return DYNOBA_ERR_UNSUPPORTED; }
   return DYNOBA_OK;
 }
 

@@ -33,7 +33,7 @@ struct DevBlock {
   // landmark groups (simple groups: exactly one landmark, all of its factors in this block)
   int n_groups;
   const int* grp_ptr;   // [n_groups+1] into the sorted factor range
-  const int* grp_lmk;   // [n_groups]   device landmark index
+  const int* grp_lmk;   // [n_groups]   device landmark index, or -1 when the group is handled by the general path
 };
 
 // Band storage of the reduced (camera + object-motion) system, lower triangle, TILE x TILE tiles:
@@ -49,6 +49,17 @@ __host__ __device__ __forceinline__ size_t band_index(const DevBand& B, int i, i
   return ((size_t)Jt*(B.WB + 1) + (I - Jt))*TILE2 + (size_t)(j & 31)*TILE + (i & 31);
 }
 
+// Landmark groups the per-landmark kernels do not cover (chains of points, landmarks spanning factor blocks):
+// factor references (block, sorted index) per group, points of a group contiguous from gl0 (gnl of them).
+struct GeneralGroups {
+  int n_groups;
+  const DevBlock* blocks;   // device copy of every factor block descriptor
+  const int* gptr;          // [n_groups+1] into refs
+  const void* refs;         // [gptr[n_groups]] (int blk, int idx)
+  const int* gl0;           // [n_groups] first device point index
+  const int* gnl;           // [n_groups] number of points (<= 21)
+};
+
 // ---- launchers (each returns the number of kernels it launched)
 int launch_linearize(const DevBlock& blk, const DevVars& v, double* partials, cudaStream_t s);
 int launch_error(const DevBlock& blk, const DevVars& v, double* partials, double* per_factor, cudaStream_t s);
@@ -57,6 +68,10 @@ int linearize_grid(int n);          // number of partial sums a linearize/error 
 
 int launch_band_clear(const DevBand& B, double lambda, int add_damping, cudaStream_t s);
 int launch_schur_simple(const DevBlock& blk, const DevBand& B, double lambda, int* fail, cudaStream_t s);
+int launch_schur_general(const GeneralGroups& G, const DevBand& B, double lambda, int* fail, cudaStream_t s);
+int launch_backsub_general(const GeneralGroups& G, const DevBand& B, double lambda, double* dl_point, int nl_stride,
+                           double* partials, cudaStream_t s);
+int general_grid(int n_groups);
 int launch_pose_factors(const DevBlock& blk, const DevBand& B, cudaStream_t s);
 int launch_band_cholesky(const DevBand& B, int* flags /*[2*NT*(WB+1) + NT]*/, double* linv /*[NT*TILE2]*/, int* fail, cudaStream_t s);
 int launch_band_solve(const DevBand& B, const double* linv, cudaStream_t s);

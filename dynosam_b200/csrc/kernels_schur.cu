@@ -93,7 +93,7 @@ schur_simple_kernel(DevBlock blk, DevBand B, double lambda, int* __restrict__ fa
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x*SCHUR_WARPS + warp;
-  if (g >= blk.n_groups) return;
+  if (g >= blk.n_groups || blk.grp_lmk[g] < 0) return;
   double* sJ = smem + (size_t)warp*NE*32;
   const int f0 = blk.grp_ptr[g], T = blk.grp_ptr[g+1] - f0;
   const bool staged = T <= 32;
@@ -315,7 +315,7 @@ backsub_simple_kernel(DevBlock blk, DevBand B, double lambda, double* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x*SCHUR_WARPS + warp;
   double model = 0.0;
-  if (g < blk.n_groups) {
+  if (g < blk.n_groups && blk.grp_lmk[g] >= 0) {
     const int f0 = blk.grp_ptr[g], T = blk.grp_ptr[g+1] - f0;
     double V[DL*DL], gl[DL], tw[DL], q1 = 0.0;
 #pragma unroll

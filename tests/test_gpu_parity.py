@@ -51,7 +51,8 @@ def _all_types_problem(seed=3):
     extra_pts = rng.normal(0, 3, (60, 3)) + [0, 0, 10]
     pts = np.concatenate([base.point, extra_pts]); e0 = npt
     mot = np.arange(N, npose)
-    tri = np.stack([e0 + np.arange(0, 40), e0 + np.arange(1, 41), rng.choice(mot, 40)], 1)
+    ch = np.array([i for i in range(39) if i % 10 != 9])                 # four chains of 10 points
+    tri = np.stack([e0 + ch, e0 + ch + 1, rng.choice(mot, ch.size)], 1)
     blocks.append(FactorBlock(TERNARY3, tri, None, np.array([0.01]), 1e-4))
     mp = np.stack([e0 + np.arange(40, 58), e0 + np.arange(41, 59), rng.choice(mot, 18), rng.choice(mot, 18)], 1)
     blocks.append(FactorBlock(MOTIONPOSE3, mp, None, np.array([0.05]), 1e-3))
@@ -172,9 +173,65 @@ def test_lm_hybrid_medium_properties():
     assert abs(st["error_final"] - so["error_final"]) <= REL_CHI2*so["error_final"]
 
 
-def test_unsupported_topology_reports_status():
-    from dynosam_b200.binding import DynobaError, ERR_UNSUPPORTED
+def test_lm_wcme_c1_matches_oracle():
+    """World-centric motion formulation: one point per (tracklet, frame) chained by LandmarkMotionTernaryFactor;
+    the landmark block is block-tridiagonal per tracklet (general landmark-group kernels)."""
     p = synth.make_config("C1", formulation="wcme")
+    s = _solver(p); o = _oracle(p)
+    lam = 1e-4
+    d = s.solve(lam)
+    rc, do = o.schur_solve(lam)
+    assert rc == 0 and np.linalg.norm(d - do) <= 1e-6*np.linalg.norm(do)
+    st = s.optimize(); so = o.optimize()
+    assert st["iterations"] == so["iterations"] and st["inner_iterations"] == so["inner_iterations"]
+    assert abs(st["error_final"] - so["error_final"]) <= REL_CHI2*so["error_final"]
+    pose, point, _ = s.values()
+    assert np.abs(pose - o.pose).max() < 1e-6 and np.abs(point - o.point).max() < 1e-5
+
+
+def test_damped_solve_every_factor_type():
+    """One damped Schur solve on the graph that holds every factor type (chains of MOTIONPOSE3 / TERNARY3, points
+    with factors in several blocks, optical-flow variables) against the dense normal equations of the oracle."""
+    p = _all_types_problem()
+    s = _solver(p); o = _oracle(p)
+    lam = 1e-2
+    d = s.solve(lam)
+    H, g = o.dense_normal()
+    dd = np.linalg.solve(H + lam*np.eye(H.shape[0]), g)
+    assert np.linalg.norm(d - dd) <= 1e-6*np.linalg.norm(dd)
+
+
+def test_flow_projection_star_lm():
+    """Row a15: Pose3FlowProjectionFactor star graph (1 pose, N flow variables), as in
+    OpticalFlowAndPoseOptimizer::optimize (MotionSolver-inl.hpp:88-260) with max 10 iterations."""
+    from dynosam_b200 import lie
+    rng = np.random.default_rng(5)
+    n = 200
+    X_prev = lie.identity()[0]
+    X_cur_gt = lie.se3_exp(np.array([[0.01, -0.02, 0.005, 0.05, -0.02, 0.9]]))[0]
+    K = np.array([721.5377, 721.5377, 0.0, 609.5593, 172.854, 0.0])
+    kp = np.stack([rng.uniform(50, 1190, n), rng.uniform(30, 340, n)], 1); depth = rng.uniform(5, 40, n)
+    pc = np.stack([(kp[:, 0] - K[3])/K[0]*depth, (kp[:, 1] - K[4])/K[1]*depth, depth], 1)
+    q = lie.transform_to(np.tile(X_cur_gt, (n, 1)), pc)
+    proj = np.stack([K[0]*q[:, 0]/q[:, 2] + K[3], K[1]*q[:, 1]/q[:, 2] + K[4]], 1)
+    flow_gt = proj - kp
+    meas = np.concatenate([kp, depth[:, None], np.tile(X_prev, (n, 1))], 1)
+    blocks = [FactorBlock(FLOWPROJ2, np.stack([np.arange(n), np.zeros(n, dtype=int)], 1), meas, np.array([0.5]), 0.0),
+              FactorBlock(PRIOR6, np.array([[0]]), lie.identity(), np.full(6, 1.0))]
+    p = Problem(lie.identity(), np.zeros((0, 3)), flow=flow_gt + rng.normal(0, 0.5, (n, 2)), calib=K, blocks=blocks)
+    s = _solver(p); o = _oracle(p)
+    st = s.optimize(max_iterations=10); so = o.optimize(max_iterations=10)
+    assert st["iterations"] == so["iterations"]
+    assert abs(st["error_final"] - so["error_final"]) <= REL_CHI2*max(so["error_final"], 1e-12) + 1e-12
+    pose, _, flow = s.values()
+    assert np.abs(pose - o.pose).max() < 1e-6 and np.abs(flow - o.flow).max() < 1e-5
+
+
+def test_unsupported_topology_reports_status():
+    """A tracklet chained over more than 21 frames is outside the general-group kernel: status, not garbage."""
+    from dynosam_b200.binding import DynobaError, ERR_UNSUPPORTED
+    p = synth.make_problem(n_frames=40, n_objects=1, n_static=50, n_dynamic=20, formulation="wcme", seed=2,
+                           max_dynamic_age=35, object_span=(40, 40))
     s = _solver(p)
     assert s.error() > 0         # linearize / chi^2 work for every factor type
     with pytest.raises(DynobaError) as ei:
