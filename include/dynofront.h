@@ -1,0 +1,73 @@
+/*
+ * dynofront.h -- C ABI of libdynofront: the front-end half of the DynOSAM hot path on sm_100a
+ * (SURVEY.md section 8 rows a13 "dense-flow warp / label correlate" and a14 "pyramidal KLT").
+ *
+ * Replaces, with the same inputs / outputs and the same ordering semantics:
+ *   dynofront_track_dynamic     FeatureTracker::trackDynamic        dynosam/src/frontend/vision/FeatureTracker.cc:339-498
+ *   dynofront_sample_candidates FeatureTracker::sampleDynamic scan  FeatureTracker.cc:864-953
+ *   dynofront_propagate_mask    FeatureTracker::propogateMask       FeatureTracker.cc:1212-1359
+ *   dynofront_klt_track         cv::calcOpticalFlowPyrLK as called by KltFeatureTracker::trackPoints
+ *                               (StaticFeatureTracker.cc:420-625) and FeatureTracker::trackDynamicKLT (FeatureTracker.cc:500-862)
+ * Images are row-major, tightly packed: flow float32[H][W][2] (CV_32FC2), masks int32[H][W] (CV_32S, ObjectId),
+ * detection / tracking masks uint8[H][W], gray uint8[H][W]  (reference image types: dynosam README.md:199-202).
+ * Plain C types only; 0 = ok, < 0 = error (same codes as dynoba.h).  No CPU fallback.
+ */
+#ifndef DYNOFRONT_H
+#define DYNOFRONT_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dynofront_ctx* dynofront_handle;
+
+typedef struct {
+  int32_t max_dynamic_feature_age;   /* params/FrontendParams.yaml:66 (20) */
+  int32_t min_distance;              /* min_distance_btw_tracked_and_detected_dynamic_features (2) */
+  int32_t shrink_row, shrink_col;    /* isWithinShrunkenImage margins (0) */
+} dynofront_track_params;
+
+int dynofront_create(int device, int width, int height, dynofront_handle* out);
+int dynofront_destroy(dynofront_handle h);
+const char* dynofront_last_error(dynofront_handle h);
+
+/* Upload the current frame's dense inputs (any pointer may be NULL to keep the previous upload). */
+int dynofront_set_frame(dynofront_handle h, const float* flow, const int32_t* motion_mask, const uint8_t* detection_mask);
+
+/* trackDynamic: n previous dynamic features (predicted key-point at this frame, object label, age, tracklet id),
+ * iterated in array order.  Outputs are per input feature (rows of rejected features are zero); new tracklet ids
+ * are handed out in iteration order starting at *next_tracklet_id, which is updated.  detection_mask_out /
+ * tracking_mask_out (may be NULL) receive the masks after the cv::circle side effects. */
+int dynofront_track_dynamic(dynofront_handle h, int32_t n, const double* prev_pred_kp, const int32_t* prev_label,
+                            const int32_t* prev_age, const int64_t* prev_tracklet, const dynofront_track_params* prm,
+                            int64_t* next_tracklet_id, uint8_t* accepted, double* pred_kp, double* flow_out,
+                            int32_t* age, int64_t* tracklet, int32_t* label, uint8_t* detection_mask_out,
+                            uint8_t* tracking_mask_out);
+
+/* sampleDynamic candidate scan over the whole image, using the detection mask left on the device by
+ * dynofront_track_dynamic (or the uploaded one).  For each of the n_objects labels: counts[o] candidates whose
+ * linear pixel indices (row*W + col, ascending) are written to indices + offsets[o]; zero_flow[o] = pixels of the
+ * object skipped because a flow component is exactly 0.  capacity = size of indices. */
+int dynofront_sample_candidates(dynofront_handle h, int32_t n_objects, const int32_t* objects, const dynofront_track_params* prm,
+                                int32_t* counts, int32_t* offsets, int32_t* zero_flow, int32_t* indices, int64_t capacity);
+
+/* propogateMask: previous-frame features (predicted key-point, label), previous mask / flow, current mask (in/out). */
+int dynofront_propagate_mask(dynofront_handle h, int32_t n, const double* prev_pred_kp, const int32_t* prev_label,
+                             const int32_t* prev_mask, const float* prev_flow, const dynofront_track_params* prm,
+                             int32_t min_votes, int32_t* current_mask);
+
+/* Pyramidal Lucas-Kanade, OpenCV semantics (fixed-point bilinear weights, int16 Scharr derivatives).
+ * next_pts is in/out when use_initial_flow != 0.  err may be NULL. */
+int dynofront_klt_track(dynofront_handle h, const uint8_t* prev_gray, const uint8_t* cur_gray, int32_t n,
+                        const float* prev_pts, float* next_pts, uint8_t* status, float* err, int32_t win,
+                        int32_t max_level, int32_t max_count, double epsilon, int32_t use_initial_flow,
+                        double min_eig_threshold, float* ms_device);
+/* parity hooks: pyramid level / Scharr derivative of the last prev image (level l): sizes via w,h out */
+int dynofront_get_pyramid_level(dynofront_handle h, int32_t which /*0 prev,1 cur*/, int32_t level, int32_t* w, int32_t* hgt,
+                                uint8_t* img, int16_t* deriv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,191 @@
+"""Front-end rows a13 (dense-flow track / sample scan / mask propagation) and a14 (pyramidal KLT).
+
+Bar (north_star): bit-exact on track / association indices (accept flags, ages, tracklet ids, labels, masks, candidate
+index sets, KLT status flags); KLT sub-pixel positions within 1e-2 px of cv2 (OpenCV accumulates the 21x21 sums in
+float with a SIMD lane order we do not replicate; our sums are exact integers).
+"""
+import numpy as np
+import pytest
+
+from dynosam_b200.synth_frames import SyntheticStream
+
+W, H = 1242, 375
+
+
+def _features_from_mask(rng, mask, flow, per_object=200, jitter=True):
+    """Previous-frame dynamic features: sampled on the objects of frame k-1, predicted key-point = kp + flow."""
+    kps, labs = [], []
+    for lab in np.unique(mask):
+        if lab == 0:
+            continue
+        ys, xs = np.nonzero(mask == lab)
+        sel = rng.choice(len(ys), size=min(per_object, len(ys)), replace=False)
+        for y, x in zip(ys[sel], xs[sel]):
+            kx = x + (rng.uniform(0, 0.9) if jitter else 0.0); ky = y + (rng.uniform(0, 0.9) if jitter else 0.0)
+            kps.append((kx + flow[y, x, 0], ky + flow[y, x, 1])); labs.append(lab)
+    kps = np.array(kps); labs = np.array(labs, dtype=np.int32)
+    keep = (kps[:, 0] > 1) & (kps[:, 0] < W - 1) & (kps[:, 1] > 1) & (kps[:, 1] < H - 1)
+    return kps[keep], labs[keep]
+
+
+def test_filled_circle_stencil_matches_opencv():
+    """The per-row half widths the kernels use reproduce cv::circle(..., FILLED) for every radius we accept."""
+    import cv2
+    for r in range(0, 16):
+        # same midpoint recurrence as frontend.cu::make_disc
+        hw = [-1]*16
+        err, dx, dy, plus, minus = 0, r, 0, 1, (r << 1) - 1
+        while dx >= dy:
+            hw[dy] = max(hw[dy], dx); hw[dx] = max(hw[dx], dy)
+            dy += 1; err += plus; plus += 2
+            m = -1 if err > 0 else 0
+            err -= minus & m; dx += m; minus -= m & 2
+        img = np.zeros((41, 41), np.uint8); cv2.circle(img, (20, 20), r, 255, cv2.FILLED)
+        ref = np.zeros_like(img)
+        for ddy in range(-r, r + 1):
+            w = hw[abs(ddy)]
+            ref[20 + ddy, 20 - w:20 + w + 1] = 255
+        assert np.array_equal(img, ref), r
+
+
+def test_frontend_oracle_sequential_semantics():
+    """Oracle self-checks: suppression by earlier accepted features and tracklet renewal order."""
+    from oracle import frontend_oracle as FO
+    mask = np.zeros((40, 60), np.int32); mask[5:35, 5:55] = 3
+    flow = np.zeros((40, 60, 2), np.float32); flow[..., 0] = 1.5; flow[..., 1] = 0.5
+    kp = np.array([[10.2, 10.1], [11.0, 10.9], [20.5, 20.5], [30.0, 12.0]])
+    acc, pk, fl, age, tid, lab, nid, det, trk = FO.track_dynamic(kp, [3, 3, 3, 3], [1, 2, 20, 5], [100, 101, 102, 103], flow, mask, None,
+                                                                 FO.TrackParams(), 500)
+    assert list(acc) == [1, 0, 1, 1]                      # second feature sits inside the first one's circle
+    assert list(tid) == [100, 0, 500, 103] and nid == 501  # age 21 > 20 -> new tracklet id, age reset
+    assert list(age) == [2, 0, 0, 6]
+    assert det[10, 10] == 0 and trk[10, 10] == 3 and det[0, 0] == 255
+
+
+def test_c_abi_frontend_exports():
+    import os
+    import __graft_entry__ as g
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "dynosam_b200", "libdynofront.so")):
+        g.build()
+    from dynosam_b200 import frontend
+    lib = frontend.load()
+    for s in frontend.EXPORTS:
+        assert hasattr(lib, s), s
+
+
+# ------------------------------------------------------------------------------------------------ GPU parity
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_det,min_dist", [(False, 2), (True, 3), (True, 0)])
+def test_track_dynamic_bit_exact(with_det, min_dist):
+    from dynosam_b200.frontend import FeatureTrackerGPU, TrackParams
+    from oracle import frontend_oracle as FO
+    rng = np.random.default_rng(1)
+    st = SyntheticStream(n_objects=10, seed=7)
+    _, m0, f0 = st.frame(4); _, m1, f1 = st.frame(5)
+    f1[100:140, 300:360] = 0.0                              # exact-zero flow region (skipped features)
+    kp, lab = _features_from_mask(rng, m0, f0, per_object=400)
+    age = rng.integers(0, 22, len(lab)).astype(np.int32); tid = np.arange(1000, 1000 + len(lab), dtype=np.int64)
+    det = None
+    if with_det:
+        det = np.full((H, W), 255, np.uint8); det[:, 500:520] = 0; det[150:160, :] = 0
+    prm = TrackParams(max_dynamic_feature_age=20, min_distance=min_dist)
+    t = FeatureTrackerGPU(W, H); t.set_frame(f1, m1, det)
+    a, pk, fl, oa, ot, ol, nid, dm, tm = t.track_dynamic(kp, lab, age, tid, prm, 5000)
+    ra, rpk, rfl, roa, rot, rol, rnid, rdm, rtm = FO.track_dynamic(kp, lab, age, tid, f1, m1, det, FO.TrackParams(20, min_dist, 0, 0), 5000)
+    assert 0 < ra.sum() < len(ra)
+    assert np.array_equal(a, ra) and np.array_equal(oa, roa) and np.array_equal(ot, rot) and np.array_equal(ol, rol) and nid == rnid
+    assert np.array_equal(pk, rpk) and np.array_equal(fl, rfl)          # fp32 -> fp64 adds are exact on both sides
+    assert np.array_equal(dm, rdm) and np.array_equal(tm, rtm)
+
+
+@pytest.mark.gpu
+def test_sample_candidates_sets():
+    from dynosam_b200.frontend import FeatureTrackerGPU, TrackParams
+    from oracle import frontend_oracle as FO
+    st = SyntheticStream(n_objects=6, seed=3)
+    _, m1, f1 = st.frame(2)
+    f1[50:80, 200:260] = 0.0
+    det = np.full((H, W), 255, np.uint8); det[::7, :] = 0
+    small = (slice(0, 200), slice(100, 500))                     # the literal Python oracle is slow: crop
+    m = np.ascontiguousarray(m1[small]); f = np.ascontiguousarray(f1[small]); d = np.ascontiguousarray(det[small])
+    hh, ww = m.shape
+    objs = [int(o) for o in np.unique(m) if o != 0][:4] + [99]
+    t = FeatureTrackerGPU(ww, hh); t.set_frame(f, m, d)
+    prm = TrackParams(shrink_row=3, shrink_col=5)
+    cand, zero = t.sample_candidates(objs, prm)
+    rc, rz = FO.sample_dynamic_candidates(f, m, d, objs, FO.TrackParams(20, 2, 3, 5))
+    for o in objs:
+        assert np.array_equal(cand[o], np.array(rc[o], dtype=np.int32)), o      # ascending pixel order on both sides
+        assert zero[o] == rz[o]
+    assert sum(len(v) for v in cand.values()) > 0
+
+
+@pytest.mark.gpu
+def test_propagate_mask_bit_exact():
+    from dynosam_b200.frontend import FeatureTrackerGPU, TrackParams
+    from oracle import frontend_oracle as FO
+    rng = np.random.default_rng(5)
+    st = SyntheticStream(n_objects=5, seed=11, width=400, height=200)
+    _, m0, f0 = st.frame(3); _, m1, _ = st.frame(4)
+    cur = m1.copy()
+    labs = [int(l) for l in np.unique(m0) if l != 0]
+    cur[cur == labs[0]] = 0                                   # the detector lost the first object in the current frame
+    if len(labs) > 1:
+        cur[cur == labs[1]] = 0
+    kps, lab = [], []
+    for l in labs:
+        ys, xs = np.nonzero(m0 == l)
+        sel = rng.choice(len(ys), size=min(220, len(ys)), replace=False)
+        kps += [(x + 0.3 + f0[y, x, 0], y + 0.4 + f0[y, x, 1]) for y, x in zip(ys[sel], xs[sel])]; lab += [l]*len(sel)
+    kps = np.array(kps); lab = np.array(lab, dtype=np.int32)
+    ok = (kps[:, 0] > 1) & (kps[:, 0] < 399) & (kps[:, 1] > 1) & (kps[:, 1] < 199)
+    kps, lab = kps[ok], lab[ok]
+    t = FeatureTrackerGPU(400, 200)
+    out = t.propagate_mask(kps, lab, m0, f0, cur, TrackParams())
+    ref = FO.propagate_mask(kps, lab, m0, f0, cur, FO.TrackParams())
+    assert np.array_equal(out, ref)
+    assert (out != cur).sum() > 0
+
+
+@pytest.mark.gpu
+def test_pyramid_and_scharr_bit_exact():
+    import cv2
+    from dynosam_b200.frontend import FeatureTrackerGPU
+    st = SyntheticStream(n_objects=4, seed=2)
+    g0, _, _ = st.frame(0); g1, _, _ = st.frame(1)
+    t = FeatureTrackerGPU(W, H)
+    t.klt_track(g0, g1, np.array([[100.0, 100.0]], np.float32))
+    ref = g0
+    for lvl in range(4):
+        img, der = t.pyramid_level(0, lvl)
+        assert np.array_equal(img, ref), lvl
+        # calcSharrDeriv == Scharr with BORDER_REFLECT_101, unnormalised, int16
+        dx = cv2.Scharr(ref, cv2.CV_16S, 1, 0, borderType=cv2.BORDER_REFLECT_101)
+        dy = cv2.Scharr(ref, cv2.CV_16S, 0, 1, borderType=cv2.BORDER_REFLECT_101)
+        assert np.array_equal(der[..., 0], dx) and np.array_equal(der[..., 1], dy), lvl
+        ref = cv2.pyrDown(ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_level,initial", [(3, False), (5, False), (3, True)])
+def test_klt_matches_opencv(max_level, initial):
+    from dynosam_b200.frontend import FeatureTrackerGPU
+    from oracle import frontend_oracle as FO
+    rng = np.random.default_rng(9)
+    st = SyntheticStream(n_objects=10, seed=42)
+    g0, _, _ = st.frame(10); g1, _, _ = st.frame(11)
+    n = 1000
+    pts = np.stack([rng.uniform(-5, W + 5, n), rng.uniform(-5, H + 5, n)], 1).astype(np.float32)     # includes border cases
+    pts[:50] = np.stack([rng.uniform(0, 12, 50), rng.uniform(0, H, 50)], 1)                        # windows hanging over the edge
+    init = (pts + rng.normal(0, 1.0, pts.shape)).astype(np.float32) if initial else None
+    t = FeatureTrackerGPU(W, H)
+    nxt, stt, err = t.klt_track(g0, g1, pts, win=21, max_level=max_level, max_count=30, eps=0.03, initial=init)
+    rn, rs, re = FO.klt_track(g0, g1, pts, 21, max_level, 30, 0.03, init)
+    agree = stt == rs
+    # status flags: bit-exact except where cv2's float accumulation puts minEig within rounding of the threshold
+    assert agree.mean() >= 0.998, agree.mean()
+    both = (stt == 1) & (rs == 1)
+    d = np.abs(nxt[both] - rn[both]).max(axis=1)
+    assert np.percentile(d, 99) < 1e-2 and np.median(d) < 1e-3, (np.percentile(d, 99), np.median(d))
+    assert np.abs(err[both] - re[both]).max() < 0.5
