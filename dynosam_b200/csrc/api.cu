@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -30,12 +31,13 @@ struct HostBlock {
   DevBlock dev{};
   bool simple = false, pose_only = false;
   int part_off = 0, bs_off = 0;
+  DevWindows win{}; bool use_window = false; int win_only_v1 = 0;
 };
 
 }  // namespace
 
 struct dynoba_solver {
-  int device = 0; cudaStream_t stream = nullptr; std::string err;
+  int device = 0; cudaStream_t stream = nullptr; cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; std::string err;
   std::vector<double> pose, point, flow, aux; std::vector<uint64_t> kpose, kpoint, kflow;
   double calib[6] = { 721.5377, 721.5377, 0.0, 609.5593, 172.854, 0.5372 };
   std::vector<int32_t> hint;
@@ -105,6 +107,8 @@ int dynoba_create(int device, dynoba_handle* out) {
   h->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DYNOBA_ERR_CUDA; }
   for (auto& e : h->ev) cudaEventCreate(&e);
+  cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   *out = h;
   return DYNOBA_OK;
 }
@@ -115,6 +119,8 @@ int dynoba_destroy(dynoba_handle h) {
   free_device(h);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork); if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return DYNOBA_OK;
 }
@@ -367,6 +373,7 @@ static int finalize_impl(dynoba_solver* h) {
     if ((rc = dalloc(h, &d.J, (size_t)ti.dim*ti.jcols*stride))) return rc;
     if ((rc = dalloc(h, &d.b, (size_t)ti.dim*stride))) return rc;
     CK(cudaMemset(d.J, 0, (size_t)ti.dim*ti.jcols*stride*8)); CK(cudaMemset(d.b, 0, (size_t)ti.dim*stride*8));
+    if (numeric_grid(b.type, (int)n) > 0) { if ((rc = dalloc(h, &d.num_scratch, (size_t)numeric_grid(b.type, (int)n)))) return rc; }
     // groups: CSR over every landmark group that has factors in this block; groups this block cannot own alone
     // (several points, or factors in other blocks too) are marked -1 and collected for the general path
     b.simple = false;
@@ -389,6 +396,64 @@ static int finalize_impl(dynoba_solver* h) {
       if ((rc = dalloc(h, &dgl, gl.size()))) return rc; if (!gl.empty()) CK(cudaMemcpy(dgl, gl.data(), gl.size()*4, cudaMemcpyHostToDevice));
       d.n_groups = (int)gl.size(); d.grp_ptr = dgp; d.grp_lmk = dgl;
       b.simple = true;
+      // ---- window decomposition (kernels_window.cu) for the 3-dof landmark types
+      const bool win_type = b.type == F_POSE2POINT3 || b.type == F_STEREO3 || b.type == F_HYBRID3 || b.type == F_HYBRID_STEREO3;
+      b.use_window = false; b.win = DevWindows{};
+      if (win_type && !gl.empty() && !getenv("DYNOBA_NO_WINDOW")) {
+        const int ng = (int)gl.size(), NPs = ti.npose;
+        std::vector<unsigned char> gwin(ng, 0), lvar((size_t)NPs*stride, 0);
+        std::vector<int32_t> chunk_g0, chunk_nloc, cvars; std::vector<int2> jobs;
+        std::vector<int32_t> stamp(np, -1), gstamp(np, -1);
+        std::vector<int32_t> cur; int cur_g0 = 0, chunk_id = 0;
+        int pose_slot[2] = {0, 0}; { int c = 0; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE && c < 2) pose_slot[c++] = k; }
+        auto close_chunk = [&](int g_end) {
+          std::vector<int32_t> sorted = cur; std::sort(sorted.begin(), sorted.end());
+          std::vector<int32_t> local(sorted.size());
+          for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = (int32_t)i;       // position -> local index
+          for (int g = cur_g0; g < g_end; g++) if (gwin[g] == 1)
+            for (int s = gp[g]; s < gp[g+1]; s++) for (int k = 0; k < NPs; k++) lvar[(size_t)k*stride + s] = (unsigned char)stamp[hidx[(size_t)pose_slot[k]*stride + s]];
+          for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = -1;
+          chunk_g0.push_back(cur_g0); chunk_nloc.push_back((int32_t)sorted.size());
+          sorted.resize(WIN_NLOC_MAX, 0); cvars.insert(cvars.end(), sorted.begin(), sorted.end());
+          const int nl_ = chunk_nloc.back(); const int nblk = nl_*(nl_ + 1)/2;
+          for (int st = 0; st*256 < nblk; st++) jobs.push_back(make_int2(chunk_id, st));
+          chunk_id++; cur.clear(); cur_g0 = g_end;
+        };
+        std::vector<int32_t> inchunk(np, -1);
+        for (int g = 0; g < ng; g++) {
+          if (gl[g] < 0) continue;
+          const int T = gp[g+1] - gp[g];
+          bool dup = false; int fresh = 0;
+          if (T > 24) { gwin[g] = 2; continue; }
+          for (int s = gp[g]; s < gp[g+1] && !dup; s++) for (int k = 0; k < NPs; k++) {
+            const int p = hidx[(size_t)pose_slot[k]*stride + s];
+            if (gstamp[p] == g) { dup = true; break; }
+            gstamp[p] = g;
+            if (inchunk[p] != chunk_id) fresh++;
+          }
+          if (dup) { gwin[g] = 2; continue; }
+          if ((int)cur.size() + fresh > WIN_NLOC_MAX) {
+            close_chunk(g);
+            fresh = T*NPs;
+          }
+          for (int s = gp[g]; s < gp[g+1]; s++) for (int k = 0; k < NPs; k++) {
+            const int p = hidx[(size_t)pose_slot[k]*stride + s];
+            if (inchunk[p] != chunk_id) { inchunk[p] = chunk_id; cur.push_back(p); }
+          }
+          gwin[g] = 1;
+        }
+        close_chunk(ng);
+        chunk_g0.push_back(ng);
+        int2* djobs; int* dg0; int* dnl; int* dcv; unsigned char* dlv; unsigned char* dgw;
+        if ((rc = dalloc(h, &djobs, jobs.size()))) return rc; if (!jobs.empty()) CK(cudaMemcpy(djobs, jobs.data(), jobs.size()*sizeof(int2), cudaMemcpyHostToDevice));
+        if ((rc = dalloc(h, &dg0, chunk_g0.size()))) return rc; CK(cudaMemcpy(dg0, chunk_g0.data(), chunk_g0.size()*4, cudaMemcpyHostToDevice));
+        if ((rc = dalloc(h, &dnl, chunk_nloc.size()))) return rc; CK(cudaMemcpy(dnl, chunk_nloc.data(), chunk_nloc.size()*4, cudaMemcpyHostToDevice));
+        if ((rc = dalloc(h, &dcv, cvars.size()))) return rc; CK(cudaMemcpy(dcv, cvars.data(), cvars.size()*4, cudaMemcpyHostToDevice));
+        if ((rc = dalloc(h, &dlv, lvar.size()))) return rc; CK(cudaMemcpy(dlv, lvar.data(), lvar.size(), cudaMemcpyHostToDevice));
+        if ((rc = dalloc(h, &dgw, gwin.size()))) return rc; CK(cudaMemcpy(dgw, gwin.data(), gwin.size(), cudaMemcpyHostToDevice));
+        b.win.n_jobs = (int)jobs.size(); b.win.jobs = djobs; b.win.chunk_g0 = dg0; b.win.chunk_nloc = dnl; b.win.cvars = dcv; b.win.lvar = dlv; b.win.grp_win = dgw;
+        b.use_window = true;
+      }
     }
     b.part_off = part; part += linearize_grid((int)n);
     b.bs_off = bs; bs += b.pose_only ? (int)((n + 127)/128) : backsub_grid(d.n_groups);
@@ -458,7 +523,15 @@ static int eval_error(dynoba_solver* h, const DevVars& v, int slot) {
   return DYNOBA_OK;
 }
 static int do_linearize(dynoba_solver* h) {
-  for (auto& b : h->blocks) h->launches += launch_linearize(b.dev, h->cur, h->partials + b.part_off, h->stream);
+  // the compute-bound numeric-Jacobian blocks run on a side stream underneath the HBM-bound analytic ones
+  bool side = false;
+  for (auto& b : h->blocks) if (b.n && numeric_grid(b.type, (int)b.n) > 0) side = true;
+  if (side) { cudaEventRecord(h->ev_fork, h->stream); cudaStreamWaitEvent(h->stream2, h->ev_fork, 0); }
+  for (auto& b : h->blocks) {
+    const bool num = numeric_grid(b.type, (int)b.n) > 0;
+    h->launches += launch_linearize(b.dev, h->cur, h->partials + b.part_off, num ? h->stream2 : h->stream);
+  }
+  if (side) { cudaEventRecord(h->ev_join, h->stream2); cudaStreamWaitEvent(h->stream, h->ev_join, 0); }
   h->launches += launch_sum(h->partials, h->n_lin_partials, h->scalars + 0, h->stream);
   h->linearized = true;
   return DYNOBA_OK;
@@ -469,7 +542,10 @@ static int build_reduced(dynoba_solver* h, double lambda) {
   h->launches += launch_band_clear(h->band, lambda, h->rank == 0, h->stream);
   for (auto& b : h->blocks) {
     if (b.pose_only) h->launches += launch_pose_factors(b.dev, h->band, h->stream);
-    else h->launches += launch_schur_simple(b.dev, h->band, lambda, h->fail, h->stream);
+    else {
+      if (b.use_window) h->launches += launch_schur_window(b.dev, b.win, h->band, lambda, h->fail, h->stream);
+      h->launches += launch_schur_simple(b.dev, b.use_window ? b.win.grp_win : nullptr, h->band, lambda, h->fail, h->stream);
+    }
   }
   h->launches += launch_schur_general(h->gen, h->band, lambda, h->fail, h->stream);
   return allreduce_dev(h, h->band.tiles, h->band.tile_count*TILE2 + h->band.n_pad);

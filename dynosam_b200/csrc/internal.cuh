@@ -34,6 +34,7 @@ struct DevBlock {
   int n_groups;
   const int* grp_ptr;   // [n_groups+1] into the sorted factor range
   const int* grp_lmk;   // [n_groups]   device landmark index, or -1 when the group is handled by the general path
+  double* num_scratch;  // numeric-Jacobian factor types: per-CTA partial sums of the column-parallel linearize kernel
 };
 
 // Band storage of the reduced (camera + object-motion) system, lower triangle, TILE x TILE tiles:
@@ -60,14 +61,28 @@ struct GeneralGroups {
   const int* gnl;           // [n_groups] number of points (<= 21)
 };
 
+// Window decomposition of a factor block for kernels_window.cu (built by the host in finalize)
+constexpr int WIN_NLOC_MAX = 48;
+struct DevWindows {
+  int n_jobs;
+  const int2* jobs;              // (chunk, stripe of 256 lower-triangular blocks)
+  const int* chunk_g0;           // [n_chunks+1] group range of a chunk
+  const int* chunk_nloc;         // [n_chunks]
+  const int* cvars;              // [n_chunks][WIN_NLOC_MAX] solver positions, ascending
+  const unsigned char* lvar;     // [npose_slots][stride] local variable of each factor's pose slot
+  const unsigned char* grp_win;  // [n_groups] 0: general path, 1: window path, 2: per-landmark atomics path
+};
+
 // ---- launchers (each returns the number of kernels it launched)
 int launch_linearize(const DevBlock& blk, const DevVars& v, double* partials, cudaStream_t s);
 int launch_error(const DevBlock& blk, const DevVars& v, double* partials, double* per_factor, cudaStream_t s);
 int launch_sum(const double* partials, int n, double* out, cudaStream_t s);
 int linearize_grid(int n);          // number of partial sums a linearize/error launch of n factors writes
+int numeric_grid(int type, int n);  // CTAs of the column-parallel linearize kernel (0 for analytic factor types)
 
 int launch_band_clear(const DevBand& B, double lambda, int add_damping, cudaStream_t s);
-int launch_schur_simple(const DevBlock& blk, const DevBand& B, double lambda, int* fail, cudaStream_t s);
+int launch_schur_simple(const DevBlock& blk, const unsigned char* grp_win, const DevBand& B, double lambda, int* fail, cudaStream_t s);
+int launch_schur_window(const DevBlock& blk, const DevWindows& Wn, const DevBand& B, double lambda, int* fail, cudaStream_t s);
 int launch_schur_general(const GeneralGroups& G, const DevBand& B, double lambda, int* fail, cudaStream_t s);
 int launch_backsub_general(const GeneralGroups& G, const DevBand& B, double lambda, double* dl_point, int nl_stride,
                            double* partials, cudaStream_t s);

@@ -15,7 +15,10 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstdio>
+#include <cooperative_groups.h>
 #include "internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dynoba {
 
@@ -451,53 +454,83 @@ __global__ void __launch_bounds__(SV_WARPS*32) band_forward_kernel(DevBand B, co
   }
 }
 
-// backward sweep  x_J = Linv_JJ^T (y_J - sum_{I>J} L_IJ^T x_I); rhs overwritten
-__global__ void __launch_bounds__(SV_WARPS*32) band_backward_kernel(DevBand B, const double* __restrict__ linv) {
+// backward sweep  x_J = Linv_JJ^T (y_J - sum_{I>J} L_IJ^T x_I); rhs overwritten.
+// One thread-block CLUSTER of 8 CTAs (8 SMs): the off-diagonal tiles of a column are spread over 8 x 4 warps so the
+// 240 KB a column reads come through eight SMs' load paths; per-CTA partial sums travel to rank 0 through
+// distributed shared memory, rank 0 applies the inverse diagonal tile and broadcasts x_J into every CTA's ring.
+constexpr int BW_CL = 8, BW_TW = 4;      // cluster size, tile warps per CTA
+__global__ void __cluster_dims__(BW_CL, 1, 1) __launch_bounds__((BW_TW + 1)*32)
+band_backward_cluster_kernel(DevBand B, const double* __restrict__ linv) {
   extern __shared__ double sm[];
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = (int)cl.block_rank();
   const int NT = B.NT, WB = B.WB, W1 = WB + 1, ring = WB + 1;
-  double* xs = sm; double* part = sm + (size_t)ring*TILE;
+  double* xs = sm;                                   // [ring][32] solved blocks (replicated in every CTA)
+  double* lpart = sm + (size_t)ring*TILE;            // [BW_TW][32] partial sums of this CTA's tile warps
+  double* cpart = lpart + BW_TW*TILE;                // [2][BW_CL][32] all-gathered per-CTA partials
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // software prefetch: the tile this warp needs for column J-1 is loaded while column J is processed
+  const int myq = rank*BW_TW + (warp - 1);
+  double tn[TILE];
+  auto prefetch = [&](int J) {
+    if (warp >= 1 && J >= 0 && myq < min(WB, NT - 1 - J)) {
+      const double* tp = B.tiles + (size_t)J*W1*TILE2 + (size_t)(myq + 1)*TILE2;
+#pragma unroll
+      for (int c = 0; c < TILE; c++) tn[c] = tp[c*TILE + lane];
+    }
+  };
+  prefetch(NT - 1);
   for (int J = NT - 1; J >= 0; J--) {
     const int nbelow = min(WB, NT - 1 - J);
     const double* colJ = B.tiles + (size_t)J*W1*TILE2;
-    double t[TILE]; int q = warp - 1; bool have = false;
-    if (warp > 0 && q < nbelow) {
-      const double* tp = colJ + (size_t)(q + 1)*TILE2;
-#pragma unroll
-      for (int c = 0; c < TILE; c++) t[c] = tp[c*TILE + lane];     // row `lane` of L_IJ
-      have = true;
-    }
-    __syncthreads();
-    if (warp > 0) {
+    if (warp >= 1) {
       double s = 0.0;
-      while (have) {
-        const int I = J + 1 + q;
-        const double xr = xs[(size_t)(I % ring)*TILE + lane];
+      double t[TILE];
+#pragma unroll
+      for (int c = 0; c < TILE; c++) t[c] = tn[c];
+      prefetch(J - 1);
+      if (myq < nbelow) {
+        const double xr = xs[(size_t)((J + 1 + myq) % ring)*TILE + lane];
 #pragma unroll
         for (int c = 0; c < TILE; c++) t[c] *= xr;
-        s += warp_transpose_sum(t, lane);                           // lane c: sum_r L[r][c] x[r]
-        q += SV_WARPS - 1; have = q < nbelow;
-        if (have) {
-          const double* tp = colJ + (size_t)(q + 1)*TILE2;
-#pragma unroll
-          for (int c = 0; c < TILE; c++) t[c] = tp[c*TILE + lane];
-        }
+        s += warp_transpose_sum(t, lane);                             // lane c: sum_r L[r][c] x[r]
       }
-      part[warp*TILE + lane] = s;
+      for (int q = myq + BW_CL*BW_TW; q < nbelow; q += BW_CL*BW_TW) {   // only when WB > 32
+        const double* tp = colJ + (size_t)(q + 1)*TILE2;
+#pragma unroll
+        for (int c = 0; c < TILE; c++) t[c] = tp[c*TILE + lane];     // row `lane` of L_IJ
+        const double xr = xs[(size_t)((J + 1 + q) % ring)*TILE + lane];
+#pragma unroll
+        for (int c = 0; c < TILE; c++) t[c] *= xr;
+        s += warp_transpose_sum(t, lane);
+      }
+      lpart[(warp - 1)*TILE + lane] = s;
     }
     __syncthreads();
+    double li[TILE];
+    if (warp == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < BW_TW; w++) s += lpart[w*TILE + lane];
+      // all-gather of the per-CTA partials through distributed shared memory (double-buffered by column parity)
+#pragma unroll
+      for (int r = 0; r < BW_CL; r++) cl.map_shared_rank(cpart, r)[((J & 1)*BW_CL + rank)*TILE + lane] = s;
+      const double* lp = linv + (size_t)J*TILE2;                       // every CTA finishes x_J itself: no second barrier
+#pragma unroll
+      for (int c = 0; c < TILE; c++) li[c] = lp[c*TILE + lane];
+    }
+    cl.sync();
     if (warp == 0) {
       double v = B.rhs[(size_t)J*TILE + lane];
-      const int nw = min(nbelow, SV_WARPS - 1);
-      for (int w = 1; w <= nw; w++) v -= part[w*TILE + lane];
-      const double* li = linv + (size_t)J*TILE2;
-      double p[TILE];
 #pragma unroll
-      for (int c = 0; c < TILE; c++) p[c] = li[c*TILE + lane]*v;    // Linv[lane][c] * v[lane]
-      const double x = warp_transpose_sum(p, lane);                  // lane c: sum_r Linv[r][c] v[r]
+      for (int r = 0; r < BW_CL; r++) v -= cpart[((J & 1)*BW_CL + r)*TILE + lane];
+#pragma unroll
+      for (int c = 0; c < TILE; c++) li[c] *= v;                      // Linv[lane][c] * v[lane]
+      const double x = warp_transpose_sum(li, lane);                  // lane c: sum_r Linv[r][c] v[r]
       xs[(size_t)(J % ring)*TILE + lane] = x;
-      B.rhs[(size_t)J*TILE + lane] = x;
+      if (rank == 0) B.rhs[(size_t)J*TILE + lane] = x;
     }
+    __syncthreads();
   }
 }
 
@@ -537,14 +570,13 @@ int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, 
 }
 
 int launch_band_solve(const DevBand& B, const double* linv, cudaStream_t s) {
-  const size_t smem = ((size_t)(B.WB + 1)*TILE + (size_t)SV_WARPS*TILE)*sizeof(double);
+  const size_t smem = ((size_t)(B.WB + 1)*TILE + (size_t)(BW_TW + 2*BW_CL)*TILE)*sizeof(double);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(band_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-    cudaFuncSetAttribute(band_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
+    cudaFuncSetAttribute(band_backward_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
     attr = true;
   }
-  band_backward_kernel<<<1, SV_WARPS*32, smem, s>>>(B, linv);   // the forward sweep is folded into the factorisation
+  band_backward_cluster_kernel<<<BW_CL, (BW_TW + 1)*32, smem, s>>>(B, linv);   // forward sweep: folded into the factorisation
   return 1;
 }
 

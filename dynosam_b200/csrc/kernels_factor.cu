@@ -87,6 +87,78 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(DevBlock blk, De
   if (threadIdx.x == 0) partials[blockIdx.x] = tot;
 }
 
+
+// K1 for the numerically differentiated factor types (LandmarkMotionPoseFactor, HybridSmoothingFactor,
+// LandmarkPoseSmoothingFactor): one thread per (factor, Jacobian column) instead of one thread per factor, so the
+// 2 x 18 perturbed residual evaluations of gtsam::numericalDerivative run in parallel (18x more threads, 3 instead
+// of 37 residual evaluations per thread).  Column arithmetic is identical to numeric_jacobian() in factors.cuh.
+template <int T>
+__global__ void __launch_bounds__(LIN_THREADS) linearize_numeric_kernel(DevBlock blk, DevVars v, double* __restrict__ partials) {
+  constexpr TypeInfo ti = type_info(T);
+  constexpr int D = ti.dim, JC = ti.jcols;
+  __shared__ double sh[LIN_THREADS/32];
+  // column-major thread map: a CTA (and every warp) works on ONE Jacobian column of 128 consecutive factors, so the
+  // perturbed slot / direction is warp-uniform and the factor-stream loads stay coalesced
+  const int cta_per_col = (blk.n + LIN_THREADS - 1)/LIN_THREADS;
+  const int col = blockIdx.x/cta_per_col;
+  const int f = (blockIdx.x - col*cta_per_col)*LIN_THREADS + threadIdx.x;
+  double hb2 = 0.0;
+  if (f < blk.n) {
+    FVars fv; Pose aux;
+    gather_vars<T>(blk, v, f, fv, aux);
+    double isig[D];
+    if (blk.sigma_dim == 1) { isig[0] = __ldg(blk.isig + f); }
+    else {
+#pragma unroll
+      for (int k = 0; k < D; k++) isig[k] = __ldg(blk.isig + (size_t)k*blk.stride + f);
+    }
+    double hx[D], h1[D], h2[D];
+    numeric_residual<T>(fv, aux, hx);
+    // which key slot / tangent direction does this column perturb?
+    int slot = 0, j = col;
+#pragma unroll
+    for (int k = 0; k < ti.arity; k++) if (col >= ti.coloff[k]) { slot = k; j = col - ti.coloff[k]; }
+    int pi = 0, li = 0;
+#pragma unroll
+    for (int k = 0; k < ti.arity; k++) if (k < slot) { if (ti.cls[k] == VC_POSE) pi++; else li++; }
+    constexpr double delta = 1e-5, factor = 1.0/(2.0*delta);
+#pragma unroll
+    for (int sgn = 0; sgn < 2; sgn++) {
+      FVars w = fv;
+      const double d = sgn == 0 ? delta : -delta;
+      bool is_pose = false;
+#pragma unroll
+      for (int k = 0; k < ti.arity; k++) if (k == slot) is_pose = ti.cls[k] == VC_POSE;
+      if (is_pose) {
+        double xi[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 6; q++) if (q == j) xi[q] = d;
+#pragma unroll
+        for (int p = 0; p < 3; p++) if (p == pi) se3_retract(fv.pose[p], xi, w.pose[p]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+          for (int q = 0; q < 3; q++) if (p == li && q == j) w.pt[p][q] += d;
+      }
+      numeric_residual<T>(w, aux, sgn == 0 ? h1 : h2);
+    }
+    double r[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) r[k] = hx[k];
+    double err;
+    const double sw = whiten_weight<D>(r, isig, blk.sigma_dim, blk.robust_k, &err);
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      const double fk = (blk.sigma_dim == 1 ? isig[0] : isig[k])*sw;
+      blk.J[(size_t)(k*JC + col)*blk.stride + f] = ((h1[k] - hx[k]) - (h2[k] - hx[k]))*factor*fk;
+      if (col == 0) { const double bk = -r[k]*sw; blk.b[(size_t)k*blk.stride + f] = bk; hb2 += 0.5*bk*bk; }
+    }
+  }
+  const double tot = block_sum(hb2, sh);
+  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+
 // K2.  chi^2 sweep: nonlinear factor errors (Gaussian 0.5|r_w|^2 or Huber rho), no Jacobians.
 template <int T>
 __global__ void __launch_bounds__(LIN_THREADS) error_kernel(DevBlock blk, DevVars v, double* __restrict__ partials,
@@ -129,6 +201,11 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ p,
 }
 
 int linearize_grid(int n) { return (n + LIN_THREADS - 1)/LIN_THREADS; }
+int numeric_grid(int type, int n) {
+  if (!(type == F_MOTIONPOSE3 || type == F_SMOOTH_HYBRID6 || type == F_SMOOTH_POSE6)) return 0;
+  return ((n + LIN_THREADS - 1)/LIN_THREADS)*type_info(type).jcols;
+}
+
 
 #define DISPATCH_TYPE(T, CALL)                       \
   switch (T) {                                       \
@@ -146,9 +223,26 @@ int linearize_grid(int n) { return (n + LIN_THREADS - 1)/LIN_THREADS; }
     default: break;                                  \
   }
 
+__global__ void fold_partials_kernel(const double* __restrict__ in, int nin, double* __restrict__ out, int nout) {
+  // deterministic fold of nin per-block sums into nout slots (slot k sums in[k], in[k+nout], ...)
+  const int k = blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= nout) return;
+  double s = 0; for (int i = k; i < nin; i += nout) s += in[i];
+  out[k] = s;
+}
+
 int launch_linearize(const DevBlock& blk, const DevVars& v, double* partials, cudaStream_t s) {
   if (blk.n == 0) return 0;
   const int grid = linearize_grid(blk.n);
+  if (blk.type == F_MOTIONPOSE3 || blk.type == F_SMOOTH_HYBRID6 || blk.type == F_SMOOTH_POSE6) {
+    const int g2 = numeric_grid(blk.type, blk.n);
+    double* scratch = blk.num_scratch;
+    if (blk.type == F_MOTIONPOSE3) linearize_numeric_kernel<F_MOTIONPOSE3><<<g2, LIN_THREADS, 0, s>>>(blk, v, scratch);
+    else if (blk.type == F_SMOOTH_HYBRID6) linearize_numeric_kernel<F_SMOOTH_HYBRID6><<<g2, LIN_THREADS, 0, s>>>(blk, v, scratch);
+    else linearize_numeric_kernel<F_SMOOTH_POSE6><<<g2, LIN_THREADS, 0, s>>>(blk, v, scratch);
+    fold_partials_kernel<<<(grid + 127)/128, 128, 0, s>>>(scratch, g2, partials, grid);
+    return 2;
+  }
 #define CALL_LIN(TT) linearize_kernel<TT><<<grid, LIN_THREADS, 0, s>>>(blk, v, partials)
   DISPATCH_TYPE(blk.type, CALL_LIN)
 #undef CALL_LIN

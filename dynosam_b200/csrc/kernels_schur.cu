@@ -88,12 +88,12 @@ struct GroupTiles {
 
 template <int NP, int DL, int D, int PCOL0, int LCOL, int PSLOT0>
 __global__ void __launch_bounds__(SCHUR_WARPS*32)
-schur_simple_kernel(DevBlock blk, DevBand B, double lambda, int* __restrict__ fail) {
+schur_simple_kernel(DevBlock blk, const unsigned char* __restrict__ grp_win, DevBand B, double lambda, int* __restrict__ fail) {
   constexpr int JC = NP*6 + DL, NE = D*JC + D;
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x*SCHUR_WARPS + warp;
-  if (g >= blk.n_groups || blk.grp_lmk[g] < 0) return;
+  if (g >= blk.n_groups || blk.grp_lmk[g] < 0 || (grp_win && grp_win[g] == 1)) return;
   double* sJ = smem + (size_t)warp*NE*32;
   const int f0 = blk.grp_ptr[g], T = blk.grp_ptr[g+1] - f0;
   const bool staged = T <= 32;
@@ -244,23 +244,23 @@ schur_simple_kernel(DevBlock blk, DevBand B, double lambda, int* __restrict__ fa
 }
 
 template <int NP, int DL, int D, int PCOL0, int LCOL, int PSLOT0>
-static int launch_schur_t(const DevBlock& blk, const DevBand& B, double lambda, int* fail, cudaStream_t s) {
+static int launch_schur_t(const DevBlock& blk, const unsigned char* grp_win, const DevBand& B, double lambda, int* fail, cudaStream_t s) {
   constexpr int NE = D*(NP*6 + DL) + D;
   const size_t smem = (size_t)SCHUR_WARPS*NE*32*sizeof(double);
   auto kern = schur_simple_kernel<NP, DL, D, PCOL0, LCOL, PSLOT0>;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
   const int grid = (blk.n_groups + SCHUR_WARPS - 1)/SCHUR_WARPS;
-  kern<<<grid, SCHUR_WARPS*32, smem, s>>>(blk, B, lambda, fail);
+  kern<<<grid, SCHUR_WARPS*32, smem, s>>>(blk, grp_win, B, lambda, fail);
   return 1;
 }
 
-int launch_schur_simple(const DevBlock& blk, const DevBand& B, double lambda, int* fail, cudaStream_t s) {
+int launch_schur_simple(const DevBlock& blk, const unsigned char* grp_win, const DevBand& B, double lambda, int* fail, cudaStream_t s) {
   if (blk.n_groups == 0) return 0;
   switch (blk.type) {
-    case F_POSE2POINT3: case F_STEREO3: return launch_schur_t<1, 3, 3, 0, 6, 0>(blk, B, lambda, fail, s);
-    case F_HYBRID3: case F_HYBRID_STEREO3: return launch_schur_t<2, 3, 3, 0, 12, 0>(blk, B, lambda, fail, s);
-    case F_FLOWPROJ2: return launch_schur_t<1, 2, 2, 2, 0, 1>(blk, B, lambda, fail, s);
+    case F_POSE2POINT3: case F_STEREO3: return launch_schur_t<1, 3, 3, 0, 6, 0>(blk, grp_win, B, lambda, fail, s);
+    case F_HYBRID3: case F_HYBRID_STEREO3: return launch_schur_t<2, 3, 3, 0, 12, 0>(blk, grp_win, B, lambda, fail, s);
+    case F_FLOWPROJ2: return launch_schur_t<1, 2, 2, 2, 0, 1>(blk, grp_win, B, lambda, fail, s);
     default: return 0;
   }
 }
