@@ -160,7 +160,8 @@ def main():
                           + (f", scale {args.scale}" if args.scale != 1.0 else ""),
               "parallelism": f"landmark-sharded x{world}, replicated reduced solve", "seed": args.seed,
               "l2_policy": "working set (Jacobian tiles, GBs) >> 126 MB L2; no explicit flush",
-              "noise": "sigma_point 0.2, Huber k 1e-4, LM defaults with rel/abs tol 0 so that exactly K iterations run"}
+              "noise": "sigma_point 0.2, Huber k 1e-4, LM defaults with rel/abs tol 0 so that exactly K iterations run",
+              "timed_region": "LM iterations 1..K from the initial values (after W warm-up iterations and a value reset)"}
     threads = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -210,10 +211,9 @@ def main():
     s = new_solver(prob)
     s.finalize()
     info = s.info()
-    lam0 = None
     if W:
-        stw = s.optimize(default_params(max_iterations=W, **prm))
-        lam0 = stw["lambda_final"]          # the timed iterations continue the same LM run (lambda carried over)
+        s.optimize(default_params(max_iterations=W, **prm))
+        s.reset_values()      # the timed region is LM iterations 1..K from the initial values, like the CPU arm
     # ---- timed region: exactly K LM iterations, device-timed (CUDA events on the solver's stream), max over ranks
     lin_ms = [s.linearize() for _ in range(3)]                      # Jacobian-build kernel alone (after warm-up)
     torch.cuda.synchronize()
@@ -223,7 +223,7 @@ def main():
     if rank == 0:
         sampler.start()
     t0 = time.perf_counter()
-    st = s.optimize(default_params(max_iterations=K, **(dict(prm, lambda_initial=lam0) if lam0 else prm)))
+    st = s.optimize(default_params(max_iterations=K, **prm))
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     if world > 1:
@@ -286,7 +286,14 @@ def main():
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline:
-        r = cpu_oracle_rate(args.config, args.formulation, args.seed, args.cpu_sample_scale*args.scale, 4, threads)
+        # separate process: a clean OpenMP runtime for the oracle (this process already hosts torch's and libdynoba's)
+        code = ("import json,sys; sys.path.insert(0, %r); import bench; "
+                "print(json.dumps(bench.cpu_oracle_rate(%r, %r, %d, %r, 4, %d)))" %
+                (ROOT, args.config, args.formulation, args.seed, args.cpu_sample_scale*args.scale, threads))
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        env.pop("OMP_PROC_BIND", None)
+        pr = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+        r = json.loads(pr.stdout.strip().splitlines()[-1])
         out["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{args.config} at {args.cpu_sample_scale*args.scale:g} scale ({r['frames']} key-frames, {r['n_factors']} factors), "
                                          f"{r['iterations']} LM iterations in {r['seconds']:.1f} s on {threads} threads; rate scaled linearly in key-frames",

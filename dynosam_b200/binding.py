@@ -174,6 +174,15 @@ class Solver:
         self._cb = ALLREDUCE_FN(_cb)
         self._ck(self.lib.dynoba_set_shard(self.h, rank, world, self._cb, None, min_bandwidth))
 
+    def reset_values(self):
+        """Re-upload the initial values of the ingested problem (device layout is kept)."""
+        p = self.problem
+        self._ck(self.lib.dynoba_set_variables(self.h, POSE6, p.n_pose, C.cast(None, c_u64p), _dp(p.pose)))
+        if p.n_point:
+            self._ck(self.lib.dynoba_set_variables(self.h, POINT3, p.n_point, C.cast(None, c_u64p), _dp(p.point)))
+        if p.n_flow:
+            self._ck(self.lib.dynoba_set_variables(self.h, FLOW2, p.n_flow, C.cast(None, c_u64p), _dp(p.flow)))
+
     def finalize(self):
         self._ck(self.lib.dynoba_finalize(self.h))
 

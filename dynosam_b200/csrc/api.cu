@@ -6,11 +6,16 @@
 // dynosam/src/backend/RegularBackendModule.cc:405-428.  Control decisions need two scalars per trial step, so
 // the loop lives on the host and everything else stays on the device.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <parallel/algorithm>
+#include <omp.h>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -133,7 +138,7 @@ int dynoba_set_variables(dynoba_handle h, int kind, int64_t n, const uint64_t* k
   ARG(dst, "bad variable kind");
   const bool same_shape = dst->size() == (size_t)n*w;
   dst->assign(data, data + (size_t)n*w);
-  if (keys) kd->assign(keys, keys + n); else kd->clear();
+  if (keys) kd->assign(keys, keys + n); else if (!same_shape) kd->clear();   // a value refresh keeps the keys
   if (h->finalized && same_shape) {
     // refresh device values only (layout unchanged)
     cudaSetDevice(h->device);
@@ -215,18 +220,30 @@ static int uf_find(std::vector<int32_t>& p, int x) { while (p[x] != x) { p[x] = 
 static int finalize_impl(dynoba_solver* h) {
   if (h->finalized) return DYNOBA_OK;
   cudaSetDevice(h->device);
+  // host-side symbolic phase runs on up to 32 threads regardless of OMP_NUM_THREADS (torchrun pins it to 1)
+  struct OmpScope { int saved; OmpScope() : saved(omp_get_max_threads()) { int t = std::min(omp_get_num_procs(), 32); if (const char* e = getenv("DYNOBA_THREADS")) t = std::max(1, atoi(e)); omp_set_num_threads(t); } ~OmpScope() { omp_set_num_threads(saved); } } omp_scope;
+  const bool timing = getenv("DYNOBA_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) { if (!timing) return; auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[dynoba finalize] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count()); t_last = t; };
   const int64_t np = (int64_t)h->pose.size()/12, npt = (int64_t)h->point.size()/3, nfl = (int64_t)h->flow.size()/2, naux = (int64_t)h->aux.size()/12;
   ARG(h->hint.empty() || (int64_t)h->hint.size() == np, "pose order hint length != number of poses");
   // ---- validate indices
   for (auto& b : h->blocks) {
     const TypeInfo ti = type_info(b.type);
-    for (int64_t i = 0; i < b.n; i++) for (int k = 0; k < ti.arity; k++) {
-      const int32_t ix = b.idx[i*ti.arity + k];
-      const int64_t lim = ti.cls[k] == VC_POSE ? np : (ti.cls[k] == VC_POINT ? npt : nfl);
-      ARG(ix >= 0 && ix < lim, "factor index out of range");
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(|:bad)
+    for (int64_t i = 0; i < b.n; i++) {
+      for (int k = 0; k < ti.arity; k++) {
+        const int32_t ix = b.idx[i*ti.arity + k];
+        const int64_t lim = ti.cls[k] == VC_POSE ? np : (ti.cls[k] == VC_POINT ? npt : nfl);
+        if (!(ix >= 0 && ix < lim)) bad |= 1;
+      }
+      if (b.has_aux && !(b.aux[i] >= 0 && b.aux[i] < naux)) bad |= 2;
     }
-    if (b.has_aux) for (int64_t i = 0; i < b.n; i++) ARG(b.aux[i] >= 0 && b.aux[i] < naux, "aux index out of range");
+    ARG(!(bad & 1), "factor index out of range"); ARG(!(bad & 2), "aux index out of range");
   }
+  lap("validate");
   // ---- pose ordering
   h->pos.resize(np);
   {
@@ -250,39 +267,72 @@ static int finalize_impl(dynoba_solver* h) {
     }
   }
   std::vector<int32_t> root(nl); for (int64_t i = 0; i < nl; i++) root[i] = uf_find(uf, (int)i);
-  std::vector<int32_t> gmin(nl, INT32_MAX), gmax(nl, -1), gblk(nl, -1), gcount(nl, 0);
+  std::vector<int32_t> gmin(nl, INT32_MAX), gmax(nl, -1), gblk(nl, -1), gcount(nl, 0), gsec(nl, INT32_MAX);
   for (int64_t i = 0; i < nl; i++) gcount[root[i]]++;
   int spread = 0;
   for (size_t bi = 0; bi < h->blocks.size(); bi++) {
     auto& b = h->blocks[bi]; const TypeInfo ti = type_info(b.type);
     b.pose_only = ti.nlmk == 0;
     int lslot = -1; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] != VC_POSE) { lslot = k; break; }
+    int bspread = 0;
+#pragma omp parallel for schedule(static) reduction(max:bspread)
     for (int64_t i = 0; i < b.n; i++) {
       int lo = INT32_MAX, hi = -1;
       for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE) { const int p = h->pos[b.idx[i*ti.arity + k]]; lo = std::min(lo, p); hi = std::max(hi, p); }
-      if (lslot < 0) { spread = std::max(spread, hi - lo); continue; }
+      if (lslot < 0) { bspread = std::max(bspread, hi - lo); continue; }
       const int g = root[lmk_id(ti.cls[lslot], b.idx[i*ti.arity + lslot])];
-      gmin[g] = std::min(gmin[g], lo); gmax[g] = std::max(gmax[g], hi);
-      if (gblk[g] == -1) gblk[g] = (int)bi; else if (gblk[g] != (int)bi) gblk[g] = -2;
+      int32_t cur = __atomic_load_n(&gmin[g], __ATOMIC_RELAXED);
+      while (lo < cur && !__atomic_compare_exchange_n(&gmin[g], &cur, lo, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+      cur = __atomic_load_n(&gmax[g], __ATOMIC_RELAXED);
+      while (hi > cur && !__atomic_compare_exchange_n(&gmax[g], &cur, hi, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+      if (ti.npose >= 2) {   // secondary ordering key: user index of the last pose slot (object-major for DynOSAM's H keys)
+        int last = -1; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE) last = b.idx[i*ti.arity + k];
+        cur = __atomic_load_n(&gsec[g], __ATOMIC_RELAXED);
+        while (last < cur && !__atomic_compare_exchange_n(&gsec[g], &cur, last, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+      }
+      int32_t gb = __atomic_load_n(&gblk[g], __ATOMIC_RELAXED);
+      while (gb != (int)bi && gb != -2) {
+        const int32_t want = gb == -1 ? (int32_t)bi : -2;
+        if (__atomic_compare_exchange_n(&gblk[g], &gb, want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) break;
+      }
     }
+    spread = std::max(spread, bspread);
   }
   for (int64_t g = 0; g < nl; g++) if (gmax[g] >= 0) spread = std::max(spread, gmax[g] - gmin[g]);
   // group rank: by first pose position, then root id
   std::vector<int32_t> gorder; gorder.reserve(nl);
   for (int64_t g = 0; g < nl; g++) if (root[g] == g) gorder.push_back((int32_t)g);
-  std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return gmin[a] < gmin[b]; });
+  // group order: by owning factor block (groups spanning blocks last), then by the secondary key (object-major for
+  // two-pose factor types so that consecutive landmarks share their clique), else by the first pose position
+  std::vector<int64_t> gkey(nl, 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t g = 0; g < nl; g++) {
+    const int64_t cls = gblk[g] >= 0 ? gblk[g] : (1 << 20);
+    const int64_t sec = gsec[g] != INT32_MAX ? gsec[g] : (gmin[g] == INT32_MAX ? 0 : gmin[g]);
+    gkey[g] = (cls << 40) | (sec & ((1LL << 40) - 1));
+  }
+  {
+    bool sorted = true;
+    for (size_t i = 1; i < gorder.size() && sorted; i++) sorted = gkey[gorder[i-1]] <= gkey[gorder[i]];
+    if (!sorted) __gnu_parallel::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return gkey[a] < gkey[b]; });
+  }
   std::vector<int32_t> grank(nl, 0);
   for (size_t r = 0; r < gorder.size(); r++) grank[gorder[r]] = (int32_t)r;
   // landmark device indices
   h->pt_new.assign(npt, 0); h->fl_new.assign(nfl, 0);
   {
     std::vector<int32_t> ord(npt); std::iota(ord.begin(), ord.end(), 0);
-    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return grank[root[a]] < grank[root[b]]; });
+    int unsorted = 0;
+#pragma omp parallel for schedule(static) reduction(|:unsorted)
+    for (int64_t i = 1; i < npt; i++) unsorted |= grank[root[i-1]] > grank[root[i]];
+    if (unsorted) __gnu_parallel::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return grank[root[a]] < grank[root[b]]; });
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < npt; i++) h->pt_new[ord[i]] = (int32_t)i;
     std::vector<int32_t> of(nfl); std::iota(of.begin(), of.end(), 0);
     std::stable_sort(of.begin(), of.end(), [&](int a, int b) { return grank[root[npt + a]] < grank[root[npt + b]]; });
     for (int64_t i = 0; i < nfl; i++) h->fl_new[of[i]] = (int32_t)i;
   }
+  lap("groups + landmark order");
   // ---- band structure
   DevBand& B = h->band;
   B.n = (int)(6*np);
@@ -327,6 +377,7 @@ static int finalize_impl(dynoba_solver* h) {
     CK(cudaMemcpy(da, soa.data(), soa.size()*8, cudaMemcpyHostToDevice));
     h->cur.aux = da; h->cand.aux = da;
   }
+  lap("band + variables upload");
   // ---- factor blocks
   h->supported = true; h->jac_bytes = 96*(np + naux) + 24*npt + 16*nfl;
   int part = 0, bs = 0;
@@ -342,16 +393,34 @@ static int finalize_impl(dynoba_solver* h) {
     if (lslot >= 0) {
       frank.resize(n);
       std::vector<int64_t> key(n);
+#pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < n; i++) {
         frank[i] = grank[root[lmk_id(ti.cls[lslot], b.idx[i*ti.arity + lslot])]];
         key[i] = ((int64_t)frank[i] << 32) | (uint32_t)h->pos[b.idx[i*ti.arity + pslot]];
       }
-      std::stable_sort(b.perm.begin(), b.perm.end(), [&](int a, int c) { return key[a] < key[c]; });
+      int unsorted = 0;
+#pragma omp parallel for schedule(static) reduction(|:unsorted)
+      for (int64_t i = 1; i < n; i++) unsorted |= key[i-1] > key[i];
+      if (unsorted) __gnu_parallel::stable_sort(b.perm.begin(), b.perm.end(), [&](int a, int c) { return key[a] < key[c]; });
     }
+    lap("  blk sort");
     // SoA host images
-    std::vector<int32_t> hidx((size_t)ti.arity*stride, 0);
-    std::vector<double> hmeas((size_t)std::max(ti.meas, 1)*stride, 0.0), hsig((size_t)b.sigma_dim*stride, 1.0);
-    std::vector<int32_t> haux(stride, 0);
+    // staging images: plain new[] (no value-initialisation pass over ~1 GB), padding filled explicitly below
+    struct Buf32 { std::unique_ptr<int32_t[]> p; size_t n; int32_t* data() { return p.get(); } size_t size() const { return n; } int32_t& operator[](size_t i) { return p[i]; } };
+    struct Buf64 { std::unique_ptr<double[]> p; size_t n; double* data() { return p.get(); } size_t size() const { return n; } double& operator[](size_t i) { return p[i]; } };
+    Buf32 hidx{ std::unique_ptr<int32_t[]>(new int32_t[(size_t)ti.arity*stride]), (size_t)ti.arity*stride };
+    Buf64 hmeas{ std::unique_ptr<double[]>(new double[(size_t)std::max(ti.meas, 1)*stride]), (size_t)std::max(ti.meas, 1)*stride };
+    Buf64 hsig{ std::unique_ptr<double[]>(new double[(size_t)b.sigma_dim*stride]), (size_t)b.sigma_dim*stride };
+    Buf32 haux{ std::unique_ptr<int32_t[]>(new int32_t[stride]), (size_t)stride };
+    for (int64_t s = n; s < stride; s++) {
+      for (int k = 0; k < ti.arity; k++) hidx[(size_t)k*stride + s] = 0;
+      for (int k = 0; k < std::max(ti.meas, 1); k++) hmeas[(size_t)k*stride + s] = 0.0;
+      for (int k = 0; k < b.sigma_dim; k++) hsig[(size_t)k*stride + s] = 1.0;
+      haux[s] = 0;
+    }
+    if (ti.meas == 0) for (int64_t s = 0; s < n; s++) hmeas[s] = 0.0;
+    if (!b.has_aux) for (int64_t s = 0; s < n; s++) haux[s] = 0;
+#pragma omp parallel for schedule(static)
     for (int64_t s = 0; s < n; s++) {
       const int64_t o = b.perm[s];
       for (int k = 0; k < ti.arity; k++) {
@@ -362,6 +431,7 @@ static int finalize_impl(dynoba_solver* h) {
       for (int k = 0; k < b.sigma_dim; k++) hsig[(size_t)k*stride + s] = 1.0/(b.bcast ? b.sigma[k] : b.sigma[o*b.sigma_dim + k]);
       if (b.has_aux) haux[s] = b.aux[o];
     }
+    lap("  blk soa fill");
     DevBlock& d = b.dev; d = DevBlock{};
     d.type = b.type; d.n = (int)n; d.stride = stride; d.sigma_dim = b.sigma_dim; d.robust_k = b.robust_k;
     int* di; double* dm; double* ds; int* dax = nullptr; int rc;
@@ -374,21 +444,28 @@ static int finalize_impl(dynoba_solver* h) {
     if ((rc = dalloc(h, &d.b, (size_t)ti.dim*stride))) return rc;
     CK(cudaMemset(d.J, 0, (size_t)ti.dim*ti.jcols*stride*8)); CK(cudaMemset(d.b, 0, (size_t)ti.dim*stride*8));
     if (numeric_grid(b.type, (int)n) > 0) { if ((rc = dalloc(h, &d.num_scratch, (size_t)numeric_grid(b.type, (int)n)))) return rc; }
+    lap("  blk upload+alloc");
     // groups: CSR over every landmark group that has factors in this block; groups this block cannot own alone
     // (several points, or factors in other blocks too) are marked -1 and collected for the general path
     b.simple = false;
     if (lslot >= 0) {
       std::vector<int32_t> gp, gl;
-      for (int64_t s = 0; s < n; s++) {
-        const int64_t o = b.perm[s];
-        if (s == 0 || frank[o] != frank[b.perm[s-1]]) {
-          gp.push_back((int32_t)s);
-          const int l = lmk_id(ti.cls[lslot], b.idx[o*ti.arity + lslot]);
-          const bool simple = ti.nlmk == 1 && gblk[root[l]] == (int)bi && gcount[root[l]] == 1;
-          gl.push_back(simple ? hidx[(size_t)lslot*stride + s] : -1);
+      {   // group boundaries of the sorted factor list, found in parallel segments and concatenated in order
+        const int nseg = std::max(1, std::min<int>(omp_get_max_threads(), (int)(n/65536) + 1));
+        std::vector<std::vector<int32_t>> sgp(nseg), sgl(nseg); std::vector<std::vector<GenRef>> sgen(nseg);
+#pragma omp parallel for schedule(static, 1)
+        for (int t = 0; t < nseg; t++) {
+          const int64_t s0 = n*t/nseg, s1 = n*(t + 1)/nseg;
+          for (int64_t s = s0; s < s1; s++) {
+            const int64_t o = b.perm[s];
+            const int l = lmk_id(ti.cls[lslot], b.idx[o*ti.arity + lslot]);
+            const bool simple = ti.nlmk == 1 && gblk[root[l]] == (int)bi && gcount[root[l]] == 1;
+            if (s == 0 || frank[o] != frank[b.perm[s-1]]) { sgp[t].push_back((int32_t)s); sgl[t].push_back(simple ? hidx[(size_t)lslot*stride + s] : -1); }
+            if (!simple) sgen[t].push_back({ grank[root[l]], (int32_t)bi, (int32_t)s });
+          }
         }
-        const int l = lmk_id(ti.cls[lslot], b.idx[o*ti.arity + lslot]);
-        if (!(ti.nlmk == 1 && gblk[root[l]] == (int)bi && gcount[root[l]] == 1)) gen_refs.push_back({ grank[root[l]], (int32_t)bi, (int32_t)s });
+        for (int t = 0; t < nseg; t++) { gp.insert(gp.end(), sgp[t].begin(), sgp[t].end()); gl.insert(gl.end(), sgl[t].begin(), sgl[t].end());
+                                         gen_refs.insert(gen_refs.end(), sgen[t].begin(), sgen[t].end()); }
       }
       gp.push_back((int32_t)n);
       int* dgp; int* dgl;
@@ -403,46 +480,54 @@ static int finalize_impl(dynoba_solver* h) {
         const int ng = (int)gl.size(), NPs = ti.npose;
         std::vector<unsigned char> gwin(ng, 0), lvar((size_t)NPs*stride, 0);
         std::vector<int32_t> chunk_g0, chunk_nloc, cvars; std::vector<int2> jobs;
-        std::vector<int32_t> stamp(np, -1), gstamp(np, -1);
-        std::vector<int32_t> cur; int cur_g0 = 0, chunk_id = 0;
         int pose_slot[2] = {0, 0}; { int c = 0; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE && c < 2) pose_slot[c++] = k; }
-        auto close_chunk = [&](int g_end) {
-          std::vector<int32_t> sorted = cur; std::sort(sorted.begin(), sorted.end());
-          std::vector<int32_t> local(sorted.size());
-          for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = (int32_t)i;       // position -> local index
-          for (int g = cur_g0; g < g_end; g++) if (gwin[g] == 1)
-            for (int s = gp[g]; s < gp[g+1]; s++) for (int k = 0; k < NPs; k++) lvar[(size_t)k*stride + s] = (unsigned char)stamp[hidx[(size_t)pose_slot[k]*stride + s]];
-          for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = -1;
-          chunk_g0.push_back(cur_g0); chunk_nloc.push_back((int32_t)sorted.size());
-          sorted.resize(WIN_NLOC_MAX, 0); cvars.insert(cvars.end(), sorted.begin(), sorted.end());
-          const int nl_ = chunk_nloc.back(); const int nblk = nl_*(nl_ + 1)/2;
-          for (int st = 0; st*256 < nblk; st++) jobs.push_back(make_int2(chunk_id, st));
-          chunk_id++; cur.clear(); cur_g0 = g_end;
-        };
-        std::vector<int32_t> inchunk(np, -1);
-        for (int g = 0; g < ng; g++) {
-          if (gl[g] < 0) continue;
-          const int T = gp[g+1] - gp[g];
-          bool dup = false; int fresh = 0;
-          if (T > 24) { gwin[g] = 2; continue; }
-          for (int s = gp[g]; s < gp[g+1] && !dup; s++) for (int k = 0; k < NPs; k++) {
-            const int p = hidx[(size_t)pose_slot[k]*stride + s];
-            if (gstamp[p] == g) { dup = true; break; }
-            gstamp[p] = g;
-            if (inchunk[p] != chunk_id) fresh++;
+        // greedy chunking, independently inside parallel segments of the group list (a chunk never crosses a segment)
+        const int nseg = std::max(1, std::min<int>(omp_get_max_threads(), ng/4096 + 1));
+        struct SegOut { std::vector<int32_t> g0, nloc, cv; };
+        std::vector<SegOut> seg(nseg);
+#pragma omp parallel for schedule(static, 1)
+        for (int t = 0; t < nseg; t++) {
+          const int ga = (int)((int64_t)ng*t/nseg), gb_ = (int)((int64_t)ng*(t + 1)/nseg);
+          std::vector<int32_t> stamp(np, -1), gstamp(np, -1), inchunk(np, -1), cur;
+          int cur_g0 = ga, chunk_id = 0; SegOut& out = seg[t];
+          auto close_chunk = [&](int g_end) {
+            std::vector<int32_t> sorted = cur; std::sort(sorted.begin(), sorted.end());
+            for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = (int32_t)i;       // position -> local index
+            for (int g = cur_g0; g < g_end; g++) if (gwin[g] == 1)
+              for (int s_ = gp[g]; s_ < gp[g+1]; s_++) for (int k = 0; k < NPs; k++) lvar[(size_t)k*stride + s_] = (unsigned char)stamp[hidx[(size_t)pose_slot[k]*stride + s_]];
+            for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = -1;
+            out.g0.push_back(cur_g0); out.nloc.push_back((int32_t)sorted.size());
+            sorted.resize(WIN_NLOC_MAX, 0); out.cv.insert(out.cv.end(), sorted.begin(), sorted.end());
+            chunk_id++; cur.clear(); cur_g0 = g_end;
+          };
+          for (int g = ga; g < gb_; g++) {
+            if (gl[g] < 0) continue;
+            const int T = gp[g+1] - gp[g];
+            bool dup = false; int fresh = 0;
+            if (T > 24) { gwin[g] = 2; continue; }
+            for (int s_ = gp[g]; s_ < gp[g+1] && !dup; s_++) for (int k = 0; k < NPs; k++) {
+              const int p_ = hidx[(size_t)pose_slot[k]*stride + s_];
+              if (gstamp[p_] == g) { dup = true; break; }
+              gstamp[p_] = g;
+              if (inchunk[p_] != chunk_id) fresh++;
+            }
+            if (dup) { gwin[g] = 2; continue; }
+            if ((int)cur.size() + fresh > WIN_NLOC_MAX) close_chunk(g);
+            for (int s_ = gp[g]; s_ < gp[g+1]; s_++) for (int k = 0; k < NPs; k++) {
+              const int p_ = hidx[(size_t)pose_slot[k]*stride + s_];
+              if (inchunk[p_] != chunk_id) { inchunk[p_] = chunk_id; cur.push_back(p_); }
+            }
+            gwin[g] = 1;
           }
-          if (dup) { gwin[g] = 2; continue; }
-          if ((int)cur.size() + fresh > WIN_NLOC_MAX) {
-            close_chunk(g);
-            fresh = T*NPs;
-          }
-          for (int s = gp[g]; s < gp[g+1]; s++) for (int k = 0; k < NPs; k++) {
-            const int p = hidx[(size_t)pose_slot[k]*stride + s];
-            if (inchunk[p] != chunk_id) { inchunk[p] = chunk_id; cur.push_back(p); }
-          }
-          gwin[g] = 1;
+          close_chunk(gb_);
         }
-        close_chunk(ng);
+        for (int t = 0; t < nseg; t++) for (size_t c = 0; c < seg[t].g0.size(); c++) {
+          const int chunk_id = (int)chunk_g0.size();
+          chunk_g0.push_back(seg[t].g0[c]); chunk_nloc.push_back(seg[t].nloc[c]);
+          cvars.insert(cvars.end(), seg[t].cv.begin() + c*WIN_NLOC_MAX, seg[t].cv.begin() + (c + 1)*WIN_NLOC_MAX);
+          const int nl_ = seg[t].nloc[c]; const int nblk = nl_*(nl_ + 1)/2;
+          for (int st = 0; st*256 < nblk; st++) jobs.push_back(make_int2(chunk_id, st));
+        }
         chunk_g0.push_back(ng);
         int2* djobs; int* dg0; int* dnl; int* dcv; unsigned char* dlv; unsigned char* dgw;
         if ((rc = dalloc(h, &djobs, jobs.size()))) return rc; if (!jobs.empty()) CK(cudaMemcpy(djobs, jobs.data(), jobs.size()*sizeof(int2), cudaMemcpyHostToDevice));
@@ -455,11 +540,13 @@ static int finalize_impl(dynoba_solver* h) {
         b.use_window = true;
       }
     }
+    lap("  blk groups+windows");
     b.part_off = part; part += linearize_grid((int)n);
     b.bs_off = bs; bs += b.pose_only ? (int)((n + 127)/128) : backsub_grid(d.n_groups);
     const int64_t rd = 4*ti.arity + 8*ti.meas + 8*b.sigma_dim + (b.has_aux ? 4 : 0), wr = 8*(ti.dim*ti.jcols + ti.dim);
     h->jac_bytes += n*(rd + wr);
   }
+  lap("factor blocks");
   // ---- general landmark groups
   h->gen = GeneralGroups{};
   if (!gen_refs.empty()) {
@@ -503,6 +590,7 @@ static int finalize_impl(dynoba_solver* h) {
   { int rc; if ((rc = dalloc(h, &h->partials, (size_t)h->n_partials))) return rc; if ((rc = dalloc(h, &h->scalars, 8))) return rc; if ((rc = dalloc(h, &h->fail, 1))) return rc; }
   CK(cudaMemset(h->scalars, 0, 64)); CK(cudaMemset(h->fail, 0, 4));
   CK(cudaDeviceSynchronize());
+  lap("general groups + sync");
   h->finalized = true; h->linearized = false;
   return DYNOBA_OK;
 }
