@@ -339,12 +339,22 @@ static int finalize_impl(dynoba_solver* h) {
   int bw = 6*spread + 5; if (bw < h->min_bw) bw = h->min_bw; if (bw > B.n - 1) bw = std::max(B.n - 1, 0);
   B.bw = bw; B.NT = std::max((B.n + TILE - 1)/TILE, 1); B.n_pad = B.NT*TILE;
   B.WB = (bw + TILE - 1)/TILE; if (B.NT > 1 && B.WB < 1) B.WB = 1; if (B.WB > B.NT - 1) B.WB = B.NT - 1;
-  B.tile_count = (size_t)B.NT*(B.WB + 1);
-  { // tiles and rhs contiguous so that one all-reduce covers both
-    double* buf; int rc = dalloc(h, &buf, B.tile_count*TILE2 + B.n_pad); if (rc) return rc;
-    B.tiles = buf; B.rhs = buf + B.tile_count*TILE2;
-    if ((rc = dalloc(h, &h->chol_flags, 2*B.tile_count + B.NT))) return rc;
-    if ((rc = dalloc(h, &h->linv, (size_t)B.NT*TILE2))) return rc;
+  // two-directional factorisation when the system is long enough: split at the middle, separator = WB tiles
+  B.two = 0; B.split_lo = B.split_hi = 0; B.NTA = B.NT; B.NTB = 0; B.tiles2 = nullptr; B.rhs2 = nullptr;
+  int min_nt = 8; if (const char* e = getenv("DYNOBA_TWIST_MIN_TILES")) min_nt = atoi(e);
+  if (!getenv("DYNOBA_NO_TWIST") && B.WB >= 1 && B.NT >= std::max(min_nt, 4*B.WB + 4)) {
+    const int KmA = (B.NT - B.WB)/2;
+    B.two = 1; B.split_lo = KmA*TILE; B.split_hi = B.split_lo + B.WB*TILE; B.NTA = KmA + B.WB; B.NTB = B.NT - KmA;
+  }
+  B.tile_count = (size_t)(B.NTA + B.NTB)*(B.WB + 1);
+  { // [tiles A | tiles B | rhs A | rhs B] contiguous so that one all-reduce (and one clear) covers everything
+    const size_t nrhs = (size_t)(B.NTA + B.NTB)*TILE;
+    double* buf; int rc = dalloc(h, &buf, B.tile_count*TILE2 + nrhs); if (rc) return rc;
+    B.tiles = buf; B.tiles2 = buf + (size_t)B.NTA*(B.WB + 1)*TILE2;
+    B.rhs = buf + B.tile_count*TILE2; B.rhs2 = B.rhs + (size_t)B.NTA*TILE;
+    if (B.two) { if ((rc = dalloc(h, &B.dp, (size_t)B.n_pad))) return rc; } else B.dp = B.rhs;
+    if ((rc = dalloc(h, &h->chol_flags, (size_t)(B.NTA + B.NTB)*(2*(B.WB + 1) + 1)))) return rc;
+    if ((rc = dalloc(h, &h->linv, (size_t)(B.NTA + B.NTB)*TILE2))) return rc;
   }
   // ---- variables
   DevVars& V = h->cur;
@@ -636,7 +646,7 @@ static int build_reduced(dynoba_solver* h, double lambda) {
     }
   }
   h->launches += launch_schur_general(h->gen, h->band, lambda, h->fail, h->stream);
-  return allreduce_dev(h, h->band.tiles, h->band.tile_count*TILE2 + h->band.n_pad);
+  return allreduce_dev(h, h->band.tiles, h->band.tile_count*TILE2 + (size_t)(h->band.NTA + h->band.NTB)*TILE);
 }
 // factor + solve + back-substitute; scalars[1] = linearised cost decrease
 static int solve_step(dynoba_solver* h, double lambda) {
@@ -750,10 +760,12 @@ int dynoba_get_reduced_system(dynoba_handle h, double lambda, double* S, double*
   if (!h->linearized) do_linearize(h);
   rc = build_reduced(h, lambda); if (rc) return rc;
   const DevBand& B = h->band;
-  std::vector<double> ht(B.tile_count*TILE2), hr(B.n_pad);
+  std::vector<double> ht(B.tile_count*TILE2), hr((size_t)(B.NTA + B.NTB)*TILE);
   CK(cudaMemcpyAsync(ht.data(), B.tiles, ht.size()*8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(hr.data(), B.rhs, hr.size()*8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  DevBand HB = B;   // host view of the same layout
+  HB.tiles = ht.data(); HB.tiles2 = ht.data() + (size_t)B.NTA*(B.WB + 1)*TILE2; HB.rhs = hr.data(); HB.rhs2 = hr.data() + (size_t)B.NTA*TILE;
   const int n = B.n; const int64_t np = n/6;
   std::vector<int32_t> inv(np); for (int64_t i = 0; i < np; i++) inv[h->pos[i]] = (int32_t)i;
   auto user = [&](int s) { return 6*inv[s/6] + s%6; };
@@ -761,18 +773,18 @@ int dynoba_get_reduced_system(dynoba_handle h, double lambda, double* S, double*
     std::fill(S, S + (size_t)n*n, 0.0);
     for (int j = 0; j < n; j++) for (int i = j; i < n && i <= j + (B.WB + 1)*TILE; i++) {
       const int I = i >> 5, Jt = j >> 5; if (I - Jt > B.WB) break;
-      const double v = ht[band_index(B, i, j)];
+      const double v = *band_at(HB, i, j);
       S[(size_t)user(i)*n + user(j)] = v; S[(size_t)user(j)*n + user(i)] = v;
     }
   }
-  if (g) for (int i = 0; i < n; i++) g[user(i)] = hr[i];
+  if (g) for (int i = 0; i < n; i++) g[user(i)] = *rhs_at(HB, i);
   return DYNOBA_OK;
 }
 
 static int download_delta(dynoba_solver* h, double* delta) {
   const DevBand& B = h->band; const int64_t np = B.n/6, npt = h->cur.nl, nfl = h->cur.nf;
   std::vector<double> hr(B.n_pad), hp((size_t)3*h->cur.nl_stride), hf((size_t)2*h->cur.nf_stride);
-  CK(cudaMemcpyAsync(hr.data(), B.rhs, hr.size()*8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(hr.data(), B.dp, hr.size()*8, cudaMemcpyDeviceToHost, h->stream));
   if (npt) CK(cudaMemcpyAsync(hp.data(), h->dl_point, hp.size()*8, cudaMemcpyDeviceToHost, h->stream));
   if (nfl) CK(cudaMemcpyAsync(hf.data(), h->dl_flow, hf.size()*8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -806,7 +818,7 @@ int dynoba_retract(dynoba_handle h, const double* delta) {
   for (int64_t i = 0; i < npt; i++) for (int c = 0; c < 3; c++) hp[(size_t)c*h->cur.nl_stride + h->pt_new[i]] = dp[3*i + c];
   const double* df = dp + 3*npt;
   for (int64_t i = 0; i < nfl; i++) for (int c = 0; c < 2; c++) hf[(size_t)c*h->cur.nf_stride + h->fl_new[i]] = df[2*i + c];
-  CK(cudaMemcpyAsync(B.rhs, hr.data(), hr.size()*8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(B.dp, hr.data(), hr.size()*8, cudaMemcpyHostToDevice, h->stream));
   if (npt) CK(cudaMemcpyAsync(h->dl_point, hp.data(), hp.size()*8, cudaMemcpyHostToDevice, h->stream));
   if (nfl) CK(cudaMemcpyAsync(h->dl_flow, hf.data(), hf.size()*8, cudaMemcpyHostToDevice, h->stream));
   h->launches += launch_retract(h->cur, h->cand, h->band, h->dl_point, h->dl_flow, h->stream);

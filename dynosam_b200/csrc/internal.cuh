@@ -39,15 +39,36 @@ struct DevBlock {
 
 // Band storage of the reduced (camera + object-motion) system, lower triangle, TILE x TILE tiles:
 // tile (I,J), J <= I <= J+WB at tiles[(J*(WB+1) + (I-J))*TILE2], element (r,c) at c*TILE + r.
+//
+// Two-directional ("twisted") layout: the system may be stored as TWO band problems that share a middle separator M =
+// positions [split_lo, split_hi):  problem A = positions [0, split_hi) in natural order, problem B = positions
+// [split_lo, n_pad) REVERSED (local index n_pad-1-p).  A is eliminated forward, B is eliminated from the far end
+// backwards at the same time; both leave their Schur complement in M, which is summed and factored last.
+// An entry (i >= j) lives in A when i < split_hi, else in B at (n_pad-1-j, n_pad-1-i).
 struct DevBand {
   int n, n_pad, NT, WB, bw;
-  double* tiles;        // [NT*(WB+1)*TILE2]
-  double* rhs;          // [n_pad]   g_S, then y = L^-1 g_S, then delta_p (solver order)
-  size_t tile_count;
+  double* tiles;        // problem A (the whole system when two == 0): [NT_A*(WB+1)*TILE2]
+  double* rhs;          // [NT_A*32]   g_S, then y = L^-1 g_S, then x
+  size_t tile_count;    // tiles of A + tiles of B (one allocation, tiles2 follows tiles, then rhs, rhs2)
+  int two, split_lo, split_hi, NTA, NTB;
+  double* tiles2;       // problem B
+  double* rhs2;
+  double* dp;           // [n_pad] solution delta_p in solver order (== rhs when two == 0)
 };
-__host__ __device__ __forceinline__ size_t band_index(const DevBand& B, int i, int j) {  // requires i >= j
+__host__ __device__ __forceinline__ size_t band_index_wb(int WB, int i, int j) {  // requires i >= j
   const int I = i >> 5, Jt = j >> 5;
-  return ((size_t)Jt*(B.WB + 1) + (I - Jt))*TILE2 + (size_t)(j & 31)*TILE + (i & 31);
+  return ((size_t)Jt*(WB + 1) + (I - Jt))*TILE2 + (size_t)(j & 31)*TILE + (i & 31);
+}
+__host__ __device__ __forceinline__ size_t band_index(const DevBand& B, int i, int j) { return band_index_wb(B.WB, i, j); }
+// address of entry (i >= j) / of rhs element p of the reduced system
+__host__ __device__ __forceinline__ double* band_at(const DevBand& B, int i, int j) {
+  if (!B.two || i < B.split_hi) return B.tiles + band_index_wb(B.WB, i, j);
+  const int np1 = B.n_pad - 1;
+  return B.tiles2 + band_index_wb(B.WB, np1 - j, np1 - i);
+}
+__host__ __device__ __forceinline__ double* rhs_at(const DevBand& B, int p) {
+  if (!B.two || p < B.split_hi) return B.rhs + p;
+  return B.rhs2 + (B.n_pad - 1 - p);
 }
 
 // Landmark groups the per-landmark kernels do not cover (chains of points, landmarks spanning factor blocks):

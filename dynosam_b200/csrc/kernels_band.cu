@@ -175,6 +175,12 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 __device__ long long g_spine_dbg[16];
 #define TS(i) do { const long long t_ = clock64(); if (lane == 0) dbgacc[i] += t_ - tlast; tlast = t_; } while (0)
 
+// One band problem handed to the factorisation kernel: columns [Kbeg, Kend) are factored; tiles in columns >= Kend
+// only receive the updates from the factored columns (their Schur complement), updates from columns < Kbeg are
+// assumed applied already (second phase of the two-directional scheme).
+struct CholProb { double* tiles; double* rhs; int NT, Kbeg, Kend; int* done; int* pre; int* ydone; };
+struct CholJob { CholProb p[2]; int np, WB; };
+
 // Tile roles (dd = I - K):
 //   dd == 0, 1 : workers apply the updates from columns J <= K-2 ("pre"), the spine applies J = K-1 and finishes
 //   dd == 2    : workers apply J <= K-1 ("pre"), the spine does the TRSM
@@ -182,19 +188,20 @@ __device__ long long g_spine_dbg[16];
 // plus one "rhs" task per column that folds the forward substitution y_K = L_KK^-1 (g_K - sum_J L_KJ y_J) in.
 // flags: done[o], pre[o] for tile o = K*(WB+1) + dd;  ydone[K]
 __global__ void __launch_bounds__(CH_WARPS*32)
-band_cholesky_dataflow_kernel(DevBand B, int* __restrict__ done, int* __restrict__ pre, int* __restrict__ ydone,
-                              int* __restrict__ fail) {
+band_cholesky_dataflow_kernel(CholJob job, int* __restrict__ fail) {
   extern __shared__ __align__(16) double chol_smem[];   // [CH_WARPS + 1][TILE2] + [CH_WARPS][32] (+ padding that pins CTAs/SM)
-  double* sspine = chol_smem + (size_t)CH_WARPS*TILE2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NT = B.NT, WB = B.WB, W1 = WB + 1;
+  const int WB = job.WB, W1 = WB + 1;
   double* sb = chol_smem + (size_t)warp*TILE2;
   double* sinv = chol_smem + (size_t)(CH_WARPS + 1)*TILE2 + warp*TILE;
 
-  if (blockIdx.x == 0) {
+  if ((int)blockIdx.x < job.np) {
     // ------------------------------------------------------------------ spine CTA (4 warps, block-wide barriers)
     //   warp 0: potrf(K,K);  warp 1: TRSM (K+1,K);  warp 2: TRSM (K+2,K);  then all four warps split the two
     //   tile updates T(K+1,K+1) -= L(K+1,K) L(K+1,K)^T and T(K+2,K+1) -= L(K+2,K) L(K+1,K)^T by column halves.
+    const CholProb P = job.p[blockIdx.x];
+    int* done = P.done; int* pre = P.pre;
+    const int NT = P.NT;
     double* sLt  = chol_smem;                       // [32*LT_STRIDE] row-major L_KK
     double* sX1  = chol_smem + 1152;                // [1024] L(K+1,K), sX1[k*32 + r]
     double* sX2  = sX1 + TILE2;                     // [1024] L(K+2,K)
@@ -204,15 +211,16 @@ band_cholesky_dataflow_kernel(DevBand B, int* __restrict__ done, int* __restrict
     double* sIv  = sP + 256;                        // [32]   1 / diag(L_KK)
     double r[TILE];                                 // warp 0: diagonal tile row; warp 1: x1 row; warp 2: x2 row
     long long dbgacc[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long tlast = clock64();
-    if (warp == 0) { wait_flag(pre + 0, lane); tile_load(B.tiles, r, lane); }
-    if (warp == 1 && NT > 1) { wait_flag(pre + 1, lane); tile_load(B.tiles + TILE2, r, lane); }
-    for (int K = 0; K < NT; K++) {
+    if (P.Kbeg >= P.Kend) return;
+    if (warp == 0) { wait_flag(pre + (size_t)P.Kbeg*W1, lane); tile_load(P.tiles + (size_t)P.Kbeg*W1*TILE2, r, lane); }
+    if (warp == 1 && P.Kbeg + 1 < NT) { wait_flag(pre + (size_t)P.Kbeg*W1 + 1, lane); tile_load(P.tiles + ((size_t)P.Kbeg*W1 + 1)*TILE2, r, lane); }
+    for (int K = P.Kbeg; K < P.Kend; K++) {
       const size_t oD = (size_t)K*W1;
       if (warp == 0) {
         TS(11);
         if (!warp_potrf_blocked(r, lane, sP) && lane == 0) atomicOr(fail, 2);
         TS(0);
-        tile_store(B.tiles + oD*TILE2, r, lane);
+        tile_store(P.tiles + oD*TILE2, r, lane);
 #pragma unroll
         for (int c = 0; c < TILE; c += 2) *reinterpret_cast<double2*>(sLt + lane*LT_STRIDE + c) = make_double2(r[c], r[c + 1]);
         double dg = 1.0;
@@ -228,15 +236,15 @@ band_cholesky_dataflow_kernel(DevBand B, int* __restrict__ done, int* __restrict
       double h[16];
       if (warp == 1) {
         tile_trsm_rm(r, sLt, sIv);
-        tile_store(B.tiles + (oD + 1)*TILE2, r, lane);
+        tile_store(P.tiles + (oD + 1)*TILE2, r, lane);
         tile_stage(sX1, r, lane);
         set_flag(done + oD + 1, lane);
       } else if (warp == 2) {
         if (has2) {
           wait_flag(pre + oD + 2, lane);
-          tile_load(B.tiles + (oD + 2)*TILE2, r, lane);
+          tile_load(P.tiles + (oD + 2)*TILE2, r, lane);
           tile_trsm_rm(r, sLt, sIv);
-          tile_store(B.tiles + (oD + 2)*TILE2, r, lane);
+          tile_store(P.tiles + (oD + 2)*TILE2, r, lane);
           tile_stage(sX2, r, lane);
           set_flag(done + oD + 2, lane);
         }
@@ -244,7 +252,7 @@ band_cholesky_dataflow_kernel(DevBand B, int* __restrict__ done, int* __restrict
         TS(2);
         const int c0 = warp == 0 ? 16 : 0;
         wait_flag(pre + oD + W1, lane);
-        const double* t = B.tiles + (oD + W1)*TILE2;
+        const double* t = P.tiles + (oD + W1)*TILE2;
 #pragma unroll
         for (int j = 0; j < 16; j++) h[j] = __ldcg(t + (c0 + j)*TILE + lane);
         TS(3);
@@ -262,7 +270,7 @@ band_cholesky_dataflow_kernel(DevBand B, int* __restrict__ done, int* __restrict
       } else if (hasn) {
         const int c0 = warp == 1 ? 16 : 0;
         wait_flag(pre + oD + W1 + 1, lane);
-        const double* t = B.tiles + (oD + W1 + 1)*TILE2;
+        const double* t = P.tiles + (oD + W1 + 1)*TILE2;
 #pragma unroll
         for (int j = 0; j < 16; j++) h[j] = __ldcg(t + (c0 + j)*TILE + lane);
         if (has2) {
@@ -285,90 +293,128 @@ band_cholesky_dataflow_kernel(DevBand B, int* __restrict__ done, int* __restrict
         for (int c = 0; c < TILE; c++) r[c] = sXn[c*TILE + lane];
       }
     }
-    if (warp == 0 && lane == 0) for (int i = 0; i < 12; i++) g_spine_dbg[i] = dbgacc[i];
+    // columns >= Kend are not factored here: hand the two partially updated tiles of column Kend back
+    if (P.Kend < NT) {
+      if (warp == 0) tile_store(P.tiles + (size_t)P.Kend*W1*TILE2, r, lane);
+      if (warp == 1 && P.Kend + 1 < NT) tile_store(P.tiles + ((size_t)P.Kend*W1 + 1)*TILE2, r, lane);
+    }
+    if (blockIdx.x == 0 && warp == 0 && lane == 0) for (int i = 0; i < 12; i++) g_spine_dbg[i] = dbgacc[i];
     return;
   }
   // -------------------------------------------------------------------- workers
-  const int nworkers = (gridDim.x - 1)*CH_WARPS;
-  const int wid = (blockIdx.x - 1)*CH_WARPS + warp;
+  const int nworkers = ((int)gridDim.x - job.np)*CH_WARPS;
+  const int wid = ((int)blockIdx.x - job.np)*CH_WARPS + warp;
   const int W2 = W1 + 1;                                 // tile tasks + the rhs task of the column
-  const long long ntasks = (long long)NT*W2;
-  for (long long o2 = wid; o2 < ntasks; o2 += nworkers) {
-    const int K = (int)(o2/W2), dd = (int)(o2 - (long long)K*W2), I = K + dd;
+  int ncols = 0;
+  for (int q = 0; q < job.np; q++) ncols = max(ncols, job.p[q].NT - job.p[q].Kbeg);
+  const long long per_col = (long long)job.np*W2;
+  const long long ntasks = (long long)ncols*per_col;
+  for (long long t = wid; t < ntasks; t += nworkers) {
+    const int c = (int)(t/per_col); const int rem = (int)(t - (long long)c*per_col);
+    const int q = rem/W2, dd = rem - q*W2;
+    const CholProb P = job.p[q];
+    int* done = P.done; int* pre = P.pre; int* ydone = P.ydone;
+    const int NT = P.NT, K = P.Kbeg + c, I = K + dd;
+    if (K >= NT) continue;
     if (dd == W1) {
-      // ---- rhs task: y_K = L_KK^-1 (g_K - sum_{J<K} L_KJ y_J)
-      double v = B.rhs[(size_t)K*TILE + lane];
-      for (int J = max(0, K - WB); J < K; J++) {
+      // ---- rhs task: y_K = L_KK^-1 (g_K - sum_{J<K} L_KJ y_J); rows >= Kend only collect the factored columns' part
+      double v = P.rhs[(size_t)K*TILE + lane];
+      const int Jend = min(K, P.Kend);
+      for (int J = max(P.Kbeg, K - WB); J < Jend; J++) {
         const size_t oK = (size_t)J*W1 + (K - J);
         wait_flag(done + oK, lane);
         double a[TILE];
-        tile_load(B.tiles + oK*TILE2, a, lane);
+        tile_load(P.tiles + oK*TILE2, a, lane);
         wait_flag(ydone + J, lane);
-        const double yj = __ldcg(B.rhs + (size_t)J*TILE + lane);
+        const double yj = __ldcg(P.rhs + (size_t)J*TILE + lane);
 #pragma unroll
         for (int k = 0; k < TILE; k++) v -= a[k]*__shfl_sync(0xffffffffu, yj, k);
       }
+      if (K >= P.Kend) { P.rhs[(size_t)K*TILE + lane] = v; continue; }
       wait_flag(done + (size_t)K*W1, lane);
       double l[TILE];
-      tile_load(B.tiles + (size_t)K*W1*TILE2, l, lane);
+      tile_load(P.tiles + (size_t)K*W1*TILE2, l, lane);
       double y = 0.0, mydiag = 1.0;
 #pragma unroll
-      for (int c = 0; c < TILE; c++) if (lane == c) mydiag = l[c];
+      for (int cc = 0; cc < TILE; cc++) if (lane == cc) mydiag = l[cc];
       const double rinv = 1.0/mydiag;
 #pragma unroll
-      for (int c = 0; c < TILE; c++) {
-        const double yc = __shfl_sync(0xffffffffu, v, c)*__shfl_sync(0xffffffffu, rinv, c);
-        if (lane == c) y = yc;
-        if (lane > c) v -= l[c]*yc;
+      for (int cc = 0; cc < TILE; cc++) {
+        const double yc = __shfl_sync(0xffffffffu, v, cc)*__shfl_sync(0xffffffffu, rinv, cc);
+        if (lane == cc) y = yc;
+        if (lane > cc) v -= l[cc]*yc;
       }
-      B.rhs[(size_t)K*TILE + lane] = y;
+      P.rhs[(size_t)K*TILE + lane] = y;
       set_flag(ydone + K, lane);
       continue;
     }
     if (I >= NT) continue;
     const size_t o = (size_t)K*W1 + dd;
     double acc[TILE];
-    double* t = B.tiles + o*TILE2;
-    tile_load(t, acc, lane);
-    const int Jlo = max(0, I - WB), Jhi = (dd <= 1) ? K - 2 : K - 1;
+    double* tp = P.tiles + o*TILE2;
+    tile_load(tp, acc, lane);
+    const int Jlo = max(P.Kbeg, I - WB);
+    const int Jhi = min((dd <= 1) ? K - 2 : K - 1, P.Kend - 1);
     for (int J = Jlo; J <= Jhi; J++) {
       const size_t oI = (size_t)J*W1 + (I - J), oK = (size_t)J*W1 + (K - J);
       wait_flag(done + oK, lane);
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < TILE; c++) sb[c*TILE + lane] = __ldcg(B.tiles + oK*TILE2 + c*TILE + lane);
+      for (int cc = 0; cc < TILE; cc++) sb[cc*TILE + lane] = __ldcg(P.tiles + oK*TILE2 + cc*TILE + lane);
       wait_flag(done + oI, lane);
       double a[TILE];
-      tile_load(B.tiles + oI*TILE2, a, lane);
+      tile_load(P.tiles + oI*TILE2, a, lane);
       __syncwarp();
       tile_gemm_sub(acc, a, sb);
     }
-    if (dd <= 2) {
-      tile_store(t, acc, lane);
+    if (dd <= 2 || K >= P.Kend) {
+      tile_store(tp, acc, lane);
       set_flag(pre + o, lane);
     } else {
       const size_t oD = (size_t)K*W1;
       wait_flag(done + oD, lane);
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < TILE; c++) sb[c*TILE + lane] = __ldcg(B.tiles + oD*TILE2 + c*TILE + lane);
+      for (int cc = 0; cc < TILE; cc++) sb[cc*TILE + lane] = __ldcg(P.tiles + oD*TILE2 + cc*TILE + lane);
       __syncwarp();
       sinv[lane] = 1.0/sb[lane*TILE + lane];
       __syncwarp();
       tile_trsm(acc, sb, sinv);
-      tile_store(t, acc, lane);
+      tile_store(tp, acc, lane);
       set_flag(done + o, lane);
     }
   }
 }
 
+// sums the two Schur complements left in the middle separator: A.M += flip(B.M), A.rhs_M += flip(B.rhs_M)
+__global__ void merge_middle_kernel(DevBand B) {
+  const int np1 = B.n_pad - 1, lo = B.split_lo, hi = B.split_hi, s = hi - lo;
+  const long long total = (long long)s*s;
+  for (long long e = (long long)blockIdx.x*blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x*blockDim.x) {
+    const int i = lo + (int)(e/s), j = lo + (int)(e%s);
+    if (j > i) continue;
+    B.tiles[band_index_wb(B.WB, i, j)] += B.tiles2[band_index_wb(B.WB, np1 - j, np1 - i)];
+  }
+  for (int p = lo + blockIdx.x*blockDim.x + threadIdx.x; p < hi; p += gridDim.x*blockDim.x) B.rhs[p] += B.rhs2[np1 - p];
+}
+// x_M (solved in A) -> the reversed copy that primes B's backward sweep
+__global__ void prime_back_kernel(DevBand B) {
+  const int np1 = B.n_pad - 1;
+  for (int p = B.split_lo + blockIdx.x*blockDim.x + threadIdx.x; p < B.split_hi; p += gridDim.x*blockDim.x) B.rhs2[np1 - p] = B.rhs[p];
+}
+__global__ void gather_solution_kernel(DevBand B) {
+  const int np1 = B.n_pad - 1;
+  for (int p = blockIdx.x*blockDim.x + threadIdx.x; p < B.n_pad; p += gridDim.x*blockDim.x)
+    B.dp[p] = p < B.split_hi ? B.rhs[p] : B.rhs2[np1 - p];
+}
+
 // explicit inverse of every diagonal tile: Linv[K] = L_KK^-1 (lower triangular), one warp per tile
-__global__ void __launch_bounds__(128) diag_inverse_kernel(DevBand B, double* __restrict__ linv) {
+__global__ void __launch_bounds__(128) diag_inverse_kernel(const double* __restrict__ tiles, int NT, int WB, double* __restrict__ linv) {
   __shared__ double sL[4][TILE2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = blockIdx.x*4 + warp;
-  if (K >= B.NT) return;
-  const double* t = B.tiles + (size_t)K*(B.WB + 1)*TILE2;
+  if (K >= NT) return;
+  const double* t = tiles + (size_t)K*(WB + 1)*TILE2;
   double* s = sL[warp];
 #pragma unroll
   for (int c = 0; c < TILE; c++) s[c*TILE + lane] = t[c*TILE + lane];
@@ -402,87 +448,41 @@ __device__ __forceinline__ double warp_transpose_sum(double (&v)[TILE], int lane
   return v[0];
 }
 
-constexpr int SV_WARPS = 16;
-// forward sweep  y_K = Linv_KK (g_K - sum_{J<K} L_KJ y_J); rhs overwritten
-__global__ void __launch_bounds__(SV_WARPS*32) band_forward_kernel(DevBand B, const double* __restrict__ linv) {
-  extern __shared__ double sm[];
-  const int NT = B.NT, WB = B.WB, W1 = WB + 1, ring = WB + 1;
-  double* xs = sm;                      // ring buffer of solved blocks: [ring][32]
-  double* part = sm + (size_t)ring*TILE; // [SV_WARPS][32]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int K = 0; K < NT; K++) {
-    const int nleft = min(WB, K);
-    double s = 0.0;
-    // tiles (K, J = K-1-q), q = warp-1, warp-1+31, ...
-    double t[TILE]; int q = warp - 1; bool have = false;
-    if (warp > 0 && q < nleft) {
-      const int J = K - 1 - q;
-      const double* tp = B.tiles + ((size_t)J*W1 + (K - J))*TILE2;
-#pragma unroll
-      for (int k = 0; k < TILE; k++) t[k] = tp[k*TILE + lane];
-      have = true;
-    }
-    __syncthreads();                    // y_{K-1} visible in the ring
-    if (warp > 0) {
-      while (have) {
-        const int J = K - 1 - q;
-        const double* y = xs + (size_t)(J % ring)*TILE;
-#pragma unroll
-        for (int k = 0; k < TILE; k++) s += t[k]*y[k];
-        q += SV_WARPS - 1; have = q < nleft;
-        if (have) {
-          const int J2 = K - 1 - q;
-          const double* tp = B.tiles + ((size_t)J2*W1 + (K - J2))*TILE2;
-#pragma unroll
-          for (int k = 0; k < TILE; k++) t[k] = tp[k*TILE + lane];
-        }
-      }
-      part[warp*TILE + lane] = s;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double v = B.rhs[(size_t)K*TILE + lane];
-      const int nw = min(nleft, SV_WARPS - 1);
-      for (int w = 1; w <= nw; w++) v -= part[w*TILE + lane];
-      const double* li = linv + (size_t)K*TILE2;
-      double y = 0.0;
-#pragma unroll
-      for (int k = 0; k < TILE; k++) y += li[k*TILE + lane]*__shfl_sync(0xffffffffu, v, k);   // Linv[lane][k] v[k]
-      xs[(size_t)(K % ring)*TILE + lane] = y;
-      B.rhs[(size_t)K*TILE + lane] = y;
-    }
-  }
-}
-
-// backward sweep  x_J = Linv_JJ^T (y_J - sum_{I>J} L_IJ^T x_I); rhs overwritten.
-// One thread-block CLUSTER of 8 CTAs (8 SMs): the off-diagonal tiles of a column are spread over 8 x 4 warps so the
-// 240 KB a column reads come through eight SMs' load paths; per-CTA partial sums travel to rank 0 through
-// distributed shared memory, rank 0 applies the inverse diagonal tile and broadcasts x_J into every CTA's ring.
+// backward sweep  x_J = Linv_JJ^T (y_J - sum_{I>J} L_IJ^T x_I) for J = Jtop-1 ... Jbot; rhs overwritten.
+// One thread-block CLUSTER of 8 CTAs (8 SMs) per band problem: the off-diagonal tiles of a column are spread over
+// 8 x 4 warps so the 240 KB a column reads come through eight SMs' load paths; per-CTA partial sums are all-gathered
+// through distributed shared memory and every CTA finishes x_J itself (one cluster barrier per column).
+// Columns >= Jtop are already solved (the middle separator of the two-directional scheme): their x primes the ring.
+struct BackProb { const double* tiles; double* rhs; const double* linv; int NT, Jtop, Jbot; };
+struct BackJob { BackProb p[2]; int WB; };
 constexpr int BW_CL = 8, BW_TW = 4;      // cluster size, tile warps per CTA
 __global__ void __cluster_dims__(BW_CL, 1, 1) __launch_bounds__((BW_TW + 1)*32)
-band_backward_cluster_kernel(DevBand B, const double* __restrict__ linv) {
+band_backward_cluster_kernel(BackJob job) {
   extern __shared__ double sm[];
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();
-  const int NT = B.NT, WB = B.WB, W1 = WB + 1, ring = WB + 1;
+  const BackProb P = job.p[blockIdx.x/BW_CL];
+  const int NT = P.NT, WB = job.WB, W1 = WB + 1, ring = WB + 1;
   double* xs = sm;                                   // [ring][32] solved blocks (replicated in every CTA)
   double* lpart = sm + (size_t)ring*TILE;            // [BW_TW][32] partial sums of this CTA's tile warps
   double* cpart = lpart + BW_TW*TILE;                // [2][BW_CL][32] all-gathered per-CTA partials
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int I = P.Jtop + warp; I < min(NT, P.Jtop + WB); I += BW_TW + 1) xs[(size_t)(I % ring)*TILE + lane] = P.rhs[(size_t)I*TILE + lane];
+  __syncthreads();
   // software prefetch: the tile this warp needs for column J-1 is loaded while column J is processed
   const int myq = rank*BW_TW + (warp - 1);
   double tn[TILE];
   auto prefetch = [&](int J) {
-    if (warp >= 1 && J >= 0 && myq < min(WB, NT - 1 - J)) {
-      const double* tp = B.tiles + (size_t)J*W1*TILE2 + (size_t)(myq + 1)*TILE2;
+    if (warp >= 1 && J >= P.Jbot && myq < min(WB, NT - 1 - J)) {
+      const double* tp = P.tiles + (size_t)J*W1*TILE2 + (size_t)(myq + 1)*TILE2;
 #pragma unroll
       for (int c = 0; c < TILE; c++) tn[c] = tp[c*TILE + lane];
     }
   };
-  prefetch(NT - 1);
-  for (int J = NT - 1; J >= 0; J--) {
+  prefetch(P.Jtop - 1);
+  for (int J = P.Jtop - 1; J >= P.Jbot; J--) {
     const int nbelow = min(WB, NT - 1 - J);
-    const double* colJ = B.tiles + (size_t)J*W1*TILE2;
+    const double* colJ = P.tiles + (size_t)J*W1*TILE2;
     if (warp >= 1) {
       double s = 0.0;
       double t[TILE];
@@ -512,23 +512,22 @@ band_backward_cluster_kernel(DevBand B, const double* __restrict__ linv) {
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < BW_TW; w++) s += lpart[w*TILE + lane];
-      // all-gather of the per-CTA partials through distributed shared memory (double-buffered by column parity)
 #pragma unroll
       for (int r = 0; r < BW_CL; r++) cl.map_shared_rank(cpart, r)[((J & 1)*BW_CL + rank)*TILE + lane] = s;
-      const double* lp = linv + (size_t)J*TILE2;                       // every CTA finishes x_J itself: no second barrier
+      const double* lp = P.linv + (size_t)J*TILE2;
 #pragma unroll
       for (int c = 0; c < TILE; c++) li[c] = lp[c*TILE + lane];
     }
     cl.sync();
     if (warp == 0) {
-      double v = B.rhs[(size_t)J*TILE + lane];
+      double v = P.rhs[(size_t)J*TILE + lane];
 #pragma unroll
       for (int r = 0; r < BW_CL; r++) v -= cpart[((J & 1)*BW_CL + r)*TILE + lane];
 #pragma unroll
       for (int c = 0; c < TILE; c++) li[c] *= v;                      // Linv[lane][c] * v[lane]
       const double x = warp_transpose_sum(li, lane);                  // lane c: sum_r Linv[r][c] v[r]
       xs[(size_t)(J % ring)*TILE + lane] = x;
-      if (rank == 0) B.rhs[(size_t)J*TILE + lane] = x;
+      if (rank == 0) P.rhs[(size_t)J*TILE + lane] = x;
     }
     __syncthreads();
   }
@@ -537,47 +536,86 @@ band_backward_cluster_kernel(DevBand B, const double* __restrict__ linv) {
 static int g_max_blocks = 0;
 static size_t g_chol_smem = 0;
 
-int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, cudaStream_t s) {
-  if (!g_max_blocks) {
-    int dev = 0, sms = 0, per = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // CTAs per SM: 1 keeps the spine warp alone on its scheduler (DYNOBA_CHOL_BPS overrides for experiments)
-    int bps = 1; if (const char* e = getenv("DYNOBA_CHOL_BPS")) bps = atoi(e) > 0 ? atoi(e) : 1;
-    const size_t need = (size_t)(1152 + 4*TILE2 + 256 + 64)*sizeof(double);
-    g_chol_smem = std::max(need, (size_t)(220*1024)/bps - 2048);
-    cudaFuncSetAttribute(band_cholesky_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_chol_smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, band_cholesky_dataflow_kernel, CH_WARPS*32, g_chol_smem);
-    g_max_blocks = sms*(per > 0 ? per : 1);
-  }
-  const size_t nflags = (size_t)B.NT*(B.WB + 1);
-  cudaMemsetAsync(flags, 0, (2*nflags + B.NT)*sizeof(int), s);
+static void chol_init() {
+  if (g_max_blocks) return;
+  int dev = 0, sms = 0, per = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // CTAs per SM: 1 keeps each spine CTA alone on its SM (DYNOBA_CHOL_BPS overrides for experiments)
+  int bps = 1; if (const char* e = getenv("DYNOBA_CHOL_BPS")) bps = atoi(e) > 0 ? atoi(e) : 1;
+  const size_t need = (size_t)(1152 + 4*TILE2 + 256 + 64)*sizeof(double);
+  g_chol_smem = std::max(need, (size_t)(220*1024)/bps - 2048);
+  cudaFuncSetAttribute(band_cholesky_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_chol_smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, band_cholesky_dataflow_kernel, CH_WARPS*32, g_chol_smem);
+  g_max_blocks = sms*(per > 0 ? per : 1);
+}
+static void chol_launch(const CholJob& job, int* fail, cudaStream_t s) {
+  long long ntile = 0;
+  for (int q = 0; q < job.np; q++) ntile += (long long)(job.p[q].NT - job.p[q].Kbeg)*(job.WB + 2);
   int grid = g_max_blocks;
-  const long long want = ((long long)nflags + B.NT + 1 + CH_WARPS - 1)/CH_WARPS + 1;
+  const long long want = (ntile + CH_WARPS - 1)/CH_WARPS + job.np;
   if (grid > want) grid = (int)want;
-  if (grid < 2) grid = 2;
-  DevBand Bc = B; int* done = flags; int* pre = flags + nflags; int* ydone = flags + 2*nflags;
-  void* args[] = { (void*)&Bc, (void*)&done, (void*)&pre, (void*)&ydone, (void*)&fail };
+  if (grid < job.np + 1) grid = job.np + 1;
+  CholJob j = job;
+  void* args[] = { (void*)&j, (void*)&fail };
   // cooperative launch only for its co-residency guarantee (the flag waits need every warp resident)
   cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel, dim3(grid), dim3(CH_WARPS*32), args, g_chol_smem, s);
-  diag_inverse_kernel<<<(B.NT + 3)/4, 128, 0, s>>>(B, linv);
+}
+
+int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, cudaStream_t s) {
+  chol_init();
+  const int W1 = B.WB + 1;
+  const int NTA = B.two ? B.NTA : B.NT, NTB = B.two ? B.NTB : 0;
+  const size_t nfl = (size_t)(NTA + NTB)*(2*W1 + 1);
+  cudaMemsetAsync(flags, 0, nfl*sizeof(int), s);
+  int* fA = flags; int* fB = flags + (size_t)NTA*(2*W1 + 1);
+  auto prob = [&](double* tiles, double* rhs, int NT, int kb, int ke, int* f) {
+    CholProb p; p.tiles = tiles; p.rhs = rhs; p.NT = NT; p.Kbeg = kb; p.Kend = ke; p.done = f; p.pre = f + (size_t)NT*W1; p.ydone = f + (size_t)2*NT*W1; return p; };
+  int launches = 0;
+  if (!B.two) {
+    CholJob job; job.np = 1; job.WB = B.WB; job.p[0] = prob(B.tiles, B.rhs, B.NT, 0, B.NT, fA); job.p[1] = job.p[0];
+    chol_launch(job, fail, s); launches++;
+    diag_inverse_kernel<<<(B.NT + 3)/4, 128, 0, s>>>(B.tiles, B.NT, B.WB, linv); launches++;
+  } else {
+    const int KmA = B.split_lo/TILE, KmB = NTB - (B.split_hi - B.split_lo)/TILE;
+    CholJob job; job.np = 2; job.WB = B.WB;
+    job.p[0] = prob(B.tiles, B.rhs, NTA, 0, KmA, fA); job.p[1] = prob(B.tiles2, B.rhs2, NTB, 0, KmB, fB);
+    chol_launch(job, fail, s); launches++;                               // both halves, towards the middle
+    merge_middle_kernel<<<64, 256, 0, s>>>(B); launches++;
+    cudaMemsetAsync(fA, 0, (size_t)NTA*(2*W1 + 1)*sizeof(int), s);
+    CholJob mid; mid.np = 1; mid.WB = B.WB; mid.p[0] = prob(B.tiles, B.rhs, NTA, KmA, NTA, fA); mid.p[1] = mid.p[0];
+    chol_launch(mid, fail, s); launches++;                               // the middle separator
+    diag_inverse_kernel<<<(NTA + 3)/4, 128, 0, s>>>(B.tiles, NTA, B.WB, linv); launches++;
+    diag_inverse_kernel<<<(KmB + 3)/4, 128, 0, s>>>(B.tiles2, KmB, B.WB, linv + (size_t)NTA*TILE2); launches++;
+  }
   if (getenv("DYNOBA_SPINE_DBG")) {
     long long hd[16]; cudaStreamSynchronize(s); cudaMemcpyFromSymbol(hd, g_spine_dbg, sizeof(hd));
     const char* nm[12] = {"potrf", "store+stage+flag D", "barA", "wait+load Dnext half", "barB (trsm)", "gemm half + stage", "barC + reload", "-", "-", "-", "-", "loop"};
-    for (int i = 0; i < 12; i++) fprintf(stderr, "[spine] %-22s %10.3f ms  (%.0f cyc/col)\n", nm[i], hd[i]/1.965e6, (double)hd[i]/B.NT);
+    for (int i = 0; i < 12; i++) fprintf(stderr, "[spine] %-22s %10.3f ms\n", nm[i], hd[i]/1.965e6);
   }
-  return 3;
+  return launches;
 }
 
 int launch_band_solve(const DevBand& B, const double* linv, cudaStream_t s) {
   const size_t smem = ((size_t)(B.WB + 1)*TILE + (size_t)(BW_TW + 2*BW_CL)*TILE)*sizeof(double);
   static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(band_backward_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-    attr = true;
+  if (!attr) { cudaFuncSetAttribute(band_backward_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024); attr = true; }
+  const int nthr = (BW_TW + 1)*32;
+  if (!B.two) {
+    BackJob job; job.WB = B.WB; job.p[0] = BackProb{ B.tiles, B.rhs, linv, B.NT, B.NT, 0 }; job.p[1] = job.p[0];
+    band_backward_cluster_kernel<<<BW_CL, nthr, smem, s>>>(job);          // forward sweep: folded into the factorisation
+    return 1;
   }
-  band_backward_cluster_kernel<<<BW_CL, (BW_TW + 1)*32, smem, s>>>(B, linv);   // forward sweep: folded into the factorisation
-  return 1;
+  const int NTA = B.NTA, NTB = B.NTB, KmA = B.split_lo/TILE, KmB = NTB - (B.split_hi - B.split_lo)/TILE;
+  BackJob mid; mid.WB = B.WB; mid.p[0] = BackProb{ B.tiles, B.rhs, linv, NTA, NTA, KmA }; mid.p[1] = mid.p[0];
+  band_backward_cluster_kernel<<<BW_CL, nthr, smem, s>>>(mid);            // x of the middle separator
+  prime_back_kernel<<<8, 256, 0, s>>>(B);
+  BackJob job; job.WB = B.WB;
+  job.p[0] = BackProb{ B.tiles, B.rhs, linv, NTA, KmA, 0 };
+  job.p[1] = BackProb{ B.tiles2, B.rhs2, linv + (size_t)NTA*TILE2, NTB, KmB, 0 };
+  band_backward_cluster_kernel<<<2*BW_CL, nthr, smem, s>>>(job);          // both halves, away from the middle
+  gather_solution_kernel<<<148, 256, 0, s>>>(B);
+  return 4;
 }
 
 }  // namespace dynoba

@@ -146,7 +146,7 @@ schur_general_kernel(const DevBlock* __restrict__ blocks, const int* __restrict_
     }
     for (int s = 0; s < v.np; s++) {
       const int pos = v.pose(s);
-      for (int c = 0; c < 6; c++) { double a = 0; for (int r = 0; r < 3; r++) a += v.J(r, v.pcol[s] + c)*rb[r]; atomicAdd(&B.rhs[pos*6 + c], a); }
+      for (int c = 0; c < 6; c++) { double a = 0; for (int r = 0; r < 3; r++) a += v.J(r, v.pcol[s] + c)*rb[r]; atomicAdd(rhs_at(B, pos*6 + c), a); }
     }
   }
   // factor pairs
@@ -176,10 +176,10 @@ schur_general_kernel(const DevBlock* __restrict__ blocks, const int* __restrict_
             if (same && c2 > c) continue;
             const double m = ai[0]*PA[c2] + ai[1]*PA[6 + c2] + ai[2]*PA[12 + c2];
             const int row = a*6 + c, col = b*6 + c2;
-            if (a > b || same) atomicAdd(&B.tiles[band_index(B, row, col)], m);
-            else if (a < b) atomicAdd(&B.tiles[band_index(B, col, row)], m);
+            if (a > b || same) atomicAdd(band_at(B, row, col), m);
+            else if (a < b) atomicAdd(band_at(B, col, row), m);
             else { const int hi = row > col ? row : col, lo = row > col ? col : row;
-                   atomicAdd(&B.tiles[band_index(B, hi, lo)], c == c2 ? 2.0*m : m); }
+                   atomicAdd(band_at(B, hi, lo), c == c2 ? 2.0*m : m); }
           }
         }
       }
@@ -209,7 +209,7 @@ backsub_general_kernel(const DevBlock* __restrict__ blocks, const int* __restric
         const FView v = make_view(blocks, rf[q]);
         double u[3] = {0, 0, 0};
         for (int s = 0; s < v.np; s++) { const int pos = v.pose(s);
-          for (int r = 0; r < 3; r++) for (int c = 0; c < 6; c++) u[r] += v.J(r, v.pcol[s] + c)*B.rhs[pos*6 + c]; }
+          for (int r = 0; r < 3; r++) for (int c = 0; c < 6; c++) u[r] += v.J(r, v.pcol[s] + c)*B.dp[pos*6 + c]; }
         if (lane == 0) for (int r = 0; r < 3; r++) q1 += v.rhs(r)*u[r];
         if (lane < 3*v.nl) {
           const int t = lane/3, c = lane%3;

@@ -62,13 +62,14 @@ __global__ void band_clear_kernel(DevBand B, double lambda, int add_damping) {
   const size_t total = B.tile_count*TILE2;
   const size_t stride = (size_t)gridDim.x*blockDim.x;
   for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < total; i += stride) B.tiles[i] = 0.0;
-  for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < (size_t)B.n_pad; i += stride) B.rhs[i] = 0.0;
+  const size_t nrhs = B.two ? (size_t)(B.NTA + B.NTB)*TILE : (size_t)B.n_pad;   // rhs2 follows rhs
+  for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < nrhs; i += stride) B.rhs[i] = 0.0;
 }
 __global__ void band_diag_kernel(DevBand B, double lambda, int add_damping) {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= B.n_pad) return;
   const double v = i < B.n ? (add_damping ? lambda : 0.0) : 1.0;
-  B.tiles[band_index(B, i, i)] = v;
+  *band_at(B, i, i) = v;
 }
 int launch_band_clear(const DevBand& B, double lambda, int add_damping, cudaStream_t s) {
   band_clear_kernel<<<148*8, 256, 0, s>>>(B, lambda, add_damping);
@@ -164,7 +165,7 @@ schur_simple_kernel(DevBlock blk, const unsigned char* __restrict__ grp_win, Dev
         double a = 0;
 #pragma unroll
         for (int r = 0; r < D; r++) a += el(r*JC + PCOL0 + 6*sl + c, i)*rb[r];
-        atomicAdd(&B.rhs[pos*6 + c], a);
+        atomicAdd(rhs_at(B, pos*6 + c), a);
       }
     }
   }
@@ -230,11 +231,11 @@ schur_simple_kernel(DevBlock blk, const unsigned char* __restrict__ grp_win, Dev
 #pragma unroll
             for (int r = 0; r < D; r++) m += Ai[r*6 + c]*PA[r*6 + c2];
             const int row = a*6 + c, col = b*6 + c2;
-            if (a > b || same) atomicAdd(&B.tiles[band_index(B, row, col)], m);
-            else if (a < b) atomicAdd(&B.tiles[band_index(B, col, row)], m);
+            if (a > b || same) atomicAdd(band_at(B, row, col), m);
+            else if (a < b) atomicAdd(band_at(B, col, row), m);
             else {  // two different factor slots on the same variable: contributes M + M^T
               const int hi = row > col ? row : col, lo = row > col ? col : row;
-              atomicAdd(&B.tiles[band_index(B, hi, lo)], c == c2 ? 2.0*m : m);
+              atomicAdd(band_at(B, hi, lo), c == c2 ? 2.0*m : m);
             }
           }
         }
@@ -279,7 +280,7 @@ __global__ void pose_factors_kernel(DevBlock blk, DevBand B, int arity) {
       double g = 0;
 #pragma unroll
       for (int r = 0; r < 6; r++) g += blk.J[(size_t)(r*JC + 6*k1 + c)*blk.stride + f]*bb[r];
-      atomicAdd(&B.rhs[a*6 + c], g);
+      atomicAdd(rhs_at(B, a*6 + c), g);
     }
     for (int k2 = 0; k2 <= k1; k2++) {
       const int b = blk.idx[(size_t)k2*blk.stride + f];
@@ -291,10 +292,10 @@ __global__ void pose_factors_kernel(DevBlock blk, DevBand B, int arity) {
           for (int r = 0; r < 6; r++)
             m += blk.J[(size_t)(r*JC + 6*k1 + c)*blk.stride + f]*blk.J[(size_t)(r*JC + 6*k2 + c2)*blk.stride + f];
           const int row = a*6 + c, col = b*6 + c2;
-          if (a > b || k1 == k2) atomicAdd(&B.tiles[band_index(B, row, col)], m);
-          else if (a < b) atomicAdd(&B.tiles[band_index(B, col, row)], m);
+          if (a > b || k1 == k2) atomicAdd(band_at(B, row, col), m);
+          else if (a < b) atomicAdd(band_at(B, col, row), m);
           else { const int hi = row > col ? row : col, lo = row > col ? col : row;
-                 atomicAdd(&B.tiles[band_index(B, hi, lo)], c == c2 ? 2.0*m : m); }
+                 atomicAdd(band_at(B, hi, lo), c == c2 ? 2.0*m : m); }
         }
     }
   }
@@ -336,7 +337,7 @@ backsub_simple_kernel(DevBlock blk, DevBand B, double lambda, double* __restrict
         const int pos = blk.idx[(size_t)(PSLOT0 + sl)*blk.stride + f];
         double dp[6];
 #pragma unroll
-        for (int c = 0; c < 6; c++) dp[c] = B.rhs[pos*6 + c];
+        for (int c = 0; c < 6; c++) dp[c] = B.dp[pos*6 + c];
 #pragma unroll
         for (int r = 0; r < D; r++)
 #pragma unroll
@@ -413,7 +414,7 @@ __global__ void pose_model_kernel(DevBlock blk, DevBand B, int arity, double* __
       double u = 0;
       for (int k = 0; k < arity; k++) {
         const int a = blk.idx[(size_t)k*blk.stride + f];
-        for (int c = 0; c < 6; c++) u += blk.J[(size_t)(r*JC + 6*k + c)*blk.stride + f]*B.rhs[a*6 + c];
+        for (int c = 0; c < 6; c++) u += blk.J[(size_t)(r*JC + 6*k + c)*blk.stride + f]*B.dp[a*6 + c];
       }
       q += blk.b[(size_t)r*blk.stride + f]*u;
     }
@@ -434,7 +435,7 @@ __global__ void pose_delta_norm_kernel(DevBand B, double lambda, double* __restr
   __shared__ double sh[256];
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
   double q = 0;
-  if (i < B.n) { const double d = B.rhs[i]; q = 0.5*lambda*d*d; }
+  if (i < B.n) { const double d = B.dp[i]; q = 0.5*lambda*d*d; }
   sh[threadIdx.x] = q;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
@@ -471,7 +472,7 @@ __global__ void retract_vec_kernel(const double* __restrict__ cur, double* __res
 int launch_retract(const DevVars& cur, const DevVars& cand, const DevBand& B, const double* dl_point,
                    const double* dl_flow, cudaStream_t s) {
   int k = 0;
-  if (cur.np) { retract_pose_kernel<<<(cur.np + 127)/128, 128, 0, s>>>(cur, cand, B.rhs); k++; }
+  if (cur.np) { retract_pose_kernel<<<(cur.np + 127)/128, 128, 0, s>>>(cur, cand, B.dp); k++; }
   if (cur.nl) { const size_t n = (size_t)3*cur.nl_stride; retract_vec_kernel<<<(unsigned)((n + 255)/256), 256, 0, s>>>(cur.point, cand.point, dl_point, n); k++; }
   if (cur.nf) { const size_t n = (size_t)2*cur.nf_stride; retract_vec_kernel<<<(unsigned)((n + 255)/256), 256, 0, s>>>(cur.flow, cand.flow, dl_flow, n); k++; }
   return k;

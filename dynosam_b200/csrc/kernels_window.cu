@@ -129,7 +129,7 @@ schur_window_kernel(DevBlock blk, DevWindows Wn, DevBand B, double lambda, int* 
               for (int c = 0; c < 6; c++) {
 #pragma unroll
                 for (int k = 0; k < 3; k++) ws.What[c*3 + k] = A[c]*Bh[k] + A[6 + c]*Bh[3 + k] + A[12 + c]*Bh[6 + k];
-                if (job.y == 0) atomicAdd(&B.rhs[blk.idx[(size_t)s*blk.stride + f]*6 + c], A[c]*rb[0] + A[6 + c]*rb[1] + A[12 + c]*rb[2]);
+                if (job.y == 0) atomicAdd(rhs_at(B, blk.idx[(size_t)s*blk.stride + f]*6 + c), A[c]*rb[0] + A[6 + c]*rb[1] + A[12 + c]*rb[2]);
               }
               mp[Wn.lvar[(size_t)s*blk.stride + f]] = (signed char)sl;
               sfac[warp*SLOTS + sl] = (unsigned char)lane;
@@ -178,7 +178,7 @@ schur_window_kernel(DevBlock blk, DevWindows Wn, DevBand B, double lambda, int* 
 #pragma unroll
       for (int c = 0; c < 6; c++) {
         if (a == b && c > r) continue;
-        atomicAdd(&B.tiles[band_index(B, pa*6 + r, pb*6 + c)], acc[r*6 + c]);
+        atomicAdd(band_at(B, pa*6 + r, pb*6 + c), acc[r*6 + c]);
       }
   }
 }
