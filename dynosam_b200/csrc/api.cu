@@ -488,8 +488,8 @@ static int finalize_impl(dynoba_solver* h) {
       b.use_window = false; b.win = DevWindows{};
       if (win_type && !gl.empty() && !getenv("DYNOBA_NO_WINDOW")) {
         const int ng = (int)gl.size(), NPs = ti.npose;
-        std::vector<unsigned char> gwin(ng, 0), lvar((size_t)NPs*stride, 0);
-        std::vector<int32_t> chunk_g0, chunk_nloc, cvars; std::vector<int2> jobs;
+        std::vector<unsigned char> gwin(ng, 0), lvar((size_t)NPs*stride, 0), glmax(ng, 0), glmin(ng, 255);
+        std::vector<int32_t> chunk_g0, chunk_nloc, cvars; std::vector<int4> jobs;
         int pose_slot[2] = {0, 0}; { int c = 0; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE && c < 2) pose_slot[c++] = k; }
         // greedy chunking, independently inside parallel segments of the group list (a chunk never crosses a segment)
         const int nseg = std::max(1, std::min<int>(omp_get_max_threads(), ng/4096 + 1));
@@ -504,7 +504,10 @@ static int finalize_impl(dynoba_solver* h) {
             std::vector<int32_t> sorted = cur; std::sort(sorted.begin(), sorted.end());
             for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = (int32_t)i;       // position -> local index
             for (int g = cur_g0; g < g_end; g++) if (gwin[g] == 1)
-              for (int s_ = gp[g]; s_ < gp[g+1]; s_++) for (int k = 0; k < NPs; k++) lvar[(size_t)k*stride + s_] = (unsigned char)stamp[hidx[(size_t)pose_slot[k]*stride + s_]];
+              for (int s_ = gp[g]; s_ < gp[g+1]; s_++) for (int k = 0; k < NPs; k++) {
+                const unsigned char lv = (unsigned char)stamp[hidx[(size_t)pose_slot[k]*stride + s_]];
+                lvar[(size_t)k*stride + s_] = lv; glmax[g] = std::max(glmax[g], lv); glmin[g] = std::min(glmin[g], lv);
+              }
             for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = -1;
             out.g0.push_back(cur_g0); out.nloc.push_back((int32_t)sorted.size());
             sorted.resize(WIN_NLOC_MAX, 0); out.cv.insert(out.cv.end(), sorted.begin(), sorted.end());
@@ -536,17 +539,26 @@ static int finalize_impl(dynoba_solver* h) {
           chunk_g0.push_back(seg[t].g0[c]); chunk_nloc.push_back(seg[t].nloc[c]);
           cvars.insert(cvars.end(), seg[t].cv.begin() + c*WIN_NLOC_MAX, seg[t].cv.begin() + (c + 1)*WIN_NLOC_MAX);
           const int nl_ = seg[t].nloc[c]; const int nblk = nl_*(nl_ + 1)/2;
-          for (int st = 0; st*256 < nblk; st++) jobs.push_back(make_int2(chunk_id, st));
+          const int cg0 = seg[t].g0[c], cg1 = c + 1 < seg[t].g0.size() ? seg[t].g0[c + 1] : (int)((int64_t)ng*(t + 1)/nseg);
+          auto row_of = [](int q) { int a = (int)((std::sqrt(8.0*q + 1.0) - 1.0)*0.5); while (a*(a + 1)/2 > q) a--; while ((a + 1)*(a + 2)/2 <= q) a++; return a; };
+          for (int st = 0; st*256 < nblk; st++) {
+            const int a_lo = row_of(st*256), a_hi = row_of(std::min(st*256 + 255, nblk - 1));
+            int gl_ = cg1, gh_ = cg0;      // groups of the chunk whose clique reaches the stripe's rows
+            for (int g = cg0; g < cg1; g++) if (gwin[g] == 1 && (st == 0 || ((int)glmax[g] >= a_lo && (int)glmin[g] <= a_hi))) { gl_ = std::min(gl_, g); gh_ = std::max(gh_, g + 1); }
+            if (gh_ > gl_) jobs.push_back(make_int4(chunk_id, st, gl_, gh_));
+          }
         }
         chunk_g0.push_back(ng);
-        int2* djobs; int* dg0; int* dnl; int* dcv; unsigned char* dlv; unsigned char* dgw;
-        if ((rc = dalloc(h, &djobs, jobs.size()))) return rc; if (!jobs.empty()) CK(cudaMemcpy(djobs, jobs.data(), jobs.size()*sizeof(int2), cudaMemcpyHostToDevice));
+        int4* djobs; int* dg0; int* dnl; int* dcv; unsigned char* dlv; unsigned char* dgw; unsigned char* dgx; unsigned char* dgn;
+        if ((rc = dalloc(h, &djobs, jobs.size()))) return rc; if (!jobs.empty()) CK(cudaMemcpy(djobs, jobs.data(), jobs.size()*sizeof(int4), cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dg0, chunk_g0.size()))) return rc; CK(cudaMemcpy(dg0, chunk_g0.data(), chunk_g0.size()*4, cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dnl, chunk_nloc.size()))) return rc; CK(cudaMemcpy(dnl, chunk_nloc.data(), chunk_nloc.size()*4, cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dcv, cvars.size()))) return rc; CK(cudaMemcpy(dcv, cvars.data(), cvars.size()*4, cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dlv, lvar.size()))) return rc; CK(cudaMemcpy(dlv, lvar.data(), lvar.size(), cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dgw, gwin.size()))) return rc; CK(cudaMemcpy(dgw, gwin.data(), gwin.size(), cudaMemcpyHostToDevice));
-        b.win.n_jobs = (int)jobs.size(); b.win.jobs = djobs; b.win.chunk_g0 = dg0; b.win.chunk_nloc = dnl; b.win.cvars = dcv; b.win.lvar = dlv; b.win.grp_win = dgw;
+        if ((rc = dalloc(h, &dgx, glmax.size()))) return rc; CK(cudaMemcpy(dgx, glmax.data(), glmax.size(), cudaMemcpyHostToDevice));
+        if ((rc = dalloc(h, &dgn, glmin.size()))) return rc; CK(cudaMemcpy(dgn, glmin.data(), glmin.size(), cudaMemcpyHostToDevice));
+        b.win.n_jobs = (int)jobs.size(); b.win.jobs = djobs; b.win.chunk_g0 = dg0; b.win.chunk_nloc = dnl; b.win.cvars = dcv; b.win.lvar = dlv; b.win.grp_win = dgw; b.win.grp_lmax = dgx; b.win.grp_lmin = dgn;
         b.use_window = true;
       }
     }

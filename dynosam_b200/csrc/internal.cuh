@@ -86,12 +86,15 @@ struct GeneralGroups {
 constexpr int WIN_NLOC_MAX = 48;
 struct DevWindows {
   int n_jobs;
-  const int2* jobs;              // (chunk, stripe of 256 lower-triangular blocks)
+  const int4* jobs;              // (chunk, stripe of 256 lower-triangular blocks, first group, end group) -- only the
+                                 // groups whose clique reaches the stripe's block rows are streamed
   const int* chunk_g0;           // [n_chunks+1] group range of a chunk
   const int* chunk_nloc;         // [n_chunks]
   const int* cvars;              // [n_chunks][WIN_NLOC_MAX] solver positions, ascending
   const unsigned char* lvar;     // [npose_slots][stride] local variable of each factor's pose slot
   const unsigned char* grp_win;  // [n_groups] 0: general path, 1: window path, 2: per-landmark atomics path
+  const unsigned char* grp_lmax; // [n_groups] largest / smallest local variable of the group's clique
+  const unsigned char* grp_lmin;
 };
 
 // ---- launchers (each returns the number of kernels it launched)

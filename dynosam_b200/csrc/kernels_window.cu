@@ -34,8 +34,8 @@ schur_window_kernel(DevBlock blk, DevWindows Wn, DevBand B, double lambda, int* 
   signed char* map = reinterpret_cast<signed char*>(slots + WIN_BATCH*SLOTS);    // [WIN_BATCH][NLOC_MAX] local var -> slot
   unsigned char* sfac = reinterpret_cast<unsigned char*>(map + WIN_BATCH*WIN_NLOC_MAX);  // [WIN_BATCH][SLOTS] slot -> factor
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int2 job = Wn.jobs[blockIdx.x];                 // (chunk, stripe)
-  const int chunk = job.x, g0 = Wn.chunk_g0[chunk], g1 = Wn.chunk_g0[chunk + 1];
+  const int4 job = Wn.jobs[blockIdx.x];                 // (chunk, stripe, first group, end group)
+  const int chunk = job.x, g0 = job.z, g1 = job.w;
   const int nloc = Wn.chunk_nloc[chunk];
   const int* cvars = Wn.cvars + (size_t)chunk*WIN_NLOC_MAX;
   // my block (a >= b) of the window's lower triangle
@@ -45,6 +45,11 @@ schur_window_kernel(DevBlock blk, DevWindows Wn, DevBand B, double lambda, int* 
   while ((a + 1)*(a + 2)/2 <= q) a++;
   const int b = q - a*(a + 1)/2;
   const bool active = a < nloc;
+  // block rows of this stripe: a landmark whose clique does not reach them is not staged at all
+  int a_lo, a_hi;
+  { const int q0 = job.y*WIN_THREADS, q1 = min(q0 + WIN_THREADS - 1, nloc*(nloc + 1)/2 - 1);
+    a_lo = (int)((sqrt(8.0*q0 + 1.0) - 1.0)*0.5); while (a_lo*(a_lo + 1)/2 > q0) a_lo--; while ((a_lo + 1)*(a_lo + 2)/2 <= q0) a_lo++;
+    a_hi = (int)((sqrt(8.0*q1 + 1.0) - 1.0)*0.5); while (a_hi*(a_hi + 1)/2 > q1) a_hi--; while ((a_hi + 1)*(a_hi + 2)/2 <= q1) a_hi++; }
   double acc[36];
 #pragma unroll
   for (int i = 0; i < 36; i++) acc[i] = 0.0;
@@ -58,7 +63,7 @@ schur_window_kernel(DevBlock blk, DevWindows Wn, DevBand B, double lambda, int* 
       signed char* mp = map + warp*WIN_NLOC_MAX;
       for (int i = lane; i < WIN_NLOC_MAX; i += 32) mp[i] = -1;
       __syncwarp();
-      if (g < g1 && Wn.grp_win[g] == 1) {
+      if (g < g1 && Wn.grp_win[g] == 1 && (job.y == 0 || ((int)Wn.grp_lmax[g] >= a_lo && (int)Wn.grp_lmin[g] <= a_hi))) {
         const int f0 = blk.grp_ptr[g], T = blk.grp_ptr[g + 1] - f0;   // T <= WIN_TMAX guaranteed by the host
         double V[9], gl[3], Bm[9], bb[3];
 #pragma unroll
@@ -66,12 +71,22 @@ schur_window_kernel(DevBlock blk, DevWindows Wn, DevBand B, double lambda, int* 
         gl[0] = gl[1] = gl[2] = 0.0;
         const bool have = lane < T;
         const int f = f0 + lane;
+        double Aall[NP*18];     // every load of the staging step is issued up front: one memory latency per landmark
+        int pidx[NP];
         if (have) {
 #pragma unroll
           for (int r = 0; r < 3; r++) {
             bb[r] = blk.b[(size_t)r*blk.stride + f];
 #pragma unroll
             for (int c = 0; c < 3; c++) Bm[r*3 + c] = blk.J[(size_t)(r*JC + LCOL + c)*blk.stride + f];
+          }
+#pragma unroll
+          for (int s = 0; s < NP; s++) {
+            pidx[s] = blk.idx[(size_t)s*blk.stride + f];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+              for (int c = 0; c < 6; c++) Aall[s*18 + r*6 + c] = blk.J[(size_t)(r*JC + PCOL0 + 6*s + c)*blk.stride + f];
           }
 #pragma unroll
           for (int c1 = 0; c1 < 3; c1++) {
@@ -120,16 +135,14 @@ schur_window_kernel(DevBlock blk, DevWindows Wn, DevBand B, double lambda, int* 
             for (int s = 0; s < NP; s++) {
               const int sl = lane*NP + s;
               WinSlot& ws = slots[warp*SLOTS + sl];
-              double A[18];
+              const double* A = Aall + s*18;
 #pragma unroll
-              for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 6; c++) { A[r*6 + c] = blk.J[(size_t)(r*JC + PCOL0 + 6*s + c)*blk.stride + f]; ws.A[r*6 + c] = A[r*6 + c]; }
+              for (int i = 0; i < 18; i++) ws.A[i] = A[i];
 #pragma unroll
               for (int c = 0; c < 6; c++) {
 #pragma unroll
                 for (int k = 0; k < 3; k++) ws.What[c*3 + k] = A[c]*Bh[k] + A[6 + c]*Bh[3 + k] + A[12 + c]*Bh[6 + k];
-                if (job.y == 0) atomicAdd(rhs_at(B, blk.idx[(size_t)s*blk.stride + f]*6 + c), A[c]*rb[0] + A[6 + c]*rb[1] + A[12 + c]*rb[2]);
+                if (job.y == 0) atomicAdd(rhs_at(B, pidx[s]*6 + c), A[c]*rb[0] + A[6 + c]*rb[1] + A[12 + c]*rb[2]);
               }
               mp[Wn.lvar[(size_t)s*blk.stride + f]] = (signed char)sl;
               sfac[warp*SLOTS + sl] = (unsigned char)lane;
