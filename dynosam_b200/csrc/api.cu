@@ -64,6 +64,25 @@ struct dynoba_solver {
 
 static int pad32(int64_t n) { return (int)((n + 31)/32*32); }
 
+// Process-wide pinned staging arena for the SoA images of the factor blocks: host->device copies from it run at PCIe
+// speed and asynchronously, so the upload of one block overlaps the host-side preparation of the next.  Grow-only.
+#include <mutex>
+namespace {
+struct PinnedArena {
+  char* base = nullptr; size_t cap = 0, off = 0; std::mutex mu;
+  bool reserve(size_t bytes) {
+    off = 0;
+    if (bytes <= cap) return true;
+    if (base) { cudaFreeHost(base); base = nullptr; cap = 0; }
+    const size_t want = bytes + bytes/8 + (1 << 20);
+    if (cudaHostAlloc((void**)&base, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); base = nullptr; return false; }
+    cap = want; return true;
+  }
+  void* take(size_t bytes) { const size_t a = (off + 255) & ~(size_t)255; if (!base || a + bytes > cap) return nullptr; off = a + bytes; return base + a; }
+};
+PinnedArena g_arena;
+}  // namespace
+
 template <class T> static int dalloc(dynoba_solver* h, T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
@@ -393,6 +412,13 @@ static int finalize_impl(dynoba_solver* h) {
   int part = 0, bs = 0;
   struct GenRef { int32_t rank, blk, idx; };
   std::vector<GenRef> gen_refs;
+  std::lock_guard<std::mutex> arena_lock(g_arena.mu);
+  {
+    size_t need = 0;
+    for (auto& b : h->blocks) { const TypeInfo ti = type_info(b.type); const size_t st = pad32(b.n);
+      need += ((size_t)ti.arity*4 + (size_t)std::max(ti.meas, 1)*8 + (size_t)b.sigma_dim*8 + 4)*st + 4*256; }
+    g_arena.reserve(need);
+  }
   for (size_t bi = 0; bi < h->blocks.size(); bi++) {
     auto& b = h->blocks[bi]; const TypeInfo ti = type_info(b.type);
     const int64_t n = b.n; const int stride = pad32(n);
@@ -418,10 +444,16 @@ static int finalize_impl(dynoba_solver* h) {
     // staging images: plain new[] (no value-initialisation pass over ~1 GB), padding filled explicitly below
     struct Buf32 { std::unique_ptr<int32_t[]> p; size_t n; int32_t* data() { return p.get(); } size_t size() const { return n; } int32_t& operator[](size_t i) { return p[i]; } };
     struct Buf64 { std::unique_ptr<double[]> p; size_t n; double* data() { return p.get(); } size_t size() const { return n; } double& operator[](size_t i) { return p[i]; } };
-    Buf32 hidx{ std::unique_ptr<int32_t[]>(new int32_t[(size_t)ti.arity*stride]), (size_t)ti.arity*stride };
-    Buf64 hmeas{ std::unique_ptr<double[]>(new double[(size_t)std::max(ti.meas, 1)*stride]), (size_t)std::max(ti.meas, 1)*stride };
-    Buf64 hsig{ std::unique_ptr<double[]>(new double[(size_t)b.sigma_dim*stride]), (size_t)b.sigma_dim*stride };
-    Buf32 haux{ std::unique_ptr<int32_t[]>(new int32_t[stride]), (size_t)stride };
+    struct View32 { int32_t* p; size_t n; std::unique_ptr<int32_t[]> own; int32_t* data() { return p; } size_t size() const { return n; } int32_t& operator[](size_t i) { return p[i]; } };
+    struct View64 { double* p; size_t n; std::unique_ptr<double[]> own; double* data() { return p; } size_t size() const { return n; } double& operator[](size_t i) { return p[i]; } };
+    auto mk32 = [&](size_t cnt) { View32 v; v.n = cnt; v.p = (int32_t*)g_arena.take(cnt*4); if (!v.p) { v.own.reset(new int32_t[cnt]); v.p = v.own.get(); } return v; };
+    auto mk64 = [&](size_t cnt) { View64 v; v.n = cnt; v.p = (double*)g_arena.take(cnt*8); if (!v.p) { v.own.reset(new double[cnt]); v.p = v.own.get(); } return v; };
+    View32 hidx = mk32((size_t)ti.arity*stride);
+    View64 hmeas = mk64((size_t)std::max(ti.meas, 1)*stride);
+    View64 hsig = mk64((size_t)b.sigma_dim*stride);
+    View32 haux = mk32((size_t)stride);
+    const bool pinned = !hidx.own && !hmeas.own && !hsig.own && !haux.own;
+    auto h2d = [&](void* dst, const void* src, size_t bytes) { return pinned ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream2) : cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); };
     for (int64_t s = n; s < stride; s++) {
       for (int k = 0; k < ti.arity; k++) hidx[(size_t)k*stride + s] = 0;
       for (int k = 0; k < std::max(ti.meas, 1); k++) hmeas[(size_t)k*stride + s] = 0.0;
@@ -445,14 +477,13 @@ static int finalize_impl(dynoba_solver* h) {
     DevBlock& d = b.dev; d = DevBlock{};
     d.type = b.type; d.n = (int)n; d.stride = stride; d.sigma_dim = b.sigma_dim; d.robust_k = b.robust_k;
     int* di; double* dm; double* ds; int* dax = nullptr; int rc;
-    if ((rc = dalloc(h, &di, hidx.size()))) return rc; CK(cudaMemcpy(di, hidx.data(), hidx.size()*4, cudaMemcpyHostToDevice));
-    if ((rc = dalloc(h, &dm, hmeas.size()))) return rc; CK(cudaMemcpy(dm, hmeas.data(), hmeas.size()*8, cudaMemcpyHostToDevice));
-    if ((rc = dalloc(h, &ds, hsig.size()))) return rc; CK(cudaMemcpy(ds, hsig.data(), hsig.size()*8, cudaMemcpyHostToDevice));
-    if (b.has_aux) { if ((rc = dalloc(h, &dax, haux.size()))) return rc; CK(cudaMemcpy(dax, haux.data(), haux.size()*4, cudaMemcpyHostToDevice)); }
+    if ((rc = dalloc(h, &di, hidx.size()))) return rc; CK(h2d(di, hidx.data(), hidx.size()*4));
+    if ((rc = dalloc(h, &dm, hmeas.size()))) return rc; CK(h2d(dm, hmeas.data(), hmeas.size()*8));
+    if ((rc = dalloc(h, &ds, hsig.size()))) return rc; CK(h2d(ds, hsig.data(), hsig.size()*8));
+    if (b.has_aux) { if ((rc = dalloc(h, &dax, haux.size()))) return rc; CK(h2d(dax, haux.data(), haux.size()*4)); }
     d.idx = di; d.meas = dm; d.isig = ds; d.aux = dax;
     if ((rc = dalloc(h, &d.J, (size_t)ti.dim*ti.jcols*stride))) return rc;
     if ((rc = dalloc(h, &d.b, (size_t)ti.dim*stride))) return rc;
-    CK(cudaMemset(d.J, 0, (size_t)ti.dim*ti.jcols*stride*8)); CK(cudaMemset(d.b, 0, (size_t)ti.dim*stride*8));
     if (numeric_grid(b.type, (int)n) > 0) { if ((rc = dalloc(h, &d.num_scratch, (size_t)numeric_grid(b.type, (int)n)))) return rc; }
     lap("  blk upload+alloc");
     // groups: CSR over every landmark group that has factors in this block; groups this block cannot own alone
