@@ -171,6 +171,82 @@ __device__ __forceinline__ void tile_gemm_sub_half(double (&acc)[16], const doub
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+// Panel-fused spine: warp 0 factors the diagonal tile in 4 panels of 8 columns and PUBLISHES each finished panel
+// (sPan[p][row*8 + j] = L[row][8p + j], sIv[k] = 1 / L[k][k]) with a non-blocking barrier arrival; the TRSM warps
+// follow one panel behind (warp_trsm_follow), so the triangular solves of the sub-diagonal tiles overlap the potrf
+// instead of starting after it.
+__device__ __forceinline__ bool warp_potrf_publish(double (&row)[TILE], int lane, double* sPan, double* sIv) {
+  bool ok = true;
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    double* sP = sPan + p*256;
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+      const int k = 8*p + kk;
+      const double d = __shfl_sync(0xffffffffu, row[k], k);
+      if (!(d > 0.0)) ok = false;
+      const double inv = rsqrt(d);
+      const double l = (lane == k) ? d*inv : row[k]*inv;
+      row[k] = l;
+      if (lane == k) sIv[k] = inv;
+#pragma unroll
+      for (int c = k + 1; c < 8*p + 8; c++) {
+        const double lc = __shfl_sync(0xffffffffu, l, c);
+        row[c] -= l*lc;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sP + lane*8 + j) = make_double2(row[8*p + j], row[8*p + j + 1]);
+    __syncwarp();
+    named_arrive(4 + p, 96);
+    if (p < 3) {
+#pragma unroll
+      for (int c = 8*p + 8; c < TILE; c++) {
+        double acc = row[c];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const double2 b = *reinterpret_cast<const double2*>(sP + c*8 + j);
+          acc -= row[8*p + j]*b.x; acc -= row[8*p + j + 1]*b.y;
+        }
+        row[c] = acc;
+      }
+    }
+  }
+  return ok;
+}
+// x(row = lane) <- x * L^-T, consuming the panels warp 0 publishes
+__device__ __forceinline__ void warp_trsm_follow(double (&x)[TILE], const double* sPan, const double* sIv) {
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const double* sP = sPan + p*256;
+    named_bar(4 + p, 96);
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+      const int k = 8*p + kk;
+      const double l = x[k]*sIv[k];
+      x[k] = l;
+#pragma unroll
+      for (int c = k + 1; c < 8*p + 8; c++) x[c] -= l*sP[c*8 + kk];
+    }
+    if (p < 3) {
+#pragma unroll
+      for (int c = 8*p + 8; c < TILE; c++) {
+        double acc = x[c];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const double2 b = *reinterpret_cast<const double2*>(sP + c*8 + j);
+          acc -= x[8*p + j]*b.x; acc -= x[8*p + j + 1]*b.y;
+        }
+        x[c] = acc;
+      }
+    }
+  }
+}
 
 __device__ long long g_spine_dbg[16];
 #define TS(i) do { const long long t_ = clock64(); if (lane == 0) dbgacc[i] += t_ - tlast; tlast = t_; } while (0)
@@ -214,49 +290,50 @@ band_cholesky_dataflow_kernel(CholJob job, int* __restrict__ fail) {
     if (P.Kbeg >= P.Kend) return;
     if (warp == 0) { wait_flag(pre + (size_t)P.Kbeg*W1, lane); tile_load(P.tiles + (size_t)P.Kbeg*W1*TILE2, r, lane); }
     if (warp == 1 && P.Kbeg + 1 < NT) { wait_flag(pre + (size_t)P.Kbeg*W1 + 1, lane); tile_load(P.tiles + ((size_t)P.Kbeg*W1 + 1)*TILE2, r, lane); }
+    double* sPan = sLt;                             // [4][256] published potrf panels (the row-major L_KK copy is gone)
     for (int K = P.Kbeg; K < P.Kend; K++) {
       const size_t oD = (size_t)K*W1;
-      if (warp == 0) {
-        TS(11);
-        if (!warp_potrf_blocked(r, lane, sP) && lane == 0) atomicOr(fail, 2);
-        TS(0);
-        tile_store(P.tiles + oD*TILE2, r, lane);
-#pragma unroll
-        for (int c = 0; c < TILE; c += 2) *reinterpret_cast<double2*>(sLt + lane*LT_STRIDE + c) = make_double2(r[c], r[c + 1]);
-        double dg = 1.0;
-#pragma unroll
-        for (int c = 0; c < TILE; c++) if (lane == c) dg = r[c];
-        sIv[lane] = 1.0/dg;
-        set_flag(done + oD, lane);
-        TS(1);
-      }
-      if (K + 1 >= NT) break;
-      named_bar(1, 128);
+      const bool last = K + 1 >= NT;
       const bool has2 = (K + 2 < NT) && (WB >= 2), hasn = (K + 2 < NT);
       double h[16];
-      if (warp == 1) {
-        tile_trsm_rm(r, sLt, sIv);
+      if (warp == 0) {
+        TS(11);
+        if (!warp_potrf_publish(r, lane, sPan, sIv) && lane == 0) atomicOr(fail, 2);
+        TS(0);
+        tile_store(P.tiles + oD*TILE2, r, lane);
+        set_flag(done + oD, lane);
+        TS(1);
+        if (!last) {
+          wait_flag(pre + oD + W1, lane);
+          const double* t = P.tiles + (oD + W1)*TILE2;
+#pragma unroll
+          for (int j = 0; j < 16; j++) h[j] = __ldcg(t + (16 + j)*TILE + lane);
+        }
+        TS(2);
+      } else if (!last && warp == 1) {
+        warp_trsm_follow(r, sPan, sIv);
         tile_store(P.tiles + (oD + 1)*TILE2, r, lane);
         tile_stage(sX1, r, lane);
         set_flag(done + oD + 1, lane);
-      } else if (warp == 2) {
+      } else if (!last && warp == 2) {
+        if (has2) { wait_flag(pre + oD + 2, lane); tile_load(P.tiles + (oD + 2)*TILE2, r, lane); }
+        else {
+#pragma unroll
+          for (int c = 0; c < TILE; c++) r[c] = 0.0;
+        }
+        warp_trsm_follow(r, sPan, sIv);                 // always follows: the panel barriers count three warps
         if (has2) {
-          wait_flag(pre + oD + 2, lane);
-          tile_load(P.tiles + (oD + 2)*TILE2, r, lane);
-          tile_trsm_rm(r, sLt, sIv);
           tile_store(P.tiles + (oD + 2)*TILE2, r, lane);
           tile_stage(sX2, r, lane);
           set_flag(done + oD + 2, lane);
         }
-      } else {
-        TS(2);
-        const int c0 = warp == 0 ? 16 : 0;
+      } else if (!last) {
         wait_flag(pre + oD + W1, lane);
         const double* t = P.tiles + (oD + W1)*TILE2;
 #pragma unroll
-        for (int j = 0; j < 16; j++) h[j] = __ldcg(t + (c0 + j)*TILE + lane);
-        TS(3);
+        for (int j = 0; j < 16; j++) h[j] = __ldcg(t + j*TILE + lane);
       }
+      if (last) break;
       named_bar(2, 128);
       if (warp == 0) TS(4);
       if (warp == 0 || warp == 3) {
