@@ -131,7 +131,7 @@ int dynoba_create(int device, dynoba_handle* out) {
   h->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DYNOBA_ERR_CUDA; }
   for (auto& e : h->ev) cudaEventCreate(&e);
-  cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi); }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   *out = h;
   return DYNOBA_OK;
@@ -668,10 +668,10 @@ static int do_linearize(dynoba_solver* h) {
   bool side = false;
   for (auto& b : h->blocks) if (b.n && numeric_grid(b.type, (int)b.n) > 0) side = true;
   if (side) { cudaEventRecord(h->ev_fork, h->stream); cudaStreamWaitEvent(h->stream2, h->ev_fork, 0); }
-  for (auto& b : h->blocks) {
-    const bool num = numeric_grid(b.type, (int)b.n) > 0;
-    h->launches += launch_linearize(b.dev, h->cur, h->partials + b.part_off, num ? h->stream2 : h->stream);
-  }
+  for (auto& b : h->blocks) if (numeric_grid(b.type, (int)b.n) > 0)      // compute-bound blocks first, high-priority stream
+    h->launches += launch_linearize(b.dev, h->cur, h->partials + b.part_off, h->stream2);
+  for (auto& b : h->blocks) if (numeric_grid(b.type, (int)b.n) == 0)
+    h->launches += launch_linearize(b.dev, h->cur, h->partials + b.part_off, h->stream);
   if (side) { cudaEventRecord(h->ev_join, h->stream2); cudaStreamWaitEvent(h->stream, h->ev_join, 0); }
   h->launches += launch_sum(h->partials, h->n_lin_partials, h->scalars + 0, h->stream);
   h->linearized = true;

@@ -50,8 +50,9 @@ __device__ __forceinline__ double block_sum(double x, double* sh) {
 }
 
 // K1.  partials[blockIdx.x] = sum over the block's factors of 0.5*|b|^2 (the linearised error at delta = 0).
+// hybrid types: cap at 80 registers (6 CTAs/SM instead of 5) -- more bytes in flight for the HBM-bound store stream
 template <int T>
-__global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(DevBlock blk, DevVars v, double* __restrict__ partials) {
+__global__ void __launch_bounds__(LIN_THREADS, (T == F_HYBRID3 || T == F_HYBRID_STEREO3) ? 6 : 1) linearize_kernel(DevBlock blk, DevVars v, double* __restrict__ partials) {
   constexpr TypeInfo ti = type_info(T);
   constexpr int D = ti.dim, JC = ti.jcols, M = ti.meas;
   __shared__ double sh[LIN_THREADS/32];
