@@ -243,7 +243,12 @@ def main():
         s.optimize(default_params(max_iterations=W, **prm))
         s.reset_values()      # the timed region is LM iterations 1..K from the initial values, like the CPU arm
     # ---- timed region: exactly K LM iterations, device-timed (CUDA events on the solver's stream), max over ranks
-    lin_ms = [s.linearize() for _ in range(3)]                      # Jacobian-build kernel alone (after warm-up)
+    lin_ms = [s.linearize() for _ in range(3)]                      # whole Jacobian-build pass (after warm-up)
+    # the dominant Jacobian-build kernel alone: the factor block with the most algorithmic bytes
+    blk_stats = [s.linearize_block(bi) for bi in range(len(prob.blocks))]
+    dom = int(np.argmax([b for _, b in blk_stats])) if blk_stats else 0
+    dom_ms = [s.linearize_block(dom)[0] for _ in range(7)] if blk_stats else [0.0]
+    dom_bytes = blk_stats[dom][1] if blk_stats else 0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -300,17 +305,23 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0); peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
     lin = float(np.median(lin_ms))
-    ach = info["jacobian_bytes"]/(lin*1e-3)/1e9 if lin > 0 else 0.0
+    pass_ach = info["jacobian_bytes"]/(lin*1e-3)/1e9 if lin > 0 else 0.0
+    dms = float(np.median(dom_ms))
+    ach = dom_bytes/(dms*1e-3)/1e9 if dms > 0 else 0.0
+    from dynosam_b200.problem import TYPE_NAMES
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done, "warmup": W,
            "ms_per_step": ms_total/max(steps_done, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(st["kernel_launches"]),
            "inner_iterations": st["inner_iterations"], "chi2": [st["error_initial"], st["error_final"]],
            "reduced_dim": info["reduced_dim"], "bandwidth": info["bandwidth"], "n_factors_rank0": prob.n_factors,
            "phases_ms": {k: st[k] for k in ("ms_linearize", "ms_schur", "ms_factor", "ms_error", "ms_total")},
-           "roofline": {"kernel": "linearize_kernel<*> (materialising Jacobian build, all factor types of one pass)",
+           "roofline": {"kernel": f"linearize_kernel<{TYPE_NAMES[prob.blocks[dom].type]}> (materialising Jacobian build of the largest factor block, "
+                                  f"{prob.blocks[dom].n} factors)",
                         "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                        "frac": ach/peak if peak else None, "traffic": None, "algorithmic_bytes": info["jacobian_bytes"],
-                        "ms_per_pass": lin}}
+                        "frac": ach/peak if peak else None, "traffic": None, "algorithmic_bytes": int(dom_bytes), "ms_per_launch": dms,
+                        "whole_pass": {"algorithmic_bytes": info["jacobian_bytes"], "ms": lin, "achieved": pass_ach,
+                                       "frac": pass_ach/peak if peak else None,
+                                       "note": "all factor blocks of one linearize() incl. the numerically differentiated smoothing factors and the final reduction"}}}
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline:

@@ -25,7 +25,7 @@ EXPORTS = [
     "dynoba_lm_default_params", "dynoba_set_variables", "dynoba_set_aux_poses", "dynoba_set_calibration",
     "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_finalize", "dynoba_error",
     "dynoba_optimize", "dynoba_get_variables", "dynoba_get_keys", "dynoba_num_variables", "dynoba_problem_info",
-    "dynoba_linearize", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
+    "dynoba_linearize", "dynoba_linearize_block", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
     "dynoba_get_reduced_system", "dynoba_retract",
 ]
 
@@ -85,6 +85,7 @@ def load():
         L.dynoba_num_variables.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
         L.dynoba_problem_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.dynoba_linearize.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.dynoba_linearize_block.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
         L.dynoba_get_linearization.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp]
         L.dynoba_get_factor_errors.argtypes = [C.c_void_p, C.c_int, c_dp]
         L.dynoba_solve.argtypes = [C.c_void_p, C.c_double, c_dp]
@@ -202,6 +203,12 @@ class Solver:
         ms = C.c_float()
         self._ck(self.lib.dynoba_linearize(self.h, C.byref(ms)))
         return ms.value
+
+    def linearize_block(self, bi):
+        """(ms, algorithmic bytes) of one launch of block bi's Jacobian-build kernel."""
+        ms = C.c_float(); nb = C.c_int64()
+        self._ck(self.lib.dynoba_linearize_block(self.h, bi, C.byref(ms), C.byref(nb)))
+        return ms.value, nb.value
 
     def linearization(self, bi):
         b = self.problem.blocks[bi]

@@ -519,9 +519,12 @@ static int finalize_impl(dynoba_solver* h) {
       b.use_window = false; b.win = DevWindows{};
       if (win_type && !gl.empty() && !getenv("DYNOBA_NO_WINDOW")) {
         const int ng = (int)gl.size(), NPs = ti.npose;
-        std::vector<unsigned char> gwin(ng, 0), lvar((size_t)NPs*stride, 0), glmax(ng, 0), glmin(ng, 255);
-        std::vector<int32_t> chunk_g0, chunk_nloc, cvars; std::vector<int4> jobs;
+        std::vector<unsigned char> gwin(ng, 0), lvar((size_t)NPs*stride, 0);
+        std::vector<int32_t> chunk_nloc, cvars; std::vector<int4> jobs, batches;
         int pose_slot[2] = {0, 0}; { int c = 0; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE && c < 2) pose_slot[c++] = k; }
+        // window size: one 512-thread CTA holds 16 tiles of 8x4 blocks; NLOC 24 -> 12 tiles (one stripe), NLOC 40 -> 30 (two)
+        int cap = NPs == 1 ? 24 : 40;
+        if (const char* e = getenv(NPs == 1 ? "DYNOBA_WIN_CAP1" : "DYNOBA_WIN_CAP2")) cap = std::max(2, std::min(WIN_NLOC_MAX, atoi(e)));
         // greedy chunking, independently inside parallel segments of the group list (a chunk never crosses a segment)
         const int nseg = std::max(1, std::min<int>(omp_get_max_threads(), ng/4096 + 1));
         struct SegOut { std::vector<int32_t> g0, nloc, cv; };
@@ -535,10 +538,8 @@ static int finalize_impl(dynoba_solver* h) {
             std::vector<int32_t> sorted = cur; std::sort(sorted.begin(), sorted.end());
             for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = (int32_t)i;       // position -> local index
             for (int g = cur_g0; g < g_end; g++) if (gwin[g] == 1)
-              for (int s_ = gp[g]; s_ < gp[g+1]; s_++) for (int k = 0; k < NPs; k++) {
-                const unsigned char lv = (unsigned char)stamp[hidx[(size_t)pose_slot[k]*stride + s_]];
-                lvar[(size_t)k*stride + s_] = lv; glmax[g] = std::max(glmax[g], lv); glmin[g] = std::min(glmin[g], lv);
-              }
+              for (int s_ = gp[g]; s_ < gp[g+1]; s_++) for (int k = 0; k < NPs; k++)
+                lvar[(size_t)k*stride + s_] = (unsigned char)stamp[hidx[(size_t)pose_slot[k]*stride + s_]];
             for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = -1;
             out.g0.push_back(cur_g0); out.nloc.push_back((int32_t)sorted.size());
             sorted.resize(WIN_NLOC_MAX, 0); out.cv.insert(out.cv.end(), sorted.begin(), sorted.end());
@@ -548,7 +549,7 @@ static int finalize_impl(dynoba_solver* h) {
             if (gl[g] < 0) continue;
             const int T = gp[g+1] - gp[g];
             bool dup = false; int fresh = 0;
-            if (T > 24) { gwin[g] = 2; continue; }
+            if (T > WIN_TMAX) { gwin[g] = 2; continue; }
             for (int s_ = gp[g]; s_ < gp[g+1] && !dup; s_++) for (int k = 0; k < NPs; k++) {
               const int p_ = hidx[(size_t)pose_slot[k]*stride + s_];
               if (gstamp[p_] == g) { dup = true; break; }
@@ -556,7 +557,9 @@ static int finalize_impl(dynoba_solver* h) {
               if (inchunk[p_] != chunk_id) fresh++;
             }
             if (dup) { gwin[g] = 2; continue; }
-            if ((int)cur.size() + fresh > WIN_NLOC_MAX) close_chunk(g);
+            if (!cur.empty() && (int)cur.size() + fresh > cap) {      // a landmark wider than cap gets a chunk of its own
+              close_chunk(g);
+            }
             for (int s_ = gp[g]; s_ < gp[g+1]; s_++) for (int k = 0; k < NPs; k++) {
               const int p_ = hidx[(size_t)pose_slot[k]*stride + s_];
               if (inchunk[p_] != chunk_id) { inchunk[p_] = chunk_id; cur.push_back(p_); }
@@ -566,30 +569,35 @@ static int finalize_impl(dynoba_solver* h) {
           close_chunk(gb_);
         }
         for (int t = 0; t < nseg; t++) for (size_t c = 0; c < seg[t].g0.size(); c++) {
-          const int chunk_id = (int)chunk_g0.size();
-          chunk_g0.push_back(seg[t].g0[c]); chunk_nloc.push_back(seg[t].nloc[c]);
+          const int chunk_id = (int)chunk_nloc.size();
+          chunk_nloc.push_back(seg[t].nloc[c]);
           cvars.insert(cvars.end(), seg[t].cv.begin() + c*WIN_NLOC_MAX, seg[t].cv.begin() + (c + 1)*WIN_NLOC_MAX);
-          const int nl_ = seg[t].nloc[c]; const int nblk = nl_*(nl_ + 1)/2;
+          const int nl_ = seg[t].nloc[c]; const int ntile = win_ntiles(nl_);
           const int cg0 = seg[t].g0[c], cg1 = c + 1 < seg[t].g0.size() ? seg[t].g0[c + 1] : (int)((int64_t)ng*(t + 1)/nseg);
-          auto row_of = [](int q) { int a = (int)((std::sqrt(8.0*q + 1.0) - 1.0)*0.5); while (a*(a + 1)/2 > q) a--; while ((a + 1)*(a + 2)/2 <= q) a++; return a; };
-          for (int st = 0; st*256 < nblk; st++) {
-            const int a_lo = row_of(st*256), a_hi = row_of(std::min(st*256 + 255, nblk - 1));
-            int gl_ = cg1, gh_ = cg0;      // groups of the chunk whose clique reaches the stripe's rows
-            for (int g = cg0; g < cg1; g++) if (gwin[g] == 1 && (st == 0 || ((int)glmax[g] >= a_lo && (int)glmin[g] <= a_hi))) { gl_ = std::min(gl_, g); gh_ = std::max(gh_, g + 1); }
-            if (gh_ > gl_) jobs.push_back(make_int4(chunk_id, st, gl_, gh_));
+          // batches: runs of window-path landmarks (other groups end a run), bounded in landmarks and slots
+          const int b0 = (int)batches.size();
+          int rg0 = -1, rslots = 0;
+          auto close_batch = [&](int g_end) { if (rg0 >= 0) batches.push_back(make_int4(rg0, g_end, gp[rg0], gp[g_end])); rg0 = -1; rslots = 0; };
+          for (int g = cg0; g < cg1; g++) {
+            if (gwin[g] != 1) { close_batch(g); continue; }
+            const int ns_ = (gp[g+1] - gp[g])*NPs;
+            if (rg0 >= 0 && (rslots + ns_ > WIN_BATCH_SLOTS || g - rg0 >= WIN_BATCH_LMK)) close_batch(g);
+            if (rg0 < 0) rg0 = g;
+            rslots += ns_;
           }
+          close_batch(cg1);
+          const int b1 = (int)batches.size();
+          if (b1 > b0) for (int st = 0; st*WIN_ACC_WARPS < ntile; st++) jobs.push_back(make_int4(chunk_id, st, b0, b1));
         }
-        chunk_g0.push_back(ng);
-        int4* djobs; int* dg0; int* dnl; int* dcv; unsigned char* dlv; unsigned char* dgw; unsigned char* dgx; unsigned char* dgn;
+        int4* djobs; int4* dbat; int* dnl; int* dcv; unsigned char* dlv; unsigned char* dgw; double* dslots;
         if ((rc = dalloc(h, &djobs, jobs.size()))) return rc; if (!jobs.empty()) CK(cudaMemcpy(djobs, jobs.data(), jobs.size()*sizeof(int4), cudaMemcpyHostToDevice));
-        if ((rc = dalloc(h, &dg0, chunk_g0.size()))) return rc; CK(cudaMemcpy(dg0, chunk_g0.data(), chunk_g0.size()*4, cudaMemcpyHostToDevice));
+        if ((rc = dalloc(h, &dbat, batches.size()))) return rc; if (!batches.empty()) CK(cudaMemcpy(dbat, batches.data(), batches.size()*sizeof(int4), cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dnl, chunk_nloc.size()))) return rc; CK(cudaMemcpy(dnl, chunk_nloc.data(), chunk_nloc.size()*4, cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dcv, cvars.size()))) return rc; CK(cudaMemcpy(dcv, cvars.data(), cvars.size()*4, cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dlv, lvar.size()))) return rc; CK(cudaMemcpy(dlv, lvar.data(), lvar.size(), cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dgw, gwin.size()))) return rc; CK(cudaMemcpy(dgw, gwin.data(), gwin.size(), cudaMemcpyHostToDevice));
-        if ((rc = dalloc(h, &dgx, glmax.size()))) return rc; CK(cudaMemcpy(dgx, glmax.data(), glmax.size(), cudaMemcpyHostToDevice));
-        if ((rc = dalloc(h, &dgn, glmin.size()))) return rc; CK(cudaMemcpy(dgn, glmin.data(), glmin.size(), cudaMemcpyHostToDevice));
-        b.win.n_jobs = (int)jobs.size(); b.win.jobs = djobs; b.win.chunk_g0 = dg0; b.win.chunk_nloc = dnl; b.win.cvars = dcv; b.win.lvar = dlv; b.win.grp_win = dgw; b.win.grp_lmax = dgx; b.win.grp_lmin = dgn;
+        if ((rc = dalloc(h, &dslots, (size_t)n*NPs*WIN_SLOT_DOUBLES))) return rc;
+        b.win.n_jobs = (int)jobs.size(); b.win.jobs = djobs; b.win.batches = dbat; b.win.chunk_nloc = dnl; b.win.cvars = dcv; b.win.lvar = dlv; b.win.grp_win = dgw; b.win.slots = dslots;
         b.use_window = true;
       }
     }
@@ -609,15 +617,10 @@ static int finalize_impl(dynoba_solver* h) {
       if (i == 0 || gen_refs[i].rank != gen_refs[i-1].rank) {
         gptr.push_back((int32_t)i);
         const int r = gorder[gen_refs[i].rank];           // root landmark id of the group
-        int first = INT32_MAX, cnt = 0; bool only_points = true;
-        // points of the group are contiguous in device order; find the first one and the count
-        (void)cnt;
+        // points of a group are contiguous in device order: count here, first device index filled in below
         gnl.push_back(gcount[r]);
-        // first device index = min over the group's points: every member maps to consecutive indices
-        first = INT32_MAX;
-        gl0.push_back(first);
-        if (r >= npt) only_points = false;
-        if (gcount[r] > 21 || !only_points) h->supported = false;
+        gl0.push_back(INT32_MAX);
+        if (gcount[r] > 21 || r >= npt) h->supported = false;
       }
       refs.push_back(gen_refs[i].blk); refs.push_back(gen_refs[i].idx);
     }
@@ -764,6 +767,23 @@ int dynoba_linearize(dynoba_handle h, float* ms) {
   CK(cudaEventRecord(h->ev[1], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (ms) CK(cudaEventElapsedTime(ms, h->ev[0], h->ev[1]));
+  CK(cudaGetLastError());
+  return DYNOBA_OK;
+}
+
+int dynoba_linearize_block(dynoba_handle h, int bi, float* ms, int64_t* bytes) {
+  int rc = check_ready(h, false); if (rc) return rc;
+  ARG(bi >= 0 && bi < (int)h->blocks.size(), "bad block index");
+  auto& b = h->blocks[bi]; const TypeInfo ti = type_info(b.type);
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  h->launches += launch_linearize(b.dev, h->cur, h->partials + b.part_off, h->stream);
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (ms) CK(cudaEventElapsedTime(ms, h->ev[0], h->ev[1]));
+  if (bytes) {   // factor record read once + whitened tiles written once (variable reads left out: conservative)
+    const int64_t rd = 4*ti.arity + 8*ti.meas + 8*b.sigma_dim + (b.has_aux ? 4 : 0), wr = 8*(ti.dim*ti.jcols + ti.dim);
+    *bytes = b.n*(rd + wr);
+  }
   CK(cudaGetLastError());
   return DYNOBA_OK;
 }

@@ -83,18 +83,29 @@ struct GeneralGroups {
 };
 
 // Window decomposition of a factor block for kernels_window.cu (built by the host in finalize)
-constexpr int WIN_NLOC_MAX = 48;
+constexpr int WIN_NLOC_MAX = 48;          // largest window (local pose-like variables of a chunk)
+constexpr int WIN_TMAX = 24;              // factors per landmark on the window path (larger ones: kernels_schur.cu)
+constexpr int WIN_SLOT_DOUBLES = 42;      // one staged clique variable of one factor: Wt[3][6] | A[3][6] | rb[3] | meta | pad[2]
+constexpr int WIN_BATCH_SLOTS = 256;      // slots per shared-memory buffer of the accumulate kernel
+constexpr int WIN_BATCH_LMK = 32;         // landmarks per batch
+// The accumulate kernel tiles the window's lower triangle of 6x6 blocks into 8x4 block tiles, one tile per warp (a
+// landmark's clique is a contiguous range of local variables, so whole tiles are active or idle together).
+__host__ __device__ __forceinline__ int win_ntiles(int nloc) {
+  int n = 0;
+  for (int tr = 0; tr*8 < nloc; tr++) { const int rmax = (8*tr + 7 < nloc - 1) ? 8*tr + 7 : nloc - 1; n += rmax/4 + 1; }
+  return n;
+}
+constexpr int WIN_ACC_WARPS = 16;         // tiles per CTA (stripe) of the accumulate kernel
 struct DevWindows {
   int n_jobs;
-  const int4* jobs;              // (chunk, stripe of 256 lower-triangular blocks, first group, end group) -- only the
-                                 // groups whose clique reaches the stripe's block rows are streamed
-  const int* chunk_g0;           // [n_chunks+1] group range of a chunk
+  const int4* jobs;              // (chunk, stripe of the window's lower-triangular blocks, first batch, end batch)
+  const int4* batches;           // (first group, end group, first factor, end factor): runs of window-path landmarks,
+                                 // at most WIN_BATCH_LMK landmarks / WIN_BATCH_SLOTS slots, never crossing a chunk
   const int* chunk_nloc;         // [n_chunks]
   const int* cvars;              // [n_chunks][WIN_NLOC_MAX] solver positions, ascending
   const unsigned char* lvar;     // [npose_slots][stride] local variable of each factor's pose slot
   const unsigned char* grp_win;  // [n_groups] 0: general path, 1: window path, 2: per-landmark atomics path
-  const unsigned char* grp_lmax; // [n_groups] largest / smallest local variable of the group's clique
-  const unsigned char* grp_lmin;
+  double* slots;                 // [n*npose_slots][WIN_SLOT_DOUBLES] staged slots in factor order (HBM scratch)
 };
 
 // ---- launchers (each returns the number of kernels it launched)

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstdio>
+#include <vector>
 #include <cooperative_groups.h>
 #include "internal.cuh"
 
@@ -39,10 +40,20 @@ __device__ __forceinline__ void wait_flag(const int* f, int lane) {
   }
   __syncwarp();
 }
+// optional timeline trace (DYNOBA_CHOL_TRACE): global timer at the moment a flag of problem 0 is released
+__device__ long long* g_trace = nullptr;
+__device__ int* g_trace_base = nullptr;
+__device__ long long g_trace_len = 0;
+__device__ __forceinline__ void trace_flag(int* f) {
+  if (g_trace) {
+    const long long off = f - g_trace_base;
+    if (off >= 0 && off < g_trace_len) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_trace[off] = t; }
+  }
+}
 __device__ __forceinline__ void set_flag(int* f, int lane) {
   __threadfence();      // every lane's tile stores are performed at gpu scope before the flag is released
   __syncwarp();
-  if (lane == 0) st_release(f, 1);
+  if (lane == 0) { st_release(f, 1); trace_flag(f); }
 }
 
 // warp-level Cholesky of a 32x32 tile held one row per lane; returns false when a pivot is not positive
@@ -75,14 +86,29 @@ __device__ __forceinline__ void tile_gemm_sub(double (&acc)[TILE], const double 
     }
   }
 }
-// x(row = lane) <- x * L^-T with L staged as sL[k*32 + c] = L[c][k]; sinv[c] = 1 / L[c][c]
+// x(row = lane) <- x * L^-T with L staged as sL[k*32 + c] = L[c][k]; sinv[c] = 1 / L[c][c].  Blocked by 8 columns: the
+// serial chain is 8 x (mul, fma) per panel, the rank-8 update of the columns behind a panel has 24/16/8 independent chains.
 __device__ __forceinline__ void tile_trsm(double (&x)[TILE], const double* sL, const double* sinv) {
 #pragma unroll
-  for (int c = 0; c < TILE; c++) {
-    double s = x[c];
+  for (int p = 0; p < 4; p++) {
 #pragma unroll
-    for (int k = 0; k < c; k++) s -= x[k]*sL[k*TILE + c];
-    x[c] = s*sinv[c];
+    for (int kk = 0; kk < 8; kk++) {
+      const int k = 8*p + kk;
+      const double l = x[k]*sinv[k];
+      x[k] = l;
+#pragma unroll
+      for (int c = k + 1; c < 8*p + 8; c++) x[c] -= l*sL[k*TILE + c];
+    }
+    if (p < 3) {
+#pragma unroll
+      for (int c = 8*p + 8; c < TILE; c += 2) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const double2 b = *reinterpret_cast<const double2*>(sL + (8*p + j)*TILE + c);
+          x[c] -= x[8*p + j]*b.x; x[c + 1] -= x[8*p + j]*b.y;
+        }
+      }
+    }
   }
 }
 __device__ __forceinline__ void tile_load(const double* t, double (&r)[TILE], int lane) {
@@ -257,6 +283,8 @@ __device__ long long g_spine_dbg[16];
 struct CholProb { double* tiles; double* rhs; int NT, Kbeg, Kend; int* done; int* pre; int* ydone; };
 struct CholJob { CholProb p[2]; int np, WB; };
 
+__device__ __forceinline__ void chol_worker(const struct CholJob& job, int wid, int nworkers, double* sb, double* sinv, int lane, int dd0_lag);
+
 // Tile roles (dd = I - K):
 //   dd == 0, 1 : workers apply the updates from columns J <= K-2 ("pre"), the spine applies J = K-1 and finishes
 //   dd == 2    : workers apply J <= K-1 ("pre"), the spine does the TRSM
@@ -379,8 +407,13 @@ band_cholesky_dataflow_kernel(CholJob job, int* __restrict__ fail) {
     return;
   }
   // -------------------------------------------------------------------- workers
-  const int nworkers = ((int)gridDim.x - job.np)*CH_WARPS;
-  const int wid = ((int)blockIdx.x - job.np)*CH_WARPS + warp;
+  chol_worker(job, ((int)blockIdx.x - job.np)*CH_WARPS + warp, ((int)gridDim.x - job.np)*CH_WARPS, sb, sinv, lane, 2);
+}
+
+// Worker warp `wid` of `nworkers`: tile tasks in column-major order (see the role table above the kernels).
+// dd0_lag: the diagonal tile (dd == 0) receives the worker updates from columns J <= K - dd0_lag only (the spine owns the rest).
+__device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nworkers, double* sb, double* sinv, int lane, int dd0_lag) {
+  const int WB = job.WB, W1 = WB + 1;
   const int W2 = W1 + 1;                                 // tile tasks + the rhs task of the column
   int ncols = 0;
   for (int q = 0; q < job.np; q++) ncols = max(ncols, job.p[q].NT - job.p[q].Kbeg);
@@ -431,7 +464,9 @@ band_cholesky_dataflow_kernel(CholJob job, int* __restrict__ fail) {
     double* tp = P.tiles + o*TILE2;
     tile_load(tp, acc, lane);
     const int Jlo = max(P.Kbeg, I - WB);
-    const int Jhi = min((dd <= 1) ? K - 2 : K - 1, P.Kend - 1);
+    // the spine finishes the tiles of columns <= Kend itself: it owns the last (dd0_lag - 1) updates of a diagonal tile and
+    // the last update of a first sub-diagonal tile
+    const int Jhi = min(dd == 0 ? (K <= P.Kend ? K - dd0_lag : K - 1) : (dd == 1 ? K - 2 : K - 1), P.Kend - 1);
     for (int J = Jlo; J <= Jhi; J++) {
       const size_t oI = (size_t)J*W1 + (I - J), oK = (size_t)J*W1 + (K - J);
       wait_flag(done + oK, lane);
@@ -459,6 +494,319 @@ band_cholesky_dataflow_kernel(CholJob job, int* __restrict__ fail) {
       tile_trsm(acc, sb, sinv);
       tile_store(tp, acc, lane);
       set_flag(done + o, lane);
+    }
+  }
+}
+
+// =====================================================================================================================
+// Spine v3.  One CTA of 8 warps per band problem; the compute warps work out of shared memory / registers only and
+// never touch global memory, fences or flags -- three I/O warps do that one column ahead / behind:
+// (warp w issues on scheduler w % 4: each A warp shares its scheduler with a mostly sleeping I/O warp)
+//   A pair (warps 0, 1)  alternate per column between  potrf(K,K)  and  accumulating the next diagonal tile
+//                        D(K+1) = T(K+1,K+1) - X2(K-1) X2(K-1)^T - X1(K) X1(K)^T  (rank-8 updates as X1 panels appear)
+//   B pair (warps 2, 3)  alternate between the TRSM of X1(K) = L(K+1,K), one panel behind the potrf, and accumulating
+//                        Xn = T(K+2,K+1) - X2(K) X1(K)^T
+//   C      (warp 6)      TRSM of X2(K) = L(K+2,K); runs on its own clock (its input arrives late from the workers)
+//   IO0    (warp 7)      L(K,K), X1(K) -> global, done flags
+//   IO1    (warp 5)      T(K+1,K+1), T(K+2,K+1) (worker-updated) -> shared memory, one column ahead
+//   IO2    (warp 4)      X2(K) -> global, done flag
+// Hand-offs are monotone event counters in shared memory (value c+1 = "done for column c").
+constexpr int SP_WARPS = 8;
+constexpr int PSTR = 10, PANSZ = TILE*PSTR;     // potrf panel [row][8], row stride 10 doubles: conflict-free LDS.128 per row
+enum { EV_PAN = 0, EV_X1P = 4, EV_X2 = 8, EV_DIN = 9, EV_XNIN = 10, EV_ST_L = 11, EV_ST_X1 = 12, EV_ST_X2 = 13, EV_TK_D = 14, EV_TK_XN = 15, EV_N = 16 };
+
+__device__ __forceinline__ void ev_signal(volatile int* ev, int i, int v, int lane) {
+  __threadfence_block();
+  __syncwarp();
+  if (lane == 0) ev[i] = v;
+}
+__device__ __forceinline__ void ev_wait(volatile int* ev, int i, int v, int lane) {
+  if (lane == 0) { int spins = 0; while (ev[i] < v) { if (++spins > 16) __nanosleep(20); } }
+  __syncwarp();
+  __threadfence_block();
+}
+
+// The spine's code must stay small: a warp that runs thousands of straight-line instructions once per column is bound by
+// instruction fetch, not by the arithmetic (tools/ubench/potrf_bench.cu: 5.8k cycles per tile alone, 14-17k inside a
+// 25k-instruction kernel).  So the panel loops below are ROLLED; the register tile keeps static indices through
+// block-of-8 switches on the (warp-uniform) panel number.
+#define SPINE_BLOCK_SWITCH(p, BODY) \
+  do { if ((p) == 0) { constexpr int B8 = 0; BODY } else if ((p) == 1) { constexpr int B8 = 8; BODY } \
+       else if ((p) == 2) { constexpr int B8 = 16; BODY } else { constexpr int B8 = 24; BODY } } while (0)
+
+// Cholesky of a 32x32 tile held one row per lane, in 4 panels of 8 columns.  The 8x8 diagonal block of a panel is read
+// back from shared memory by EVERY lane and factored redundantly in registers, each lane solving its own row against it
+// on the way (no shuffles); the serial chain per column is rsqrt -> scale -> one FMA.  Finished panels are published:
+// sPan[p][row*PSTR + j] = L[row][8p + j], sIv[k] = 1 / L[k][k], event EV_PAN + p.
+__device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, double* sPan, double* sIv, volatile int* ev, int cval) {
+  bool ok = true;
+#pragma unroll 1
+  for (int p = 0; p < 4; p++) {
+    double* sP = sPan + p*PANSZ;
+    double x[8];
+    SPINE_BLOCK_SWITCH(p, {
+#pragma unroll
+      for (int j = 0; j < 8; j++) x[j] = row[B8 + j];
+    });
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sP + lane*PSTR + j) = make_double2(x[j], x[j + 1]);
+    __syncwarp();
+    double G[36];                                   // packed lower triangle, G[i(i+1)/2 + j] = block[i][j]
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) G[i*(i + 1)/2 + j] = sP[(8*p + i)*PSTR + j];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const double d = G[k*(k + 1)/2 + k];
+      if (!(d > 0.0)) ok = false;
+      const double inv = rsqrt(d);
+      if (lane == 8*p + k) sIv[8*p + k] = inv;
+      x[k] *= inv;
+#pragma unroll
+      for (int i = k + 1; i < 8; i++) G[i*(i + 1)/2 + k] *= inv;
+#pragma unroll
+      for (int j = k + 1; j < 8; j++) {
+        const double ljk = G[j*(j + 1)/2 + k];
+        x[j] -= x[k]*ljk;
+#pragma unroll
+        for (int i = j; i < 8; i++) G[i*(i + 1)/2 + j] -= G[i*(i + 1)/2 + k]*ljk;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sP + lane*PSTR + j) = make_double2(x[j], x[j + 1]);
+    ev_signal(ev, EV_PAN + p, cval, lane);
+    // rank-8 update of the columns behind the panel (blocks of 8 columns, static register indices)
+#pragma unroll
+    for (int blk = 1; blk < 4; blk++) {
+      if (blk > p) {
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) {
+          const int c = 8*blk + cc;
+          double acc = row[c];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const double2 b = *reinterpret_cast<const double2*>(sP + c*PSTR + j);
+            acc -= x[j]*b.x; acc -= x[j + 1]*b.y;
+          }
+          row[c] = acc;
+        }
+      }
+    }
+  }
+  return ok;
+}
+// x(row = lane) <- x * L^-T from the published panels; every finished panel of x is staged k-major (sX[k*32 + row]) and
+// announced on ev_out + p (ev_out < 0: no per-panel events)
+__device__ __forceinline__ void spine_trsm(double (&x)[TILE], int lane, const double* sPan, const double* sIv, volatile int* ev, int cval,
+                                           double* sX, int ev_out) {
+#pragma unroll 1
+  for (int p = 0; p < 4; p++) {
+    const double* sP = sPan + p*PANSZ;
+    ev_wait(ev, EV_PAN + p, cval, lane);
+    double xs[8];
+    SPINE_BLOCK_SWITCH(p, {
+#pragma unroll
+      for (int j = 0; j < 8; j++) xs[j] = x[B8 + j];
+    });
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+      const double l = xs[kk]*sIv[8*p + kk];
+      xs[kk] = l;
+#pragma unroll
+      for (int j = kk + 1; j < 8; j++) xs[j] -= l*sP[(8*p + j)*PSTR + kk];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) sX[(8*p + j)*TILE + lane] = xs[j];
+    if (ev_out >= 0) ev_signal(ev, ev_out + p, cval, lane);
+#pragma unroll
+    for (int blk = 1; blk < 4; blk++) {
+      if (blk > p) {
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) {
+          const int c = 8*blk + cc;
+          double acc = x[c];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const double2 b = *reinterpret_cast<const double2*>(sP + c*PSTR + j);
+            acc -= xs[j]*b.x; acc -= xs[j + 1]*b.y;
+          }
+          x[c] = acc;
+        }
+      }
+    }
+  }
+}
+// r(row = lane)[c] -= sum_{j < 8} A[lane][j] * Bm[c][j], both operands k-major panels (p[j*32 + row])
+__device__ __forceinline__ void spine_rank8(double (&r)[TILE], const double* pa, const double* pb, int lane) {
+  double own[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) own[j] = pa[j*TILE + lane];
+#pragma unroll
+  for (int c = 0; c < TILE; c += 2) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const double2 b = *reinterpret_cast<const double2*>(pb + j*TILE + c);
+      r[c] -= own[j]*b.x; r[c + 1] -= own[j]*b.y;
+    }
+  }
+}
+
+// full rank-32 update in four rank-8 steps (rolled); ev_base >= 0: wait for panel event ev_base + p before step p
+__device__ __forceinline__ void spine_rank32(double (&r)[TILE], const double* xa, const double* xb, volatile int* ev, int ev_base, int cval, int lane) {
+#pragma unroll 1
+  for (int p = 0; p < 4; p++) {
+    if (ev_base >= 0) ev_wait(ev, ev_base + p, cval, lane);
+    spine_rank8(r, xa + 8*p*TILE, xb + 8*p*TILE, lane);
+  }
+}
+
+__global__ void __launch_bounds__(SP_WARPS*32)
+band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fail) {
+  extern __shared__ __align__(16) double chol_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((int)blockIdx.x >= job.np) {
+    if (warp >= wk_warps) return;
+    chol_worker(job, ((int)blockIdx.x - job.np)*wk_warps + warp, ((int)gridDim.x - job.np)*wk_warps,
+                chol_smem + (size_t)warp*TILE2, chol_smem + (size_t)SP_WARPS*TILE2 + warp*TILE, lane, 3);
+    return;
+  }
+  const CholProb P = job.p[blockIdx.x];
+  const int WB = job.WB, W1 = WB + 1, NT = P.NT, Kbeg = P.Kbeg, Kend = P.Kend;
+  if (Kbeg >= Kend) return;
+  double* sPan = chol_smem;                   // [2][4][PANSZ]
+  double* sIv = sPan + 2*4*PANSZ;             // [2][32]
+  double* sX1 = sIv + 2*TILE;                 // [2][1024]  k-major
+  double* sX2 = sX1 + 2*TILE2;                // [2][1024]
+  double* sDin = sX2 + 2*TILE2;               // [2][1024]  column-major, as in global memory
+  double* sXnin = sDin + 2*TILE2;             // [2][1024]
+  volatile int* ev = reinterpret_cast<volatile int*>(sXnin + 2*TILE2);
+  if (threadIdx.x < EV_N) ev[threadIdx.x] = Kbeg;
+  __syncthreads();
+  int* done = P.done; int* pre = P.pre;
+  const bool x2 = WB >= 2;
+  double r[TILE];
+  if (warp == 0 || warp == 1) {
+    // ---------------------------------------------------------------- A pair: potrf / next diagonal tile
+    const int i = warp;
+    long long dbg[4] = {0, 0, 0, 0};
+    for (int c = Kbeg - 1; c < Kend; c++) {
+      if (c >= Kbeg && (c & 1) == i) {
+        const long long t0 = clock64();
+        ev_wait(ev, EV_ST_L, c - 1, lane);
+        const long long t1 = clock64();
+        if (!spine_potrf(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1) && lane == 0) atomicOr(fail, 2);
+        dbg[0] += clock64() - t1; dbg[1] += t1 - t0;
+      } else if (((c + 1) & 1) == i && c + 1 < NT) {
+        const long long t0 = clock64();
+        ev_wait(ev, EV_DIN, c + 2, lane);
+        const double* sd = sDin + ((c + 1) & 1)*TILE2;
+#pragma unroll
+        for (int col = 0; col < TILE; col++) r[col] = sd[col*TILE + lane];
+        ev_signal(ev, EV_TK_D, c + 2, lane);
+        const long long t1 = clock64();
+        // term 0: X2(c-1) = L(c+1, c-1), staged two columns ago and still in its buffer; term 1: X1(c), panel by panel
+#pragma unroll 1
+        for (int t = 0; t < 2; t++) {
+          if (t == 0 ? !(x2 && c - 1 >= Kbeg) : !(c >= Kbeg)) continue;
+          if (t == 0) ev_wait(ev, EV_X2, c, lane);
+          const double* xa = t == 0 ? sX2 + ((c - 1) & 1)*TILE2 : sX1 + (c & 1)*TILE2;
+          spine_rank32(r, xa, xa, ev, t == 0 ? -1 : EV_X1P, c + 1, lane);
+        }
+        const long long t2 = t1;
+        dbg[2] += t1 - t0; dbg[3] += clock64() - t2;
+        if (c + 1 == Kend) tile_store(P.tiles + (size_t)Kend*W1*TILE2, r, lane);   // not factored here: hand it back
+      }
+    }
+    if (blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) g_spine_dbg[i*4 + k] = dbg[k];
+  } else if (warp == 2 || warp == 3) {
+    // ---------------------------------------------------------------- B pair: X1 TRSM / next X1 input
+    const int i = warp - 2;
+    for (int c = Kbeg - 1; c < Kend; c++) {
+      if (c >= Kbeg && (c & 1) == i) {
+        if (c + 1 < NT) {
+          ev_wait(ev, EV_ST_X1, c - 1, lane);
+          spine_trsm(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, sX1 + (c & 1)*TILE2, EV_X1P);
+        }
+      } else if (((c + 1) & 1) == i && c + 2 < NT) {
+        ev_wait(ev, EV_XNIN, c + 2, lane);
+        const double* sd = sXnin + ((c + 1) & 1)*TILE2;
+#pragma unroll
+        for (int col = 0; col < TILE; col++) r[col] = sd[col*TILE + lane];
+        ev_signal(ev, EV_TK_XN, c + 2, lane);
+        if (x2 && c >= Kbeg) {
+          const double* xa = sX2 + (c & 1)*TILE2; const double* xb = sX1 + (c & 1)*TILE2;
+          ev_wait(ev, EV_X2, c + 1, lane);
+          spine_rank32(r, xa, xb, ev, EV_X1P, c + 1, lane);
+        }
+        if (c + 1 == Kend) tile_store(P.tiles + ((size_t)Kend*W1 + 1)*TILE2, r, lane);
+      }
+    }
+  } else if (warp == 6) {
+    // ---------------------------------------------------------------- C: X2 TRSM
+    if (x2) for (int c = Kbeg; c < Kend; c++) if (c + 2 < NT) {
+      wait_flag(pre + (size_t)c*W1 + 2, lane);
+      tile_load(P.tiles + ((size_t)c*W1 + 2)*TILE2, r, lane);
+      ev_wait(ev, EV_ST_X2, c - 1, lane);
+      spine_trsm(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, sX2 + (c & 1)*TILE2, -1);
+      ev_signal(ev, EV_X2, c + 1, lane);
+    }
+  } else if (warp == 7) {
+    // ---------------------------------------------------------------- IO0: L(c,c), X1(c) -> global
+    for (int c = Kbeg; c < Kend; c++) {
+      ev_wait(ev, EV_PAN + 3, c + 1, lane);
+      const double* pan = sPan + (c & 1)*4*PANSZ;
+      double* t = P.tiles + (size_t)c*W1*TILE2;
+#pragma unroll
+      for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(pan + p*PANSZ + lane*PSTR + j);
+          t[(8*p + j)*TILE + lane] = v.x; t[(8*p + j + 1)*TILE + lane] = v.y;
+        }
+      set_flag(done + (size_t)c*W1, lane);
+      ev_signal(ev, EV_ST_L, c + 1, lane);
+      if (c + 1 < NT) {
+        ev_wait(ev, EV_X1P + 3, c + 1, lane);
+        const double* sx = sX1 + (c & 1)*TILE2;
+#pragma unroll
+        for (int col = 0; col < TILE; col++) t[TILE2 + col*TILE + lane] = sx[col*TILE + lane];
+        set_flag(done + (size_t)c*W1 + 1, lane);
+        ev_signal(ev, EV_ST_X1, c + 1, lane);
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------- IO1: inputs of column c+1 -> shared memory
+    for (int c = Kbeg - 1; c < Kend; c++) if (c + 1 < NT) {
+      const double* t = P.tiles + (size_t)(c + 1)*W1*TILE2;
+      ev_wait(ev, EV_TK_D, c, lane);
+      wait_flag(pre + (size_t)(c + 1)*W1, lane);
+      tile_load(t, r, lane);
+      double* sd = sDin + ((c + 1) & 1)*TILE2;
+#pragma unroll
+      for (int col = 0; col < TILE; col++) sd[col*TILE + lane] = r[col];
+      ev_signal(ev, EV_DIN, c + 2, lane);
+      if (c + 2 < NT) {
+        ev_wait(ev, EV_TK_XN, c, lane);
+        wait_flag(pre + (size_t)(c + 1)*W1 + 1, lane);
+        tile_load(t + TILE2, r, lane);
+        double* sx = sXnin + ((c + 1) & 1)*TILE2;
+#pragma unroll
+        for (int col = 0; col < TILE; col++) sx[col*TILE + lane] = r[col];
+        ev_signal(ev, EV_XNIN, c + 2, lane);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- IO2: X2(c) -> global
+    if (x2) for (int c = Kbeg; c < Kend; c++) if (c + 2 < NT) {
+      ev_wait(ev, EV_X2, c + 1, lane);
+      const double* sx = sX2 + (c & 1)*TILE2;
+      double* t = P.tiles + ((size_t)c*W1 + 2)*TILE2;
+#pragma unroll
+      for (int col = 0; col < TILE; col++) t[col*TILE + lane] = sx[col*TILE + lane];
+      set_flag(done + (size_t)c*W1 + 2, lane);
+      ev_signal(ev, EV_ST_X2, c + 1, lane);
     }
   }
 }
@@ -610,7 +958,7 @@ band_backward_cluster_kernel(BackJob job) {
   }
 }
 
-static int g_max_blocks = 0;
+static int g_max_blocks = 0, g_spine_ver = 3, g_wk_warps = 4;
 static size_t g_chol_smem = 0;
 
 static void chol_init() {
@@ -620,23 +968,35 @@ static void chol_init() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // CTAs per SM: 1 keeps each spine CTA alone on its SM (DYNOBA_CHOL_BPS overrides for experiments)
   int bps = 1; if (const char* e = getenv("DYNOBA_CHOL_BPS")) bps = atoi(e) > 0 ? atoi(e) : 1;
-  const size_t need = (size_t)(1152 + 4*TILE2 + 256 + 64)*sizeof(double);
+  if (const char* e = getenv("DYNOBA_SPINE")) g_spine_ver = atoi(e) == 2 ? 2 : 3;
+  if (const char* e = getenv("DYNOBA_WK_WARPS")) g_wk_warps = std::max(1, std::min(SP_WARPS, atoi(e)));
+  if (g_spine_ver == 2) g_wk_warps = CH_WARPS;
+  const size_t need = g_spine_ver == 2 ? (size_t)(1152 + 4*TILE2 + 256 + 64)*sizeof(double)
+                                       : (size_t)(2*4*PANSZ + 2*TILE + 8*TILE2 + 64)*sizeof(double);   // >= the workers' [8][TILE2 + TILE]
   g_chol_smem = std::max(need, (size_t)(220*1024)/bps - 2048);
-  cudaFuncSetAttribute(band_cholesky_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_chol_smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, band_cholesky_dataflow_kernel, CH_WARPS*32, g_chol_smem);
+  const void* kern = g_spine_ver == 2 ? (const void*)band_cholesky_dataflow_kernel : (const void*)band_cholesky_dataflow_kernel_v3;
+  const int nthr = g_spine_ver == 2 ? CH_WARPS*32 : SP_WARPS*32;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_chol_smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, nthr, g_chol_smem);
   g_max_blocks = sms*(per > 0 ? per : 1);
 }
 static void chol_launch(const CholJob& job, int* fail, cudaStream_t s) {
   long long ntile = 0;
   for (int q = 0; q < job.np; q++) ntile += (long long)(job.p[q].NT - job.p[q].Kbeg)*(job.WB + 2);
   int grid = g_max_blocks;
-  const long long want = (ntile + CH_WARPS - 1)/CH_WARPS + job.np;
+  const long long want = (ntile + g_wk_warps - 1)/g_wk_warps + job.np;
   if (grid > want) grid = (int)want;
   if (grid < job.np + 1) grid = job.np + 1;
   CholJob j = job;
-  void* args[] = { (void*)&j, (void*)&fail };
   // cooperative launch only for its co-residency guarantee (the flag waits need every warp resident)
-  cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel, dim3(grid), dim3(CH_WARPS*32), args, g_chol_smem, s);
+  if (g_spine_ver == 2) {
+    void* args[] = { (void*)&j, (void*)&fail };
+    cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel, dim3(grid), dim3(CH_WARPS*32), args, g_chol_smem, s);
+  } else {
+    int wk = g_wk_warps;
+    void* args[] = { (void*)&j, (void*)&wk, (void*)&fail };
+    cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel_v3, dim3(grid), dim3(SP_WARPS*32), args, g_chol_smem, s);
+  }
 }
 
 int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, cudaStream_t s) {
@@ -649,15 +1009,40 @@ int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, 
   auto prob = [&](double* tiles, double* rhs, int NT, int kb, int ke, int* f) {
     CholProb p; p.tiles = tiles; p.rhs = rhs; p.NT = NT; p.Kbeg = kb; p.Kend = ke; p.done = f; p.pre = f + (size_t)NT*W1; p.ydone = f + (size_t)2*NT*W1; return p; };
   int launches = 0;
+  long long* dtrace = nullptr; const long long trace_len = (long long)NTA*(2*W1 + 1);
+  if (getenv("DYNOBA_CHOL_TRACE")) {
+    cudaMalloc(&dtrace, trace_len*sizeof(long long)); cudaMemsetAsync(dtrace, 0, trace_len*sizeof(long long), s);
+    cudaMemcpyToSymbolAsync(g_trace, &dtrace, sizeof(dtrace), 0, cudaMemcpyHostToDevice, s);
+    cudaMemcpyToSymbolAsync(g_trace_base, &fA, sizeof(fA), 0, cudaMemcpyHostToDevice, s);
+    cudaMemcpyToSymbolAsync(g_trace_len, &trace_len, sizeof(trace_len), 0, cudaMemcpyHostToDevice, s);
+  }
+  auto dump_trace = [&]() {     // after the first factorisation launch: flag-release times of columns in the middle of problem 0
+    if (!dtrace) return;
+    cudaStreamSynchronize(s);
+    std::vector<long long> ht(trace_len); cudaMemcpy(ht.data(), dtrace, trace_len*sizeof(long long), cudaMemcpyDeviceToHost);
+    long long* nul = nullptr; cudaMemcpyToSymbol(g_trace, &nul, sizeof(nul)); cudaFree(dtrace);
+    const int K0 = std::max(4, (B.two ? B.split_lo/TILE : NTA)/2), nd = std::min(W1, 8);
+    const long long t0 = ht[(size_t)K0*W1];
+    fprintf(stderr, "[trace] ns relative to done(K0,K0), K0 = %d; columns: done dd=0..%d | pre dd=0..2\n", K0, nd - 1);
+    for (int K = K0 - 2; K < K0 + 10; K++) {
+      fprintf(stderr, "[trace] K=%d done:", K);
+      for (int d = 0; d < nd; d++) fprintf(stderr, " %7lld", ht[(size_t)K*W1 + d] ? ht[(size_t)K*W1 + d] - t0 : -1);
+      fprintf(stderr, "  pre:");
+      for (int d = 0; d < std::min(W1, 3); d++) fprintf(stderr, " %7lld", ht[(size_t)NTA*W1 + (size_t)K*W1 + d] ? ht[(size_t)NTA*W1 + (size_t)K*W1 + d] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  };
   if (!B.two) {
     CholJob job; job.np = 1; job.WB = B.WB; job.p[0] = prob(B.tiles, B.rhs, B.NT, 0, B.NT, fA); job.p[1] = job.p[0];
     chol_launch(job, fail, s); launches++;
+    dump_trace();
     diag_inverse_kernel<<<(B.NT + 3)/4, 128, 0, s>>>(B.tiles, B.NT, B.WB, linv); launches++;
   } else {
     const int KmA = B.split_lo/TILE, KmB = NTB - (B.split_hi - B.split_lo)/TILE;
     CholJob job; job.np = 2; job.WB = B.WB;
     job.p[0] = prob(B.tiles, B.rhs, NTA, 0, KmA, fA); job.p[1] = prob(B.tiles2, B.rhs2, NTB, 0, KmB, fB);
     chol_launch(job, fail, s); launches++;                               // both halves, towards the middle
+    dump_trace();
     merge_middle_kernel<<<64, 256, 0, s>>>(B); launches++;
     cudaMemsetAsync(fA, 0, (size_t)NTA*(2*W1 + 1)*sizeof(int), s);
     CholJob mid; mid.np = 1; mid.WB = B.WB; mid.p[0] = prob(B.tiles, B.rhs, NTA, KmA, NTA, fA); mid.p[1] = mid.p[0];
@@ -667,7 +1052,9 @@ int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, 
   }
   if (getenv("DYNOBA_SPINE_DBG")) {
     long long hd[16]; cudaStreamSynchronize(s); cudaMemcpyFromSymbol(hd, g_spine_dbg, sizeof(hd));
-    const char* nm[12] = {"potrf", "store+stage+flag D", "barA", "wait+load Dnext half", "barB (trsm)", "gemm half + stage", "barC + reload", "-", "-", "-", "-", "loop"};
+    const char* nm2[12] = {"potrf", "store+stage+flag D", "barA", "wait+load Dnext half", "barB (trsm)", "gemm half + stage", "barC + reload", "-", "-", "-", "-", "loop"};
+    const char* nm3[12] = {"A0 potrf", "A0 wait L stored", "A0 wait D input", "A0 X1 rank-8 (+waits)", "A1 potrf", "A1 wait L stored", "A1 wait D input", "A1 X1 rank-8 (+waits)", "-", "-", "-", "-"};
+    const char** nm = g_spine_ver == 2 ? nm2 : nm3;
     for (int i = 0; i < 12; i++) fprintf(stderr, "[spine] %-22s %10.3f ms\n", nm[i], hd[i]/1.965e6);
   }
   return launches;

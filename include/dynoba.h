@@ -125,6 +125,9 @@ int dynoba_problem_info(dynoba_handle h, int32_t* reduced_dim, int32_t* bandwidt
 /* Materialising linearize of every factor at the current values (the roofline kernel).  Returns the
  * CUDA-event time of the linearize kernels alone in *ms (may be NULL). */
 int dynoba_linearize(dynoba_handle h, float* ms);
+/* Same, for the factor block of the block_index-th dynoba_add_factors call alone: one launch of the Jacobian-build
+ * kernel of that factor type, CUDA-event time in *ms, its algorithmic bytes in *bytes. */
+int dynoba_linearize_block(dynoba_handle h, int block_index, float* ms, int64_t* bytes);
 /* Whitened Jacobian A[n][dim][jcols] and rhs b[n][dim] of the block_index-th dynoba_add_factors call,
  * in the caller's factor order (valid after dynoba_linearize / dynoba_optimize). */
 int dynoba_get_linearization(dynoba_handle h, int block_index, double* A, double* b);
