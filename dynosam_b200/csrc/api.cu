@@ -36,7 +36,7 @@ struct HostBlock {
   DevBlock dev{};
   bool simple = false, pose_only = false;
   int part_off = 0, bs_off = 0;
-  DevWindows win{}; bool use_window = false; int win_only_v1 = 0;
+  DevWindows win{}; bool use_window = false; bool all_window = false;   // all_window: no group left for the per-landmark atomics kernel
 };
 
 }  // namespace
@@ -516,7 +516,7 @@ static int finalize_impl(dynoba_solver* h) {
       b.simple = true;
       // ---- window decomposition (kernels_window.cu) for the 3-dof landmark types
       const bool win_type = b.type == F_POSE2POINT3 || b.type == F_STEREO3 || b.type == F_HYBRID3 || b.type == F_HYBRID_STEREO3;
-      b.use_window = false; b.win = DevWindows{};
+      b.use_window = false; b.all_window = false; b.win = DevWindows{};
       if (win_type && !gl.empty() && !getenv("DYNOBA_NO_WINDOW")) {
         const int ng = (int)gl.size(), NPs = ti.npose;
         std::vector<unsigned char> gwin(ng, 0), lvar((size_t)NPs*stride, 0);
@@ -599,6 +599,7 @@ static int finalize_impl(dynoba_solver* h) {
         if ((rc = dalloc(h, &dslots, (size_t)n*NPs*WIN_SLOT_DOUBLES))) return rc;
         b.win.n_jobs = (int)jobs.size(); b.win.jobs = djobs; b.win.batches = dbat; b.win.chunk_nloc = dnl; b.win.cvars = dcv; b.win.lvar = dlv; b.win.grp_win = dgw; b.win.slots = dslots;
         b.use_window = true;
+        { size_t nw = 0; for (int g = 0; g < ng; g++) nw += gwin[g] == 1 || gl[g] < 0; b.all_window = nw == (size_t)ng; }
       }
     }
     lap("  blk groups+windows");
@@ -688,7 +689,7 @@ static int build_reduced(dynoba_solver* h, double lambda) {
     if (b.pose_only) h->launches += launch_pose_factors(b.dev, h->band, h->stream);
     else {
       if (b.use_window) h->launches += launch_schur_window(b.dev, b.win, h->band, lambda, h->fail, h->stream);
-      h->launches += launch_schur_simple(b.dev, b.use_window ? b.win.grp_win : nullptr, h->band, lambda, h->fail, h->stream);
+      if (!b.all_window) h->launches += launch_schur_simple(b.dev, b.use_window ? b.win.grp_win : nullptr, h->band, lambda, h->fail, h->stream);
     }
   }
   h->launches += launch_schur_general(h->gen, h->band, lambda, h->fail, h->stream);

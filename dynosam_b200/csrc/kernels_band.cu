@@ -50,8 +50,13 @@ __device__ __forceinline__ void trace_flag(int* f) {
     if (off >= 0 && off < g_trace_len) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_trace[off] = t; }
   }
 }
+__device__ long long* g_strace = nullptr;     // [NT][16] spine event times of problem 0 (DYNOBA_CHOL_TRACE)
+__device__ __forceinline__ void strace(int col, int slot, int lane) {
+  if (g_strace && blockIdx.x == 0 && lane == 0 && col >= 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_strace[(size_t)col*16 + slot] = t; }
+}
 __device__ __forceinline__ void set_flag(int* f, int lane) {
-  __threadfence();      // every lane's tile stores are performed at gpu scope before the flag is released
+  // the lanes' tile stores are ordered before lane 0's release by the warp barrier (release is cumulative).  No
+  // __threadfence(): that is MEMBAR.SC.GPU + ERRBAR + CCTL.IVALL, microseconds per flag on the two-die part.
   __syncwarp();
   if (lane == 0) { st_release(f, 1); trace_flag(f); }
 }
@@ -411,6 +416,47 @@ band_cholesky_dataflow_kernel(CholJob job, int* __restrict__ fail) {
 }
 
 // Worker warp `wid` of `nworkers`: tile tasks in column-major order (see the role table above the kernels).
+// ---- fp64 tensor-core tile update for the workers: T(32x32) -= LI LK^T as 128 x mma.m8n8k4 (DMMA).  The FMA version
+// reads its B operand from shared memory (one LDS.128 per two FMAs) and saturates the SM's shared-memory pipe with four
+// warps at about half the fp64 rate; the MMA fragments live in registers, so the inner loop has no memory operation.
+// Fragment maps (g = lane >> 2, q = lane & 3):  A/B operand block b, k-step kb: L[8b + g][4kb + q];
+// accumulator block (rb, cb): T[8rb + g][8cb + 2q + {0, 1}].  Tiles are column-major (element (r, c) at c*32 + r).
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void frag_load(const double* t, double (&f)[TILE], int lane) {
+  const double* p = t + (lane & 3)*TILE + (lane >> 2);
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) f[b*8 + kb] = __ldcg(p + 4*kb*TILE + 8*b);
+}
+__device__ __forceinline__ void cfrag_load(const double* t, double (&c)[TILE], int lane) {
+  const double* p = t + 2*(lane & 3)*TILE + (lane >> 2);
+#pragma unroll
+  for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+    for (int cb = 0; cb < 4; cb++) { c[(rb*4 + cb)*2] = __ldcg(p + 8*cb*TILE + 8*rb); c[(rb*4 + cb)*2 + 1] = __ldcg(p + (8*cb + 1)*TILE + 8*rb); }
+}
+__device__ __forceinline__ void cfrag_store(double* t, const double (&c)[TILE], int lane) {
+  double* p = t + 2*(lane & 3)*TILE + (lane >> 2);
+#pragma unroll
+  for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+    for (int cb = 0; cb < 4; cb++) { p[8*cb*TILE + 8*rb] = c[(rb*4 + cb)*2]; p[(8*cb + 1)*TILE + 8*rb] = c[(rb*4 + cb)*2 + 1]; }
+}
+// c -= A B^T with A, B given as operand fragments
+__device__ __forceinline__ void frag_gemm_sub(double (&c)[TILE], const double (&a)[TILE], const double (&b)[TILE]) {
+#pragma unroll
+  for (int kb = 0; kb < 8; kb++)
+#pragma unroll
+    for (int rb = 0; rb < 4; rb++) {
+      const double na = -a[rb*8 + kb];
+#pragma unroll
+      for (int cb = 0; cb < 4; cb++) dmma(c[(rb*4 + cb)*2], c[(rb*4 + cb)*2 + 1], na, b[cb*8 + kb]);
+    }
+}
+
 // dd0_lag: the diagonal tile (dd == 0) receives the worker updates from columns J <= K - dd0_lag only (the spine owns the rest).
 __device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nworkers, double* sb, double* sinv, int lane, int dd0_lag) {
   const int WB = job.WB, W1 = WB + 1;
@@ -460,29 +506,36 @@ __device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nwo
     }
     if (I >= NT) continue;
     const size_t o = (size_t)K*W1 + dd;
-    double acc[TILE];
+    double acc[TILE];                       // accumulator fragments while the updates run, one row per lane afterwards
     double* tp = P.tiles + o*TILE2;
-    tile_load(tp, acc, lane);
+    cfrag_load(tp, acc, lane);
     const int Jlo = max(P.Kbeg, I - WB);
     // the spine finishes the tiles of columns <= Kend itself: it owns the last (dd0_lag - 1) updates of a diagonal tile and
     // the last update of a first sub-diagonal tile
     const int Jhi = min(dd == 0 ? (K <= P.Kend ? K - dd0_lag : K - 1) : (dd == 1 ? K - 2 : K - 1), P.Kend - 1);
     for (int J = Jlo; J <= Jhi; J++) {
       const size_t oI = (size_t)J*W1 + (I - J), oK = (size_t)J*W1 + (K - J);
+      double fb[TILE];
       wait_flag(done + oK, lane);
-      __syncwarp();
-#pragma unroll
-      for (int cc = 0; cc < TILE; cc++) sb[cc*TILE + lane] = __ldcg(P.tiles + oK*TILE2 + cc*TILE + lane);
-      wait_flag(done + oI, lane);
-      double a[TILE];
-      tile_load(P.tiles + oI*TILE2, a, lane);
-      __syncwarp();
-      tile_gemm_sub(acc, a, sb);
+      frag_load(P.tiles + oK*TILE2, fb, lane);
+      if (dd == 0) frag_gemm_sub(acc, fb, fb);
+      else {
+        double fa[TILE];
+        wait_flag(done + oI, lane);
+        frag_load(P.tiles + oI*TILE2, fa, lane);
+        frag_gemm_sub(acc, fa, fb);
+      }
     }
     if (dd <= 2 || K >= P.Kend) {
-      tile_store(tp, acc, lane);
+      cfrag_store(tp, acc, lane);
       set_flag(pre + o, lane);
     } else {
+      // accumulator fragments -> one row per lane, through the warp's shared-memory tile
+      __syncwarp();
+      cfrag_store(sb, acc, lane);
+      __syncwarp();
+#pragma unroll
+      for (int cc = 0; cc < TILE; cc++) acc[cc] = sb[cc*TILE + lane];
       const size_t oD = (size_t)K*W1;
       wait_flag(done + oD, lane);
       __syncwarp();
@@ -506,24 +559,30 @@ __device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nwo
 //                        D(K+1) = T(K+1,K+1) - X2(K-1) X2(K-1)^T - X1(K) X1(K)^T  (rank-8 updates as X1 panels appear)
 //   B pair (warps 2, 3)  alternate between the TRSM of X1(K) = L(K+1,K), one panel behind the potrf, and accumulating
 //                        Xn = T(K+2,K+1) - X2(K) X1(K)^T
-//   C      (warp 6)      TRSM of X2(K) = L(K+2,K); runs on its own clock (its input arrives late from the workers)
+//   C      (warp 6)      TRSM of X2(K) = L(K+2,K) and its store; runs on its own clock (its input arrives late from the workers)
 //   IO0    (warp 7)      L(K,K), X1(K) -> global, done flags
 //   IO1    (warp 5)      T(K+1,K+1), T(K+2,K+1) (worker-updated) -> shared memory, one column ahead
-//   IO2    (warp 4)      X2(K) -> global, done flag
 // Hand-offs are monotone event counters in shared memory (value c+1 = "done for column c").
 constexpr int SP_WARPS = 8;
-constexpr int PSTR = 10, PANSZ = TILE*PSTR;     // potrf panel [row][8], row stride 10 doubles: conflict-free LDS.128 per row
+constexpr int PSTR = 10, PANSZ = TILE*PSTR;
+constexpr int TS = 40, TSZ = TILE*TS;      // column stride of the spine's shared-memory tiles: conflict-free MMA operand loads     // potrf panel [row][8], row stride 10 doubles: conflict-free LDS.128 per row
 enum { EV_PAN = 0, EV_X1P = 4, EV_X2 = 8, EV_DIN = 9, EV_XNIN = 10, EV_ST_L = 11, EV_ST_X1 = 12, EV_ST_X2 = 13, EV_TK_D = 14, EV_TK_XN = 15, EV_N = 16 };
 
 __device__ __forceinline__ void ev_signal(volatile int* ev, int i, int v, int lane) {
-  __threadfence_block();
   __syncwarp();
-  if (lane == 0) ev[i] = v;
+  if (lane == 0) asm volatile("st.release.cta.shared.s32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared((const void*)(ev + i))), "r"(v) : "memory");
 }
 __device__ __forceinline__ void ev_wait(volatile int* ev, int i, int v, int lane) {
-  if (lane == 0) { int spins = 0; while (ev[i] < v) { if (++spins > 16) __nanosleep(20); } }
+  if (lane == 0) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared((const void*)(ev + i));
+    int cur, spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(cur) : "r"(a) : "memory");
+      if (cur >= v) break;
+      if (++spins > 16) __nanosleep(20);
+    }
+  }
   __syncwarp();
-  __threadfence_block();
 }
 
 // The spine's code must stay small: a warp that runs thousands of straight-line instructions once per column is bound by
@@ -538,10 +597,11 @@ __device__ __forceinline__ void ev_wait(volatile int* ev, int i, int v, int lane
 // back from shared memory by EVERY lane and factored redundantly in registers, each lane solving its own row against it
 // on the way (no shuffles); the serial chain per column is rsqrt -> scale -> one FMA.  Finished panels are published:
 // sPan[p][row*PSTR + j] = L[row][8p + j], sIv[k] = 1 / L[k][k], event EV_PAN + p.
-__device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, double* sPan, double* sIv, volatile int* ev, int cval) {
+__device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, double* sPan, double* sIv, volatile int* ev, int cval, long long (&prof)[3]) {
   bool ok = true;
 #pragma unroll 1
   for (int p = 0; p < 4; p++) {
+    const long long tp0 = clock64();
     double* sP = sPan + p*PANSZ;
     double x[8];
     SPINE_BLOCK_SWITCH(p, {
@@ -557,6 +617,7 @@ __device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, doubl
 #pragma unroll
       for (int j = 0; j <= i; j++) G[i*(i + 1)/2 + j] = sP[(8*p + i)*PSTR + j];
     __syncwarp();
+    const long long tp1 = clock64();
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const double d = G[k*(k + 1)/2 + k];
@@ -574,6 +635,7 @@ __device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, doubl
         for (int i = j; i < 8; i++) G[i*(i + 1)/2 + j] -= G[i*(i + 1)/2 + k]*ljk;
       }
     }
+    const long long tp2 = clock64();
 #pragma unroll
     for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sP + lane*PSTR + j) = make_double2(x[j], x[j + 1]);
     ev_signal(ev, EV_PAN + p, cval, lane);
@@ -594,10 +656,12 @@ __device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, doubl
         }
       }
     }
+    const long long tp3 = clock64();
+    prof[0] += tp1 - tp0; prof[1] += tp2 - tp1; prof[2] += tp3 - tp2;
   }
   return ok;
 }
-// x(row = lane) <- x * L^-T from the published panels; every finished panel of x is staged k-major (sX[k*32 + row]) and
+// x(row = lane) <- x * L^-T from the published panels; every finished panel of x is staged k-major (sX[k*TS + row]) and
 // announced on ev_out + p (ev_out < 0: no per-panel events)
 __device__ __forceinline__ void spine_trsm(double (&x)[TILE], int lane, const double* sPan, const double* sIv, volatile int* ev, int cval,
                                            double* sX, int ev_out) {
@@ -618,7 +682,7 @@ __device__ __forceinline__ void spine_trsm(double (&x)[TILE], int lane, const do
       for (int j = kk + 1; j < 8; j++) xs[j] -= l*sP[(8*p + j)*PSTR + kk];
     }
 #pragma unroll
-    for (int j = 0; j < 8; j++) sX[(8*p + j)*TILE + lane] = xs[j];
+    for (int j = 0; j < 8; j++) sX[(8*p + j)*TS + lane] = xs[j];
     if (ev_out >= 0) ev_signal(ev, ev_out + p, cval, lane);
 #pragma unroll
     for (int blk = 1; blk < 4; blk++) {
@@ -638,28 +702,56 @@ __device__ __forceinline__ void spine_trsm(double (&x)[TILE], int lane, const do
     }
   }
 }
-// r(row = lane)[c] -= sum_{j < 8} A[lane][j] * Bm[c][j], both operands k-major panels (p[j*32 + row])
-__device__ __forceinline__ void spine_rank8(double (&r)[TILE], const double* pa, const double* pb, int lane) {
-  double own[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) own[j] = pa[j*TILE + lane];
-#pragma unroll
-  for (int c = 0; c < TILE; c += 2) {
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const double2 b = *reinterpret_cast<const double2*>(pb + j*TILE + c);
-      r[c] -= own[j]*b.x; r[c + 1] -= own[j]*b.y;
-    }
-  }
-}
-
-// full rank-32 update in four rank-8 steps (rolled); ev_base >= 0: wait for panel event ev_base + p before step p
-__device__ __forceinline__ void spine_rank32(double (&r)[TILE], const double* xa, const double* xb, volatile int* ev, int ev_base, int cval, int lane) {
+// Rank-32 update of an accumulator tile held as MMA fragments (see frag_gemm_sub): c -= XA XB^T, XA / XB k-major tiles in
+// shared memory with column stride TS, applied in four rank-8 steps (two k-steps of the m8n8k4 MMA each) as the panels
+// of XB appear (ev_base >= 0: wait for event ev_base + p first).  16 LDS.64 + 32 DMMA per step: next to nothing on the
+// shared-memory pipe, which the FMA formulation (one LDS.128 per two FMAs) saturates when several spine warps run it.
+__device__ __forceinline__ void spine_rank32(double (&c)[TILE], const double* xa, const double* xb, bool same,
+                                             volatile int* ev, int ev_base, int cval, int lane) {
+  const int off = (lane & 3)*TS + (lane >> 2);
 #pragma unroll 1
   for (int p = 0; p < 4; p++) {
     if (ev_base >= 0) ev_wait(ev, ev_base + p, cval, lane);
-    spine_rank8(r, xa + 8*p*TILE, xb + 8*p*TILE, lane);
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+      const int kb = 2*p + kk;
+      double fa[4], fb[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) fb[b] = xb[off + 4*kb*TS + 8*b];
+#pragma unroll
+      for (int b = 0; b < 4; b++) fa[b] = same ? -fb[b] : -xa[off + 4*kb*TS + 8*b];
+#pragma unroll
+      for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) dmma(c[(rb*4 + cb)*2], c[(rb*4 + cb)*2 + 1], fa[rb], fb[cb]);
+    }
   }
+}
+// accumulator fragments <-> shared-memory tile with column stride S
+template <int S>
+__device__ __forceinline__ void cfrag_load_s(const double* t, double (&c)[TILE], int lane) {
+  const double* p = t + 2*(lane & 3)*S + (lane >> 2);
+#pragma unroll
+  for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+    for (int cb = 0; cb < 4; cb++) { c[(rb*4 + cb)*2] = p[8*cb*S + 8*rb]; c[(rb*4 + cb)*2 + 1] = p[(8*cb + 1)*S + 8*rb]; }
+}
+template <int S>
+__device__ __forceinline__ void cfrag_store_s(double* t, const double (&c)[TILE], int lane) {
+  double* p = t + 2*(lane & 3)*S + (lane >> 2);
+#pragma unroll
+  for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+    for (int cb = 0; cb < 4; cb++) { p[8*cb*S + 8*rb] = c[(rb*4 + cb)*2]; p[(8*cb + 1)*S + 8*rb] = c[(rb*4 + cb)*2 + 1]; }
+}
+// accumulator fragments -> one row per lane through a private shared-memory tile
+__device__ __forceinline__ void cfrag_to_rows(double (&r)[TILE], double* scr, int lane) {
+  __syncwarp();
+  cfrag_store_s<TILE>(scr, r, lane);
+  __syncwarp();
+#pragma unroll
+  for (int col = 0; col < TILE; col++) r[col] = scr[col*TILE + lane];
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(SP_WARPS*32)
@@ -677,11 +769,12 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
   if (Kbeg >= Kend) return;
   double* sPan = chol_smem;                   // [2][4][PANSZ]
   double* sIv = sPan + 2*4*PANSZ;             // [2][32]
-  double* sX1 = sIv + 2*TILE;                 // [2][1024]  k-major
-  double* sX2 = sX1 + 2*TILE2;                // [2][1024]
-  double* sDin = sX2 + 2*TILE2;               // [2][1024]  column-major, as in global memory
-  double* sXnin = sDin + 2*TILE2;             // [2][1024]
-  volatile int* ev = reinterpret_cast<volatile int*>(sXnin + 2*TILE2);
+  double* sX1 = sIv + 2*TILE;                 // [2][TSZ]  k-major, column stride TS
+  double* sX2 = sX1 + 2*TSZ;                  // [2][TSZ]
+  double* sDin = sX2 + 2*TSZ;                 // [2][TSZ]  column-major, column stride TS
+  double* sXnin = sDin + 2*TSZ;               // [2][TSZ]
+  double* sScr = sXnin + 2*TSZ;               // [4][TILE2] layout-conversion scratch of the A / B warps
+  volatile int* ev = reinterpret_cast<volatile int*>(sScr + 4*TILE2);
   if (threadIdx.x < EV_N) ev[threadIdx.x] = Kbeg;
   __syncthreads();
   int* done = P.done; int* pre = P.pre;
@@ -690,36 +783,39 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
   if (warp == 0 || warp == 1) {
     // ---------------------------------------------------------------- A pair: potrf / next diagonal tile
     const int i = warp;
-    long long dbg[4] = {0, 0, 0, 0};
+    long long dbg[4] = {0, 0, 0, 0}, prof[3] = {0, 0, 0};
     for (int c = Kbeg - 1; c < Kend; c++) {
       if (c >= Kbeg && (c & 1) == i) {
         const long long t0 = clock64();
         ev_wait(ev, EV_ST_L, c - 1, lane);
         const long long t1 = clock64();
-        if (!spine_potrf(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1) && lane == 0) atomicOr(fail, 2);
+        strace(c, 0, lane);
+        if (!spine_potrf(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, prof) && lane == 0) atomicOr(fail, 2);
         dbg[0] += clock64() - t1; dbg[1] += t1 - t0;
+        strace(c, 1, lane);
       } else if (((c + 1) & 1) == i && c + 1 < NT) {
         const long long t0 = clock64();
         ev_wait(ev, EV_DIN, c + 2, lane);
-        const double* sd = sDin + ((c + 1) & 1)*TILE2;
-#pragma unroll
-        for (int col = 0; col < TILE; col++) r[col] = sd[col*TILE + lane];
+        cfrag_load_s<TS>(sDin + ((c + 1) & 1)*TSZ, r, lane);      // r: accumulator fragments until cfrag_to_rows
         ev_signal(ev, EV_TK_D, c + 2, lane);
         const long long t1 = clock64();
+        strace(c + 1, 2, lane);
         // term 0: X2(c-1) = L(c+1, c-1), staged two columns ago and still in its buffer; term 1: X1(c), panel by panel
 #pragma unroll 1
         for (int t = 0; t < 2; t++) {
           if (t == 0 ? !(x2 && c - 1 >= Kbeg) : !(c >= Kbeg)) continue;
-          if (t == 0) ev_wait(ev, EV_X2, c, lane);
-          const double* xa = t == 0 ? sX2 + ((c - 1) & 1)*TILE2 : sX1 + (c & 1)*TILE2;
-          spine_rank32(r, xa, xa, ev, t == 0 ? -1 : EV_X1P, c + 1, lane);
+          if (t == 0) { ev_wait(ev, EV_X2, c, lane); strace(c + 1, 3, lane); } else strace(c + 1, 4, lane);
+          const double* xa = t == 0 ? sX2 + ((c - 1) & 1)*TSZ : sX1 + (c & 1)*TSZ;
+          spine_rank32(r, xa, xa, true, ev, t == 0 ? -1 : EV_X1P, c + 1, lane);
         }
+        cfrag_to_rows(r, sScr + i*TILE2, lane);
         const long long t2 = t1;
+        strace(c + 1, 5, lane);
         dbg[2] += t1 - t0; dbg[3] += clock64() - t2;
         if (c + 1 == Kend) tile_store(P.tiles + (size_t)Kend*W1*TILE2, r, lane);   // not factored here: hand it back
       }
     }
-    if (blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) g_spine_dbg[i*4 + k] = dbg[k];
+    if (blockIdx.x == 0 && lane == 0) { for (int k = 0; k < 4; k++) g_spine_dbg[i*4 + k] = dbg[k]; if (i == 0) for (int k = 0; k < 3; k++) g_spine_dbg[8 + k] = prof[k]; }
   } else if (warp == 2 || warp == 3) {
     // ---------------------------------------------------------------- B pair: X1 TRSM / next X1 input
     const int i = warp - 2;
@@ -727,19 +823,22 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
       if (c >= Kbeg && (c & 1) == i) {
         if (c + 1 < NT) {
           ev_wait(ev, EV_ST_X1, c - 1, lane);
-          spine_trsm(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, sX1 + (c & 1)*TILE2, EV_X1P);
+          strace(c, 6, lane);
+          spine_trsm(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, sX1 + (c & 1)*TSZ, EV_X1P);
+          strace(c, 7, lane);
         }
       } else if (((c + 1) & 1) == i && c + 2 < NT) {
         ev_wait(ev, EV_XNIN, c + 2, lane);
-        const double* sd = sXnin + ((c + 1) & 1)*TILE2;
-#pragma unroll
-        for (int col = 0; col < TILE; col++) r[col] = sd[col*TILE + lane];
+        cfrag_load_s<TS>(sXnin + ((c + 1) & 1)*TSZ, r, lane);
         ev_signal(ev, EV_TK_XN, c + 2, lane);
+        strace(c + 1, 8, lane);
         if (x2 && c >= Kbeg) {
-          const double* xa = sX2 + (c & 1)*TILE2; const double* xb = sX1 + (c & 1)*TILE2;
           ev_wait(ev, EV_X2, c + 1, lane);
-          spine_rank32(r, xa, xb, ev, EV_X1P, c + 1, lane);
+          strace(c + 1, 9, lane);
+          spine_rank32(r, sX2 + (c & 1)*TSZ, sX1 + (c & 1)*TSZ, false, ev, EV_X1P, c + 1, lane);
+          strace(c + 1, 10, lane);
         }
+        cfrag_to_rows(r, sScr + (2 + i)*TILE2, lane);
         if (c + 1 == Kend) tile_store(P.tiles + ((size_t)Kend*W1 + 1)*TILE2, r, lane);
       }
     }
@@ -748,9 +847,18 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
     if (x2) for (int c = Kbeg; c < Kend; c++) if (c + 2 < NT) {
       wait_flag(pre + (size_t)c*W1 + 2, lane);
       tile_load(P.tiles + ((size_t)c*W1 + 2)*TILE2, r, lane);
-      ev_wait(ev, EV_ST_X2, c - 1, lane);
-      spine_trsm(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, sX2 + (c & 1)*TILE2, -1);
+      strace(c, 11, lane);
+      spine_trsm(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, sX2 + (c & 1)*TSZ, -1);
       ev_signal(ev, EV_X2, c + 1, lane);
+      strace(c, 12, lane);
+      // publish X2(c) from its staged copy (this warp runs on its own clock: the store is off the spine's critical path)
+      {
+        const double* sx = sX2 + (c & 1)*TSZ;
+        double* t = P.tiles + ((size_t)c*W1 + 2)*TILE2;
+#pragma unroll
+        for (int col = 0; col < TILE; col++) t[col*TILE + lane] = sx[col*TS + lane];
+      }
+      set_flag(done + (size_t)c*W1 + 2, lane);
     }
   } else if (warp == 7) {
     // ---------------------------------------------------------------- IO0: L(c,c), X1(c) -> global
@@ -769,9 +877,9 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
       ev_signal(ev, EV_ST_L, c + 1, lane);
       if (c + 1 < NT) {
         ev_wait(ev, EV_X1P + 3, c + 1, lane);
-        const double* sx = sX1 + (c & 1)*TILE2;
+        const double* sx = sX1 + (c & 1)*TSZ;
 #pragma unroll
-        for (int col = 0; col < TILE; col++) t[TILE2 + col*TILE + lane] = sx[col*TILE + lane];
+        for (int col = 0; col < TILE; col++) t[TILE2 + col*TILE + lane] = sx[col*TS + lane];
         set_flag(done + (size_t)c*W1 + 1, lane);
         ev_signal(ev, EV_ST_X1, c + 1, lane);
       }
@@ -783,32 +891,22 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
       ev_wait(ev, EV_TK_D, c, lane);
       wait_flag(pre + (size_t)(c + 1)*W1, lane);
       tile_load(t, r, lane);
-      double* sd = sDin + ((c + 1) & 1)*TILE2;
+      double* sd = sDin + ((c + 1) & 1)*TSZ;
 #pragma unroll
-      for (int col = 0; col < TILE; col++) sd[col*TILE + lane] = r[col];
+      for (int col = 0; col < TILE; col++) sd[col*TS + lane] = r[col];
       ev_signal(ev, EV_DIN, c + 2, lane);
       if (c + 2 < NT) {
         ev_wait(ev, EV_TK_XN, c, lane);
         wait_flag(pre + (size_t)(c + 1)*W1 + 1, lane);
         tile_load(t + TILE2, r, lane);
-        double* sx = sXnin + ((c + 1) & 1)*TILE2;
+        double* sx = sXnin + ((c + 1) & 1)*TSZ;
 #pragma unroll
-        for (int col = 0; col < TILE; col++) sx[col*TILE + lane] = r[col];
+        for (int col = 0; col < TILE; col++) sx[col*TS + lane] = r[col];
         ev_signal(ev, EV_XNIN, c + 2, lane);
       }
     }
-  } else {
-    // ---------------------------------------------------------------- IO2: X2(c) -> global
-    if (x2) for (int c = Kbeg; c < Kend; c++) if (c + 2 < NT) {
-      ev_wait(ev, EV_X2, c + 1, lane);
-      const double* sx = sX2 + (c & 1)*TILE2;
-      double* t = P.tiles + ((size_t)c*W1 + 2)*TILE2;
-#pragma unroll
-      for (int col = 0; col < TILE; col++) t[col*TILE + lane] = sx[col*TILE + lane];
-      set_flag(done + (size_t)c*W1 + 2, lane);
-      ev_signal(ev, EV_ST_X2, c + 1, lane);
-    }
   }
+  // warp 4 has no role: it leaves scheduler 0 to the A warp that issues there
 }
 
 // sums the two Schur complements left in the middle separator: A.M += flip(B.M), A.rhs_M += flip(B.rhs_M)
@@ -972,7 +1070,7 @@ static void chol_init() {
   if (const char* e = getenv("DYNOBA_WK_WARPS")) g_wk_warps = std::max(1, std::min(SP_WARPS, atoi(e)));
   if (g_spine_ver == 2) g_wk_warps = CH_WARPS;
   const size_t need = g_spine_ver == 2 ? (size_t)(1152 + 4*TILE2 + 256 + 64)*sizeof(double)
-                                       : (size_t)(2*4*PANSZ + 2*TILE + 8*TILE2 + 64)*sizeof(double);   // >= the workers' [8][TILE2 + TILE]
+                                       : (size_t)(2*4*PANSZ + 2*TILE + 8*TSZ + 4*TILE2 + 64)*sizeof(double);   // >= the workers' [8][TILE2 + TILE]
   g_chol_smem = std::max(need, (size_t)(220*1024)/bps - 2048);
   const void* kern = g_spine_ver == 2 ? (const void*)band_cholesky_dataflow_kernel : (const void*)band_cholesky_dataflow_kernel_v3;
   const int nthr = g_spine_ver == 2 ? CH_WARPS*32 : SP_WARPS*32;
@@ -1009,12 +1107,14 @@ int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, 
   auto prob = [&](double* tiles, double* rhs, int NT, int kb, int ke, int* f) {
     CholProb p; p.tiles = tiles; p.rhs = rhs; p.NT = NT; p.Kbeg = kb; p.Kend = ke; p.done = f; p.pre = f + (size_t)NT*W1; p.ydone = f + (size_t)2*NT*W1; return p; };
   int launches = 0;
-  long long* dtrace = nullptr; const long long trace_len = (long long)NTA*(2*W1 + 1);
+  long long* dtrace = nullptr; long long* dstrace = nullptr; const long long trace_len = (long long)NTA*(2*W1 + 1);
   if (getenv("DYNOBA_CHOL_TRACE")) {
     cudaMalloc(&dtrace, trace_len*sizeof(long long)); cudaMemsetAsync(dtrace, 0, trace_len*sizeof(long long), s);
     cudaMemcpyToSymbolAsync(g_trace, &dtrace, sizeof(dtrace), 0, cudaMemcpyHostToDevice, s);
     cudaMemcpyToSymbolAsync(g_trace_base, &fA, sizeof(fA), 0, cudaMemcpyHostToDevice, s);
     cudaMemcpyToSymbolAsync(g_trace_len, &trace_len, sizeof(trace_len), 0, cudaMemcpyHostToDevice, s);
+    cudaMalloc(&dstrace, (size_t)NTA*16*sizeof(long long)); cudaMemsetAsync(dstrace, 0, (size_t)NTA*16*sizeof(long long), s);
+    cudaMemcpyToSymbolAsync(g_strace, &dstrace, sizeof(dstrace), 0, cudaMemcpyHostToDevice, s);
   }
   auto dump_trace = [&]() {     // after the first factorisation launch: flag-release times of columns in the middle of problem 0
     if (!dtrace) return;
@@ -1029,6 +1129,14 @@ int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, 
       for (int d = 0; d < nd; d++) fprintf(stderr, " %7lld", ht[(size_t)K*W1 + d] ? ht[(size_t)K*W1 + d] - t0 : -1);
       fprintf(stderr, "  pre:");
       for (int d = 0; d < std::min(W1, 3); d++) fprintf(stderr, " %7lld", ht[(size_t)NTA*W1 + (size_t)K*W1 + d] ? ht[(size_t)NTA*W1 + (size_t)K*W1 + d] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+    std::vector<long long> hs((size_t)NTA*16); cudaMemcpy(hs.data(), dstrace, hs.size()*sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpyToSymbol(g_strace, &nul, sizeof(nul)); cudaFree(dstrace);
+    fprintf(stderr, "[strace] potrf start,end | D: taken, X2 seen, X1 term start, done | X1 trsm start,end | Xn: taken, X2 seen, done | X2 trsm start,end\n");
+    for (int K = K0 - 1; K < K0 + 8; K++) {
+      fprintf(stderr, "[strace] K=%d", K);
+      for (int e = 0; e < 13; e++) { if (e == 2 || e == 6 || e == 8 || e == 11) fprintf(stderr, " |"); fprintf(stderr, " %7lld", hs[(size_t)K*16 + e] ? hs[(size_t)K*16 + e] - t0 : -1); }
       fprintf(stderr, "\n");
     }
   };
@@ -1053,7 +1161,7 @@ int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, 
   if (getenv("DYNOBA_SPINE_DBG")) {
     long long hd[16]; cudaStreamSynchronize(s); cudaMemcpyFromSymbol(hd, g_spine_dbg, sizeof(hd));
     const char* nm2[12] = {"potrf", "store+stage+flag D", "barA", "wait+load Dnext half", "barB (trsm)", "gemm half + stage", "barC + reload", "-", "-", "-", "-", "loop"};
-    const char* nm3[12] = {"A0 potrf", "A0 wait L stored", "A0 wait D input", "A0 X1 rank-8 (+waits)", "A1 potrf", "A1 wait L stored", "A1 wait D input", "A1 X1 rank-8 (+waits)", "-", "-", "-", "-"};
+    const char* nm3[12] = {"A0 potrf", "A0 wait L stored", "A0 wait D input", "A0 X1 rank-8 (+waits)", "A1 potrf", "A1 wait L stored", "A1 wait D input", "A1 X1 rank-8 (+waits)", "A0 potrf: stage + block load", "A0 potrf: 8x8 factor", "A0 potrf: publish + trailing", "-"};
     const char** nm = g_spine_ver == 2 ? nm2 : nm3;
     for (int i = 0; i < 12; i++) fprintf(stderr, "[spine] %-22s %10.3f ms\n", nm[i], hd[i]/1.965e6);
   }
