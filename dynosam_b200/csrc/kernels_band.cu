@@ -24,6 +24,7 @@ namespace cg = cooperative_groups;
 namespace dynoba {
 
 constexpr int CH_WARPS = 4;
+constexpr int TS = 40, TSZ = TILE*TS;      // column stride of shared-memory tiles that feed MMA operand fragments: conflict-free loads
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -286,9 +287,9 @@ __device__ long long g_spine_dbg[16];
 // only receive the updates from the factored columns (their Schur complement), updates from columns < Kbeg are
 // assumed applied already (second phase of the two-directional scheme).
 struct CholProb { double* tiles; double* rhs; int NT, Kbeg, Kend; int* done; int* pre; int* ydone; };
-struct CholJob { CholProb p[2]; int np, WB; };
+struct CholJob { CholProb p[2]; int np, WB, skew; };
 
-__device__ __forceinline__ void chol_worker(const struct CholJob& job, int wid, int nworkers, double* sb, double* sinv, int lane, int dd0_lag);
+__device__ __forceinline__ void chol_worker(const struct CholJob& job, int wid, int nworkers, double* sb, double* sinv, double* stage, int lane, int dd0_lag);
 
 // Tile roles (dd = I - K):
 //   dd == 0, 1 : workers apply the updates from columns J <= K-2 ("pre"), the spine applies J = K-1 and finishes
@@ -412,7 +413,7 @@ band_cholesky_dataflow_kernel(CholJob job, int* __restrict__ fail) {
     return;
   }
   // -------------------------------------------------------------------- workers
-  chol_worker(job, ((int)blockIdx.x - job.np)*CH_WARPS + warp, ((int)gridDim.x - job.np)*CH_WARPS, sb, sinv, lane, 2);
+  chol_worker(job, ((int)blockIdx.x - job.np)*CH_WARPS + warp, ((int)gridDim.x - job.np)*CH_WARPS, sb, sinv, nullptr, lane, 2);
 }
 
 // Worker warp `wid` of `nworkers`: tile tasks in column-major order (see the role table above the kernels).
@@ -457,17 +458,50 @@ __device__ __forceinline__ void frag_gemm_sub(double (&c)[TILE], const double (&
     }
 }
 
+// asynchronous copy of one 32x32 tile (column-major, 8 KB) into a shared-memory tile with column stride TS
+__device__ __forceinline__ void tile_prefetch(double* s, const double* t, int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int ch = lane + 32*i, c = ch >> 4, part = ch & 15;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(s + c*TS + 2*part);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(t + c*TILE + 2*part) : "memory");
+  }
+}
+__device__ __forceinline__ void sfrag_load(const double* t, double (&f)[TILE], int lane) {
+  const double* p = t + (lane & 3)*TS + (lane >> 2);
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) f[b*8 + kb] = p[4*kb*TS + 8*b];
+}
+// both flags set?  (non-blocking, acquire)
+__device__ __forceinline__ bool flags_ready(const int* fa, const int* fb, int lane) {
+  int ok = 0;
+  if (lane == 0) ok = ld_acquire(fa) != 0 && ld_acquire(fb) != 0;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+
 // dd0_lag: the diagonal tile (dd == 0) receives the worker updates from columns J <= K - dd0_lag only (the spine owns the rest).
-__device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nworkers, double* sb, double* sinv, int lane, int dd0_lag) {
+// stage: per-warp [2][2][TSZ] shared-memory operand buffers for the asynchronous prefetch of the next update, or nullptr.
+__device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nworkers, double* sb, double* sinv, double* stage, int lane, int dd0_lag) {
   const int WB = job.WB, W1 = WB + 1;
   const int W2 = W1 + 1;                                 // tile tasks + the rhs task of the column
   int ncols = 0;
   for (int q = 0; q < job.np; q++) ncols = max(ncols, job.p[q].NT - job.p[q].Kbeg);
-  const long long per_col = (long long)job.np*W2;
-  const long long ntasks = (long long)ncols*per_col;
+  // Task order: skewed wavefronts s = skew*K + dd instead of column-major.  A worker processes its tasks in order and
+  // blocks on operands, so a task's lead over the spine has to cover its own serial work; the (WB - dd) updates of a tile
+  // near the diagonal need more lead than the short tasks far from it.  With the skew the tiles of one column are handed
+  // out over WB/skew columns, longest first.  Every operand of task (K, dd) has a strictly smaller s, so in-order
+  // blocking cannot deadlock.  (Measured on C5: skew 2 is 1-2 % faster than column-major or a near/far split of the
+  // worker pool; the column period is set by the row-chain hop latency, see DESIGN.md.)
+  const int skew = job.skew, nj = (W2 + skew - 1)/skew;
+  const long long per_s = (long long)job.np*nj;
+  const long long ntasks = ((long long)skew*ncols + W2)*per_s;
   for (long long t = wid; t < ntasks; t += nworkers) {
-    const int c = (int)(t/per_col); const int rem = (int)(t - (long long)c*per_col);
-    const int q = rem/W2, dd = rem - q*W2;
+    const int sidx = (int)(t/per_s); const int u = (int)(t - (long long)sidx*per_s);
+    const int q = u/nj, j = u - q*nj;
+    const int dd = sidx%skew + skew*j, c = sidx/skew - j;
+    if (dd > W1 || c < 0 || c >= ncols) continue;
     const CholProb P = job.p[q];
     int* done = P.done; int* pre = P.pre; int* ydone = P.ydone;
     const int NT = P.NT, K = P.Kbeg + c, I = K + dd;
@@ -513,6 +547,43 @@ __device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nwo
     // the spine finishes the tiles of columns <= Kend itself: it owns the last (dd0_lag - 1) updates of a diagonal tile and
     // the last update of a first sub-diagonal tile
     const int Jhi = min(dd == 0 ? (K <= P.Kend ? K - dd0_lag : K - 1) : (dd == 1 ? K - 2 : K - 1), P.Kend - 1);
+    if (stage) {
+      // software pipeline: while update J runs on the tensor pipe, the operand tiles of J+1 (when their flags are already
+      // up) stream into the other shared-memory stage with cp.async -- the L2 latency leaves the critical path
+      int st = 0; bool have = false;
+      for (int J = Jlo; J <= Jhi; J++) {
+        const size_t oI = (size_t)J*W1 + (I - J), oK = (size_t)J*W1 + (K - J);
+        if (!have) {
+          wait_flag(done + oK, lane);
+          if (dd != 0) wait_flag(done + oI, lane);
+          tile_prefetch(stage + (size_t)(st*2 + 1)*TSZ, P.tiles + oK*TILE2, lane);
+          if (dd != 0) tile_prefetch(stage + (size_t)(st*2)*TSZ, P.tiles + oI*TILE2, lane);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        bool next = false;
+        if (J + 1 <= Jhi) {
+          const size_t nI = (size_t)(J + 1)*W1 + (I - J - 1), nK = (size_t)(J + 1)*W1 + (K - J - 1);
+          next = flags_ready(done + nK, done + (dd != 0 ? nI : nK), lane);
+          if (next) {
+            tile_prefetch(stage + (size_t)((st ^ 1)*2 + 1)*TSZ, P.tiles + nK*TILE2, lane);
+            if (dd != 0) tile_prefetch(stage + (size_t)((st ^ 1)*2)*TSZ, P.tiles + nI*TILE2, lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+          }
+        }
+        if (next) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        double fb[TILE];
+        sfrag_load(stage + (size_t)(st*2 + 1)*TSZ, fb, lane);
+        if (dd == 0) frag_gemm_sub(acc, fb, fb);
+        else {
+          double fa[TILE];
+          sfrag_load(stage + (size_t)(st*2)*TSZ, fa, lane);
+          frag_gemm_sub(acc, fa, fb);
+        }
+        __syncwarp();            // the stage is free for the prefetch after next
+        st ^= 1; have = next;
+      }
+    } else
     for (int J = Jlo; J <= Jhi; J++) {
       const size_t oI = (size_t)J*W1 + (I - J), oK = (size_t)J*W1 + (K - J);
       double fb[TILE];
@@ -564,8 +635,7 @@ __device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nwo
 //   IO1    (warp 5)      T(K+1,K+1), T(K+2,K+1) (worker-updated) -> shared memory, one column ahead
 // Hand-offs are monotone event counters in shared memory (value c+1 = "done for column c").
 constexpr int SP_WARPS = 8;
-constexpr int PSTR = 10, PANSZ = TILE*PSTR;
-constexpr int TS = 40, TSZ = TILE*TS;      // column stride of the spine's shared-memory tiles: conflict-free MMA operand loads     // potrf panel [row][8], row stride 10 doubles: conflict-free LDS.128 per row
+constexpr int PSTR = 10, PANSZ = TILE*PSTR;     // potrf panel [row][8], row stride 10 doubles: conflict-free LDS.128 per row
 enum { EV_PAN = 0, EV_X1P = 4, EV_X2 = 8, EV_DIN = 9, EV_XNIN = 10, EV_ST_L = 11, EV_ST_X1 = 12, EV_ST_X2 = 13, EV_TK_D = 14, EV_TK_XN = 15, EV_N = 16 };
 
 __device__ __forceinline__ void ev_signal(volatile int* ev, int i, int v, int lane) {
@@ -618,12 +688,13 @@ __device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, doubl
       for (int j = 0; j <= i; j++) G[i*(i + 1)/2 + j] = sP[(8*p + i)*PSTR + j];
     __syncwarp();
     const long long tp1 = clock64();
+    double myinv = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const double d = G[k*(k + 1)/2 + k];
       if (!(d > 0.0)) ok = false;
       const double inv = rsqrt(d);
-      if (lane == 8*p + k) sIv[8*p + k] = inv;
+      if ((lane & 7) == k) myinv = inv;      // published after the loop: a store inside it makes ptxas clone the rsqrt
       x[k] *= inv;
 #pragma unroll
       for (int i = k + 1; i < 8; i++) G[i*(i + 1)/2 + k] *= inv;
@@ -636,6 +707,7 @@ __device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, doubl
       }
     }
     const long long tp2 = clock64();
+    if (lane < 8) sIv[8*p + lane] = myinv;
 #pragma unroll
     for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sP + lane*PSTR + j) = make_double2(x[j], x[j + 1]);
     ev_signal(ev, EV_PAN + p, cval, lane);
@@ -760,8 +832,14 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= job.np) {
     if (warp >= wk_warps) return;
-    chol_worker(job, ((int)blockIdx.x - job.np)*wk_warps + warp, ((int)gridDim.x - job.np)*wk_warps,
-                chol_smem + (size_t)warp*TILE2, chol_smem + (size_t)SP_WARPS*TILE2 + warp*TILE, lane, 3);
+    if (wk_warps <= 4) {       // room for the prefetch buffers: [warp][2 stages][2 tiles][TSZ] | [TILE2] | [TILE]
+      double* base = chol_smem + (size_t)warp*(4*TSZ + TILE2 + TILE);
+      chol_worker(job, ((int)blockIdx.x - job.np)*wk_warps + warp, ((int)gridDim.x - job.np)*wk_warps,
+                  base + 4*TSZ, base + 4*TSZ + TILE2, base, lane, 3);
+    } else {
+      chol_worker(job, ((int)blockIdx.x - job.np)*wk_warps + warp, ((int)gridDim.x - job.np)*wk_warps,
+                  chol_smem + (size_t)warp*TILE2, chol_smem + (size_t)SP_WARPS*TILE2 + warp*TILE, nullptr, lane, 3);
+    }
     return;
   }
   const CholProb P = job.p[blockIdx.x];
@@ -1056,7 +1134,7 @@ band_backward_cluster_kernel(BackJob job) {
   }
 }
 
-static int g_max_blocks = 0, g_spine_ver = 3, g_wk_warps = 4;
+static int g_max_blocks = 0, g_spine_ver = 3, g_wk_warps = 4, g_skew = 2;
 static size_t g_chol_smem = 0;
 
 static void chol_init() {
@@ -1067,10 +1145,11 @@ static void chol_init() {
   // CTAs per SM: 1 keeps each spine CTA alone on its SM (DYNOBA_CHOL_BPS overrides for experiments)
   int bps = 1; if (const char* e = getenv("DYNOBA_CHOL_BPS")) bps = atoi(e) > 0 ? atoi(e) : 1;
   if (const char* e = getenv("DYNOBA_SPINE")) g_spine_ver = atoi(e) == 2 ? 2 : 3;
+  if (const char* e = getenv("DYNOBA_SKEW")) g_skew = std::max(2, atoi(e));
   if (const char* e = getenv("DYNOBA_WK_WARPS")) g_wk_warps = std::max(1, std::min(SP_WARPS, atoi(e)));
   if (g_spine_ver == 2) g_wk_warps = CH_WARPS;
   const size_t need = g_spine_ver == 2 ? (size_t)(1152 + 4*TILE2 + 256 + 64)*sizeof(double)
-                                       : (size_t)(2*4*PANSZ + 2*TILE + 8*TSZ + 4*TILE2 + 64)*sizeof(double);   // >= the workers' [8][TILE2 + TILE]
+                                       : std::max((size_t)(2*4*PANSZ + 2*TILE + 8*TSZ + 4*TILE2 + 64), (size_t)4*(4*TSZ + TILE2 + TILE))*sizeof(double);   // spine | workers with prefetch stages
   g_chol_smem = std::max(need, (size_t)(220*1024)/bps - 2048);
   const void* kern = g_spine_ver == 2 ? (const void*)band_cholesky_dataflow_kernel : (const void*)band_cholesky_dataflow_kernel_v3;
   const int nthr = g_spine_ver == 2 ? CH_WARPS*32 : SP_WARPS*32;
@@ -1085,7 +1164,7 @@ static void chol_launch(const CholJob& job, int* fail, cudaStream_t s) {
   const long long want = (ntile + g_wk_warps - 1)/g_wk_warps + job.np;
   if (grid > want) grid = (int)want;
   if (grid < job.np + 1) grid = job.np + 1;
-  CholJob j = job;
+  CholJob j = job; j.skew = g_skew;
   // cooperative launch only for its co-residency guarantee (the flag waits need every warp resident)
   if (g_spine_ver == 2) {
     void* args[] = { (void*)&j, (void*)&fail };
@@ -1121,7 +1200,7 @@ int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, 
     cudaStreamSynchronize(s);
     std::vector<long long> ht(trace_len); cudaMemcpy(ht.data(), dtrace, trace_len*sizeof(long long), cudaMemcpyDeviceToHost);
     long long* nul = nullptr; cudaMemcpyToSymbol(g_trace, &nul, sizeof(nul)); cudaFree(dtrace);
-    const int K0 = std::max(4, (B.two ? B.split_lo/TILE : NTA)/2), nd = std::min(W1, 8);
+    const int K0 = std::max(4, (B.two ? B.split_lo/TILE : NTA)/2), nd = getenv("DYNOBA_CHOL_TRACE_ALL") ? W1 : std::min(W1, 8);
     const long long t0 = ht[(size_t)K0*W1];
     fprintf(stderr, "[trace] ns relative to done(K0,K0), K0 = %d; columns: done dd=0..%d | pre dd=0..2\n", K0, nd - 1);
     for (int K = K0 - 2; K < K0 + 10; K++) {

@@ -64,7 +64,8 @@ __global__ void potrf_bench(double* out, long long* cyc, int mode, int iters, in
     __syncwarp();
     const long long t0 = clock64();
     if (mode == 0) ok &= spine_potrf(row, lane, sPan, sIv, ev, it + 1, prof);
-    else { spine_rank32(row, sX, sX + TSZ, false, ev, -1, 0, lane); }
+    else if (mode == 1) { spine_rank32(row, sX, sX + TSZ, false, ev, -1, 0, lane); }
+    else { spine_trsm(row, lane, sPan, sIv, ev, 0, sX, -1); }
     total += clock64() - t0;
   }
   double s = 0.0;
@@ -76,12 +77,12 @@ __global__ void potrf_bench(double* out, long long* cyc, int mode, int iters, in
 
 int main() {
   double* out; long long* cyc; cudaMalloc(&out, 128*8); cudaMalloc(&cyc, 32);
-  const char* names[2] = {"spine_potrf", "spine_rank32"};
+  const char* names[3] = {"spine_potrf", "spine_rank32", "spine_trsm"};
   struct Cfg { int nw, sib, mask; const char* what; } cfgs[] = {
     {1, 0, 0, "alone"}, {8, 1, 0, "7 polling siblings"}, {8, 2, 4, "heavy on warps 4-7 (same scheduler as warp 0: warp 4)"},
     {8, 2, 3, "heavy on warps 1,2,3,5,6,7 (other schedulers), warp 4 polls"}, {8, 2, 7, "heavy on all 7 siblings"},
     {8, 3, 3, "big code (16 x 1.6k-instr bodies), low duty, other schedulers"}, {8, 4, 3, "big code, medium duty, other schedulers"}, {8, 4, 7, "big code, medium duty, all siblings"} };
-  for (auto& c : cfgs) for (int mode = 0; mode < 2; mode++) {
+  for (auto& c : cfgs) for (int mode = 0; mode < 3; mode++) {
     potrf_bench<<<1, 32*c.nw>>>(out, cyc, mode, 200, c.sib, c.mask);
     cudaDeviceSynchronize();
     long long h[4]; cudaMemcpy(h, cyc, 32, cudaMemcpyDeviceToHost);
