@@ -165,6 +165,19 @@ def cpu_oracle_best(cfg_name, formulation, seed, sample_scale, iters):
     return r
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant Jacobian-build kernel, from the ncu --set full
+# capture summarised in profiles/r01_final.md (a counter value cannot be measured inside a timed run).  Only valid for the
+# exact launch that was profiled: C5 at full scale on one GPU; anything else reports null.
+NCU_TRAFFIC = {("C5", "hybrid", 5, 11376204): 577.77e6 + 4309.57e6}
+
+
+def ncu_traffic(args, world, blk):
+    if world != 1 or args.scale != 1.0:
+        return None
+    v = NCU_TRAFFIC.get((args.config, args.formulation, int(blk.type), int(blk.n)))
+    return float(v) if v else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -318,7 +331,7 @@ def main():
            "roofline": {"kernel": f"linearize_kernel<{TYPE_NAMES[prob.blocks[dom].type]}> (materialising Jacobian build of the largest factor block, "
                                   f"{prob.blocks[dom].n} factors)",
                         "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                        "frac": ach/peak if peak else None, "traffic": None, "algorithmic_bytes": int(dom_bytes), "ms_per_launch": dms,
+                        "frac": ach/peak if peak else None, "traffic": ncu_traffic(args, world, prob.blocks[dom]), "algorithmic_bytes": int(dom_bytes), "ms_per_launch": dms,
                         "whole_pass": {"algorithmic_bytes": info["jacobian_bytes"], "ms": lin, "achieved": pass_ach,
                                        "frac": pass_ach/peak if peak else None,
                                        "note": "all factor blocks of one linearize() incl. the numerically differentiated smoothing factors and the final reduction"}}}

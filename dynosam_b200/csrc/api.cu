@@ -19,6 +19,7 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <map>
 
 #include "../../include/dynoba.h"
 #include "internal.cuh"
@@ -55,7 +56,7 @@ struct dynoba_solver {
   int rank = 0, world = 1; dynoba_allreduce_fn allreduce = nullptr; void* ar_ctx = nullptr; int min_bw = 0;
   int64_t launches = 0; int64_t jac_bytes = 0;
   GeneralGroups gen{}; int gen_bs_off = 0;
-  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> allocs;   // device allocations (pointer, bytes)
   cudaEvent_t ev[8]{};
 };
 
@@ -83,15 +84,54 @@ struct PinnedArena {
 PinnedArena g_arena;
 }  // namespace
 
+// Process-wide cache of device allocations: a closed solver's blocks are kept and handed to the next one that asks for
+// (about) the same size, because cudaMalloc / cudaFree of multi-GB blocks cost hundreds of milliseconds per optimize()
+// call when the caller builds one solver per batch.  DYNOBA_NO_DEVCACHE=1 turns it off; the cache is trimmed when an
+// allocation fails or when it holds more than DYNOBA_DEVCACHE_GB (default 96) gigabytes.
+namespace {
+struct DevCache {
+  std::mutex mu; std::multimap<size_t, void*> blocks; size_t bytes = 0;
+  void* take(size_t need, size_t* got) {     // smallest cached block of at least `need` bytes, if it is not much larger
+    std::lock_guard<std::mutex> l(mu);
+    auto it = blocks.lower_bound(need);
+    if (it == blocks.end() || it->first > need + need/4 + 4096) return nullptr;
+    void* p = it->second; *got = it->first; bytes -= it->first; blocks.erase(it); return p;
+  }
+  void give(void* p, size_t n) {
+    static const bool off = getenv("DYNOBA_NO_DEVCACHE") != nullptr;
+    static const size_t cap = (size_t)(getenv("DYNOBA_DEVCACHE_GB") ? atof(getenv("DYNOBA_DEVCACHE_GB")) : 96.0)*(1ull << 30);
+    std::lock_guard<std::mutex> l(mu);
+    if (off || bytes + n > cap) { cudaFree(p); return; }
+    blocks.emplace(n, p); bytes += n;
+  }
+  void trim() { std::lock_guard<std::mutex> l(mu); for (auto& b : blocks) cudaFree(b.second); blocks.clear(); bytes = 0; }
+};
+DevCache g_devcache;
+}  // namespace
+
 template <class T> static int dalloc(dynoba_solver* h, T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  CK(cudaMalloc((void**)p, count*sizeof(T)));
-  h->allocs.push_back((void*)*p);
+  const size_t bytes = (count*sizeof(T) + 255) & ~(size_t)255;
+  size_t got = bytes;                        // a cached block may be larger than asked: its true size goes back with it
+  void* q = g_devcache.take(bytes, &got);
+  if (!q) {
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); g_devcache.trim(); CK(cudaMalloc(&q, bytes)); }
+  }
+  else {
+    // a recycled block holds the previous owner's data; several kernels leave entries they own untouched (padding lanes,
+    // partial sums of early-exit CTAs) and count on the zeros a fresh allocation happens to have.  Ordered before any
+    // later use: the solver's streams are non-blocking, so wait for the memset here.
+    CK(cudaMemsetAsync(q, 0, bytes, h->stream)); CK(cudaStreamSynchronize(h->stream));
+  }
+  *p = (T*)q;
+  h->allocs.emplace_back(q, got);
   return DYNOBA_OK;
 }
 static void free_device(dynoba_solver* h) {
-  for (void* p : h->allocs) cudaFree(p);
+  if (!h->allocs.empty()) cudaDeviceSynchronize();      // cudaFree used to imply this; cached blocks must be idle too
+  for (auto& a : h->allocs) g_devcache.give(a.first, a.second);
   h->allocs.clear();
   h->finalized = false; h->linearized = false;
 }
@@ -437,7 +477,49 @@ static int finalize_impl(dynoba_solver* h) {
       int unsorted = 0;
 #pragma omp parallel for schedule(static) reduction(|:unsorted)
       for (int64_t i = 1; i < n; i++) unsorted |= key[i-1] > key[i];
-      if (unsorted) __gnu_parallel::stable_sort(b.perm.begin(), b.perm.end(), [&](int a, int c) { return key[a] < key[c]; });
+      if (unsorted) {
+        // Fast path: the caller lists each landmark's factors contiguously with ascending poses (how DynOSAM's
+        // formulations add them) and only the ORDER OF THE LANDMARKS differs from ours -- then sorting the runs (one per
+        // landmark) replaces sorting the factors.  Anything else falls back to the general stable sort.
+        std::vector<int64_t> run0;                                 // first factor of each run of equal group rank
+        {
+          const int nseg = std::max(1, std::min<int>(omp_get_max_threads(), (int)(n/65536) + 1));
+          std::vector<std::vector<int64_t>> seg(nseg);
+#pragma omp parallel for schedule(static, 1)
+          for (int t = 0; t < nseg; t++) {
+            const int64_t s0 = n*t/nseg, s1 = n*(t + 1)/nseg;
+            for (int64_t i = s0; i < s1; i++) if (i == 0 || frank[i] != frank[i-1]) seg[t].push_back(i);
+          }
+          for (auto& v : seg) run0.insert(run0.end(), v.begin(), v.end());
+        }
+        const int64_t nrun = (int64_t)run0.size();
+        int bad = 0;                                               // a rank in two runs, or poses not ascending inside a run
+        std::vector<int64_t> order(nrun);
+        if (nrun <= (int64_t)gorder.size()) {
+#pragma omp parallel for schedule(static) reduction(|:bad)
+          for (int64_t r = 0; r < nrun; r++) {
+            order[r] = r;
+            const int64_t e = r + 1 < nrun ? run0[r + 1] : n;
+            for (int64_t i = run0[r] + 1; i < e; i++) bad |= key[i-1] > key[i];
+          }
+          if (!bad) {
+            __gnu_parallel::sort(order.begin(), order.end(), [&](int64_t a, int64_t c) { return frank[run0[a]] < frank[run0[c]]; });
+#pragma omp parallel for schedule(static) reduction(|:bad)
+            for (int64_t r = 1; r < nrun; r++) bad |= frank[run0[order[r-1]]] == frank[run0[order[r]]];
+          }
+        } else bad = 1;
+        if (!bad) {
+          std::vector<int64_t> dst(nrun + 1, 0);
+          for (int64_t r = 0; r < nrun; r++) { const int64_t a = order[r]; dst[r + 1] = dst[r] + ((a + 1 < nrun ? run0[a + 1] : n) - run0[a]); }
+#pragma omp parallel for schedule(static)
+          for (int64_t r = 0; r < nrun; r++) {
+            const int64_t a = order[r], len = dst[r + 1] - dst[r];
+            for (int64_t k = 0; k < len; k++) b.perm[dst[r] + k] = (int32_t)(run0[a] + k);
+          }
+        } else {
+          __gnu_parallel::stable_sort(b.perm.begin(), b.perm.end(), [&](int a, int c) { return key[a] < key[c]; });
+        }
+      }
     }
     lap("  blk sort");
     // SoA host images
@@ -645,7 +727,7 @@ static int finalize_impl(dynoba_solver* h) {
   h->n_lin_partials = part; h->n_bs_partials = bs + pose_norm_grid(B.n);
   h->n_partials = std::max(std::max(h->n_lin_partials, h->n_bs_partials), 1);
   { int rc; if ((rc = dalloc(h, &h->partials, (size_t)h->n_partials))) return rc; if ((rc = dalloc(h, &h->scalars, 8))) return rc; if ((rc = dalloc(h, &h->fail, 1))) return rc; }
-  CK(cudaMemset(h->scalars, 0, 64)); CK(cudaMemset(h->fail, 0, 4));
+  CK(cudaMemset(h->scalars, 0, 64)); CK(cudaMemset(h->fail, 0, 4)); CK(cudaMemset(h->partials, 0, (size_t)h->n_partials*8));
   CK(cudaDeviceSynchronize());
   lap("general groups + sync");
   h->finalized = true; h->linearized = false;
@@ -815,7 +897,8 @@ int dynoba_get_factor_errors(dynoba_handle h, int bi, double* err) {
   CK(cudaMemcpyAsync(he.data(), d, he.size()*8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (int64_t s = 0; s < b.n; s++) err[b.perm[s]] = he[s];
-  cudaFree(d); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)d));
+  { auto it = std::find_if(h->allocs.begin(), h->allocs.end(), [&](const std::pair<void*, size_t>& a) { return a.first == (void*)d; });
+    g_devcache.give(it->first, it->second); h->allocs.erase(it); }
   return DYNOBA_OK;
 }
 

@@ -5,13 +5,15 @@
 // the system is banded (half-width = the co-visibility window, <= max track age), stored as 32x32 tiles.
 // tcgen05/UMMA has no fp64 path, so the tile kernels are fp64 FMA code.
 //
-// Factorisation = one persistent DATAFLOW kernel (no grid-wide barriers):
-//   * worker warps take tiles in column-major order and apply, in registers, every left-looking update
-//     T_IK -= L_IJ L_KJ^T as soon as the per-tile "done" flags of the two operand tiles are released;
-//   * one spine warp owns the sequential dependency chain  potrf(K,K) -> trsm(K+1,K) -> update+potrf(K+1,K+1)
-//     and keeps those tiles in registers / shared memory, so the chain never waits on an L2 round trip.
-// Solve = explicit inverses of the diagonal tiles (one warp each, fully parallel) followed by single-CTA
-// forward / backward sweeps in which 31 warps do the off-diagonal tile GEMVs of a column concurrently.
+// Factorisation = one persistent DATAFLOW kernel (no grid-wide barriers), band_cholesky_dataflow_kernel_v3:
+//   * worker warps own one tile task at a time: every left-looking update T_IK -= L_IJ L_KJ^T (fp64 tensor-core MMA,
+//     operands prefetched with cp.async) as soon as the per-tile "done" flags of the operand tiles are released, then
+//     the TRSM against L_KK;
+//   * one spine CTA per band problem owns the sequential chain potrf(K,K) -> trsm(K+1,K) -> update+potrf(K+1,K+1) and
+//     the two tiles below it, in shared memory / registers, so the chain never waits on an L2 round trip.
+// band_cholesky_dataflow_kernel (4-warp spine, DYNOBA_SPINE=2) is the previous generation, kept for A/B runs.
+// Solve = explicit inverses of the diagonal tiles (one warp each, fully parallel); the forward substitution is folded
+// into the factorisation as one task per column, the backward sweep runs on a cluster of 8 CTAs per band problem.
 #include <algorithm>
 #include <cstdlib>
 #include <cstdio>
