@@ -1059,78 +1059,152 @@ __device__ __forceinline__ double warp_transpose_sum(double (&v)[TILE], int lane
 struct BackProb { const double* tiles; double* rhs; const double* linv; int NT, Jtop, Jbot; };
 struct BackJob { BackProb p[2]; int WB; };
 constexpr int BW_CL = 8, BW_TW = 4;      // cluster size, tile warps per CTA
+constexpr int BW_PS = 34;                // padded column stride of warp 0's shared-memory tiles (conflict-free LDS.128 per column)
+// dot product of 32 register values with a 32-vector in shared memory (broadcast reads)
+__device__ __forceinline__ double dot32(const double (&a)[TILE], const double* x) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+  for (int r = 0; r < TILE; r += 4) {
+    const double2 u = *reinterpret_cast<const double2*>(x + r), w = *reinterpret_cast<const double2*>(x + r + 2);
+    s0 += a[r]*u.x; s1 += a[r + 1]*u.y; s2 += a[r + 2]*w.x; s3 += a[r + 3]*w.y;
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+// Backward sweep x_J = L_JJ^-T (y_J - sum_{I>J} L_IJ^T x_I), TWO columns per cluster barrier: the off-diagonal terms of
+// columns J and J-1 that involve x_I, I > J, are independent of each other (and use the same x_I: tile (I,J) and tile
+// (I,J-1) go to the same warp), only L(J,J-1)^T x_J has to wait for x_J and is done by warp 0 between the two solves.
+// Every tile GEMV^T is COLUMN-per-lane: lane c holds column c of the tile (32 contiguous doubles) and reads x as
+// broadcast LDS.128 -- 32 FMAs and no shuffles (the row-per-lane form needs a 31-shuffle transpose-sum per tile).
 __global__ void __cluster_dims__(BW_CL, 1, 1) __launch_bounds__((BW_TW + 1)*32)
 band_backward_cluster_kernel(BackJob job) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();
   const BackProb P = job.p[blockIdx.x/BW_CL];
-  const int NT = P.NT, WB = job.WB, W1 = WB + 1, ring = WB + 1;
+  const int NT = P.NT, WB = job.WB, W1 = WB + 1, ring = WB + 2;
   double* xs = sm;                                   // [ring][32] solved blocks (replicated in every CTA)
-  double* lpart = sm + (size_t)ring*TILE;            // [BW_TW][32] partial sums of this CTA's tile warps
-  double* cpart = lpart + BW_TW*TILE;                // [2][BW_CL][32] all-gathered per-CTA partials
+  double* lpart = sm + (size_t)ring*TILE;            // [2][BW_TW][32] partial sums of this CTA's tile warps, per column
+  double* cpart = lpart + 2*BW_TW*TILE;              // [2][2][BW_CL][32] all-gathered per-CTA partials (pair parity, column)
+  double* sv = cpart + 4*BW_CL*TILE;                 // [32] warp 0: right-hand side to broadcast
+  double* sW0 = sv + TILE;                           // [2 stages][3][32*BW_PS] warp 0: Linv(J), Linv(J-1), L(J,J-1) of a pair, fetched with
+                                                     // cp.async one pair ahead
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int I = P.Jtop + warp; I < min(NT, P.Jtop + WB); I += BW_TW + 1) xs[(size_t)(I % ring)*TILE + lane] = P.rhs[(size_t)I*TILE + lane];
   __syncthreads();
-  // software prefetch: the tile this warp needs for column J-1 is loaded while column J is processed
-  const int myq = rank*BW_TW + (warp - 1);
-  double tn[TILE];
-  auto prefetch = [&](int J) {
-    if (warp >= 1 && J >= P.Jbot && myq < min(WB, NT - 1 - J)) {
-      const double* tp = P.tiles + (size_t)J*W1*TILE2 + (size_t)(myq + 1)*TILE2;
+  const int myq = rank*BW_TW + (warp - 1);           // this warp's tile of column J; of column J-1 it takes tile myq + 1
+  double tA[TILE], tB[TILE];                          // column `lane` of the prefetched tiles (warp 0: tA = Linv(J))
+  auto load_col = [&](const double* tile, double (&t)[TILE]) {
+    const double2* p = reinterpret_cast<const double2*>(tile + lane*TILE);
 #pragma unroll
-      for (int c = 0; c < TILE; c++) tn[c] = tp[c*TILE + lane];
+    for (int r = 0; r < TILE/2; r++) { const double2 u = p[r]; t[2*r] = u.x; t[2*r + 1] = u.y; }
+  };
+  // software prefetch: the tiles of the next pair are loaded while this pair is processed
+  auto prefetchA = [&](int J) { if (J >= P.Jbot && myq < min(WB, NT - 1 - J)) load_col(P.tiles + (size_t)J*W1*TILE2 + (size_t)(myq + 1)*TILE2, tA); };
+  auto prefetchB = [&](int J) { if (J - 1 >= P.Jbot && myq + 1 < min(WB, NT - J)) load_col(P.tiles + (size_t)(J - 1)*W1*TILE2 + (size_t)(myq + 2)*TILE2, tB); };
+  auto fetch_w0 = [&](int J, int stage) {              // warp 0: the three tiles of pair (J, J-1) -> shared memory stage
+    if (J >= P.Jbot) {
+      double* dst = sW0 + (size_t)stage*3*TILE*BW_PS;
+      const double* l0 = P.linv + (size_t)J*TILE2;
+      const double* l1 = P.linv + (size_t)(J - 1)*TILE2;
+      const double* tp = P.tiles + (size_t)(J - 1)*W1*TILE2 + TILE2;
+      const bool two = J - 1 >= P.Jbot;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int ch = lane + 32*i, c = ch >> 4, part = ch & 15;
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + c*BW_PS + 2*part);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(l0 + 2*ch) : "memory");
+        if (two) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + (unsigned)(TILE*BW_PS*8)), "l"(l1 + 2*ch) : "memory");
+        if (two && WB >= 1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + (unsigned)(2*TILE*BW_PS*8)), "l"(tp + 2*ch) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count in step with the pair count
+  };
+  // the factor is far larger than L2 and was written long ago: pull the tiles of the pair after next into L2 early, so
+  // that the register / cp.async prefetches above see L2 latency instead of HBM latency
+  auto l2_line = [&](const double* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); };
+  auto warm = [&](int J) {
+    if (J < P.Jbot) return;
+    if (warp >= 1) {
+      if (myq < min(WB, NT - 1 - J)) { const double* t = P.tiles + (size_t)J*W1*TILE2 + (size_t)(myq + 1)*TILE2; l2_line(t + lane*16); l2_line(t + 512 + lane*16); }
+      if (J - 1 >= P.Jbot && myq + 1 < min(WB, NT - J)) { const double* t = P.tiles + (size_t)(J - 1)*W1*TILE2 + (size_t)(myq + 2)*TILE2; l2_line(t + lane*16); l2_line(t + 512 + lane*16); }
+    } else {
+      const double* t = P.linv + (size_t)J*TILE2; l2_line(t + lane*16); l2_line(t + 512 + lane*16);
+      if (J - 1 >= P.Jbot) {
+        const double* u = P.linv + (size_t)(J - 1)*TILE2; l2_line(u + lane*16); l2_line(u + 512 + lane*16);
+        const double* w = P.tiles + (size_t)(J - 1)*W1*TILE2 + TILE2; l2_line(w + lane*16); l2_line(w + 512 + lane*16);
+      }
     }
   };
-  prefetch(P.Jtop - 1);
-  for (int J = P.Jtop - 1; J >= P.Jbot; J--) {
-    const int nbelow = min(WB, NT - 1 - J);
-    const double* colJ = P.tiles + (size_t)J*W1*TILE2;
+  if (warp >= 1) { prefetchA(P.Jtop - 1); prefetchB(P.Jtop - 1); } else fetch_w0(P.Jtop - 1, 0);
+  warm(P.Jtop - 3); warm(P.Jtop - 5); warm(P.Jtop - 7);
+  int par = 0;
+  for (int J = P.Jtop - 1; J >= P.Jbot; J -= 2, par ^= 1) {
+    const bool hasB = J - 1 >= P.Jbot;
+    const int nbA = min(WB, NT - 1 - J), nbB = min(WB, NT - J);       // tiles below the diagonal in columns J, J-1
+    warm(J - 8);
     if (warp >= 1) {
-      double s = 0.0;
-      double t[TILE];
-#pragma unroll
-      for (int c = 0; c < TILE; c++) t[c] = tn[c];
-      prefetch(J - 1);
-      if (myq < nbelow) {
-        const double xr = xs[(size_t)((J + 1 + myq) % ring)*TILE + lane];
-#pragma unroll
-        for (int c = 0; c < TILE; c++) t[c] *= xr;
-        s += warp_transpose_sum(t, lane);                             // lane c: sum_r L[r][c] x[r]
+      double sA = 0.0, sB = 0.0;
+      if (myq < nbA) {
+        const double* xv = xs + (size_t)((J + 1 + myq) % ring)*TILE;
+        sA += dot32(tA, xv);                                          // lane c: sum_r L[r][c] x[r]
+        if (hasB && myq + 1 < nbB) sB += dot32(tB, xv);
       }
-      for (int q = myq + BW_CL*BW_TW; q < nbelow; q += BW_CL*BW_TW) {   // only when WB > 32
-        const double* tp = colJ + (size_t)(q + 1)*TILE2;
-#pragma unroll
-        for (int c = 0; c < TILE; c++) t[c] = tp[c*TILE + lane];     // row `lane` of L_IJ
-        const double xr = xs[(size_t)((J + 1 + q) % ring)*TILE + lane];
-#pragma unroll
-        for (int c = 0; c < TILE; c++) t[c] *= xr;
-        s += warp_transpose_sum(t, lane);
+      for (int q = myq + BW_CL*BW_TW; q < nbA; q += BW_CL*BW_TW) {    // only when WB > 32 (tA / tB double as scratch)
+        const double* xv = xs + (size_t)((J + 1 + q) % ring)*TILE;
+        load_col(P.tiles + (size_t)J*W1*TILE2 + (size_t)(q + 1)*TILE2, tA);
+        sA += dot32(tA, xv);
+        if (hasB && q + 1 < nbB) { load_col(P.tiles + (size_t)(J - 1)*W1*TILE2 + (size_t)(q + 2)*TILE2, tB); sB += dot32(tB, xv); }
       }
-      lpart[(warp - 1)*TILE + lane] = s;
+      prefetchA(J - 2);                                                // in flight across the cluster barrier
+      prefetchB(J - 2);
+      lpart[(warp - 1)*TILE + lane] = sA;
+      lpart[(BW_TW + warp - 1)*TILE + lane] = sB;
     }
     __syncthreads();
-    double li[TILE];
     if (warp == 0) {
-      double s = 0.0;
+      double sA = 0.0, sB = 0.0;
 #pragma unroll
-      for (int w = 0; w < BW_TW; w++) s += lpart[w*TILE + lane];
+      for (int w = 0; w < BW_TW; w++) { sA += lpart[w*TILE + lane]; sB += lpart[(BW_TW + w)*TILE + lane]; }
 #pragma unroll
-      for (int r = 0; r < BW_CL; r++) cl.map_shared_rank(cpart, r)[((J & 1)*BW_CL + rank)*TILE + lane] = s;
-      const double* lp = P.linv + (size_t)J*TILE2;
-#pragma unroll
-      for (int c = 0; c < TILE; c++) li[c] = lp[c*TILE + lane];
+      for (int r = 0; r < BW_CL; r++) {
+        double* cp = cl.map_shared_rank(cpart, r) + (size_t)par*2*BW_CL*TILE;
+        cp[rank*TILE + lane] = sA; cp[(BW_CL + rank)*TILE + lane] = sB;
+      }
+      fetch_w0(J - 2, par ^ 1);                                        // next pair's tiles
+      tA[0] = P.rhs[(size_t)J*TILE + lane];                            // this pair's right-hand sides: latency under the barrier
+      tA[1] = hasB ? P.rhs[(size_t)(J - 1)*TILE + lane] : 0.0;
     }
     cl.sync();
     if (warp == 0) {
-      double v = P.rhs[(size_t)J*TILE + lane];
+      const double* cp = cpart + (size_t)par*2*BW_CL*TILE;
+      const double* st = sW0 + (size_t)par*3*TILE*BW_PS;
+      double v = tA[0], v2 = tA[1];
 #pragma unroll
-      for (int r = 0; r < BW_CL; r++) v -= cpart[((J & 1)*BW_CL + r)*TILE + lane];
+      for (int r = 0; r < BW_CL; r++) { v -= cp[r*TILE + lane]; v2 -= cp[(BW_CL + r)*TILE + lane]; }
+      asm volatile("cp.async.wait_group 1;" ::: "memory");           // everything but the group issued above has landed
+      sv[lane] = v;
+      __syncwarp();
+      auto col = [&](const double* tile) {
+        const double2* lc = reinterpret_cast<const double2*>(tile + lane*BW_PS);
 #pragma unroll
-      for (int c = 0; c < TILE; c++) li[c] *= v;                      // Linv[lane][c] * v[lane]
-      const double x = warp_transpose_sum(li, lane);                  // lane c: sum_r Linv[r][c] v[r]
-      xs[(size_t)(J % ring)*TILE + lane] = x;
+        for (int r = 0; r < TILE/2; r++) { const double2 u = lc[r]; tB[2*r] = u.x; tB[2*r + 1] = u.y; }
+      };
+      col(st);
+      const double x = dot32(tB, sv);                                 // lane c: sum_r Linv[r][c] v[r]
+      double* xj = xs + (size_t)(J % ring)*TILE;
+      xj[lane] = x;
       if (rank == 0) P.rhs[(size_t)J*TILE + lane] = x;
+      if (hasB) {
+        __syncwarp();
+        if (WB >= 1) { col(st + 2*TILE*BW_PS); v2 -= dot32(tB, xj); }   // (L(J,J-1)^T x_J)[lane]
+        __syncwarp();
+        sv[lane] = v2;
+        __syncwarp();
+        col(st + TILE*BW_PS);
+        const double x2 = dot32(tB, sv);
+        xs[(size_t)((J - 1) % ring)*TILE + lane] = x2;
+        if (rank == 0) P.rhs[(size_t)(J - 1)*TILE + lane] = x2;
+      }
     }
     __syncthreads();
   }
@@ -1250,7 +1324,7 @@ int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, 
 }
 
 int launch_band_solve(const DevBand& B, const double* linv, cudaStream_t s) {
-  const size_t smem = ((size_t)(B.WB + 1)*TILE + (size_t)(BW_TW + 2*BW_CL)*TILE)*sizeof(double);
+  const size_t smem = ((size_t)(B.WB + 2)*TILE + (size_t)(2*BW_TW + 4*BW_CL + 1)*TILE + 6*TILE*BW_PS)*sizeof(double);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(band_backward_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024); attr = true; }
   const int nthr = (BW_TW + 1)*32;
