@@ -377,6 +377,9 @@ static int finalize_impl(dynoba_solver* h) {
   }
   std::vector<int32_t> grank(nl, 0);
   for (size_t r = 0; r < gorder.size(); r++) grank[gorder[r]] = (int32_t)r;
+  std::vector<int32_t> lrank(nl);                       // group rank of every landmark (one gather per factor later)
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nl; i++) lrank[i] = grank[root[i]];
   // landmark device indices
   h->pt_new.assign(npt, 0); h->fl_new.assign(nfl, 0);
   {
@@ -471,7 +474,7 @@ static int finalize_impl(dynoba_solver* h) {
       std::vector<int64_t> key(n);
 #pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < n; i++) {
-        frank[i] = grank[root[lmk_id(ti.cls[lslot], b.idx[i*ti.arity + lslot])]];
+        frank[i] = lrank[lmk_id(ti.cls[lslot], b.idx[i*ti.arity + lslot])];
         key[i] = ((int64_t)frank[i] << 32) | (uint32_t)h->pos[b.idx[i*ti.arity + pslot]];
       }
       int unsorted = 0;
