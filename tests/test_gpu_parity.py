@@ -250,6 +250,56 @@ def test_two_directional_factorisation_long_trajectory():
     assert abs(st["error_final"] - so["error_final"]) <= 1e-5*so["error_final"]
 
 
+def _permuted(p, seed, landmark_runs):
+    """The same graph with its factors listed in another order: whole landmark runs shuffled (the order DynOSAM's
+    formulations produce up to the order of the landmarks -- the run-based sort of the symbolic phase) or every factor
+    shuffled individually (the general stable sort)."""
+    import dataclasses
+    rng = np.random.default_rng(seed)
+    blocks = []
+    for b in p.blocks:
+        n = b.idx.shape[0]
+        if landmark_runs and b.type in (POSE2POINT3, HYBRID3):
+            lm = b.idx[:, -1]
+            starts = np.flatnonzero(np.r_[True, lm[1:] != lm[:-1]])
+            runs = np.split(np.arange(n), starts[1:])
+            perm = np.concatenate([runs[i] for i in rng.permutation(len(runs))])
+        else:
+            perm = rng.permutation(n)
+        sig = b.sigma if b.sigma.ndim == 1 else b.sigma[perm]
+        blocks.append(FactorBlock(b.type, b.idx[perm], None if b.meas is None else b.meas[perm], sig, b.robust_k,
+                                  aux_idx=None if b.aux_idx is None else b.aux_idx[perm]))
+    return dataclasses.replace(p, blocks=blocks)
+
+
+@pytest.mark.parametrize("landmark_runs", [True, False])
+def test_factor_order_does_not_matter(landmark_runs):
+    """Both sorting paths of the symbolic phase lead to the same damped step and the same LM result."""
+    p = synth.make_config("C1")
+    q = _permuted(p, 11, landmark_runs)
+    lam = 1e-3
+    d0 = _solver(p).solve(lam); d1 = _solver(q).solve(lam)
+    assert np.linalg.norm(d0 - d1) <= 1e-9*np.linalg.norm(d0)
+    s0 = _solver(p).optimize(); s1 = _solver(q).optimize()
+    assert s0["iterations"] == s1["iterations"] and s0["inner_iterations"] == s1["inner_iterations"]
+    assert abs(s0["error_final"] - s1["error_final"]) <= 1e-9*s0["error_final"]
+
+
+def test_recycled_device_blocks_are_clean():
+    """Solvers created one after the other reuse cached device allocations; results must not depend on what the
+    previous owner left behind (a world-centric graph first, then the hybrid one twice)."""
+    w = synth.make_config("C1", formulation="wcme")
+    _solver(w).optimize()
+    p = synth.make_config("C1")
+    a = _solver(p); sa = a.optimize(); va = a.values()
+    del a
+    _solver(w).optimize()
+    b = _solver(p); sb = b.optimize(); vb = b.values()
+    # (atomic flushes make the sums order-dependent at the last bits, hence tolerances instead of equality)
+    assert sa["iterations"] == sb["iterations"] and abs(sa["error_final"] - sb["error_final"]) <= 1e-9*sa["error_final"]
+    assert np.abs(va[0] - vb[0]).max() < 1e-8 and np.abs(va[1] - vb[1]).max() < 1e-8
+
+
 def test_unsupported_topology_reports_status():
     """A tracklet chained over more than 21 frames is outside the general-group kernel: status, not garbage."""
     from dynosam_b200.binding import DynobaError, ERR_UNSUPPORTED
