@@ -28,12 +28,20 @@ using namespace dynoba;
 
 namespace {
 
+// std::vector without the serial value-initialisation pass (the elements are written in parallel right after resize)
+template <class T> struct NoInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInitAlloc<U>; };
+  template <class U, class... A> void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+
 struct HostBlock {
   int type = 0; int64_t n = 0;
   std::vector<int32_t> idx; std::vector<double> meas, sigma; int sigma_dim = 1; bool bcast = true;
   double robust_k = 0; std::vector<int32_t> aux; bool has_aux = false;
   // finalize products
-  std::vector<int32_t> perm;   // sorted position -> original factor index
+  std::vector<int32_t, NoInitAlloc<int32_t>> perm;   // sorted position -> original factor index (filled in parallel, never value-initialised)
   DevBlock dev{};
   bool simple = false, pose_only = false;
   int part_off = 0, bs_off = 0;
@@ -109,7 +117,9 @@ struct DevCache {
 DevCache g_devcache;
 }  // namespace
 
-template <class T> static int dalloc(dynoba_solver* h, T** p, size_t count) {
+// clean = false: the caller overwrites every element it will ever read (band tiles: band_clear; Jacobian tiles: linearize;
+// Schur slots: schur_stage) -- a recycled block then skips the multi-GB memset.
+template <class T> static int dalloc(dynoba_solver* h, T** p, size_t count, bool clean = true) {
   *p = nullptr;
   if (count == 0) count = 1;
   const size_t bytes = (count*sizeof(T) + 255) & ~(size_t)255;
@@ -119,7 +129,7 @@ template <class T> static int dalloc(dynoba_solver* h, T** p, size_t count) {
     cudaError_t e = cudaMalloc(&q, bytes);
     if (e != cudaSuccess) { cudaGetLastError(); g_devcache.trim(); CK(cudaMalloc(&q, bytes)); }
   }
-  else {
+  else if (clean) {
     // a recycled block holds the previous owner's data; several kernels leave entries they own untouched (padding lanes,
     // partial sums of early-exit CTAs) and count on the zeros a fresh allocation happens to have.  Ordered before any
     // later use: the solver's streams are non-blocking, so wait for the memset here.
@@ -325,7 +335,9 @@ static int finalize_impl(dynoba_solver* h) {
       }
     }
   }
-  std::vector<int32_t> root(nl); for (int64_t i = 0; i < nl; i++) root[i] = uf_find(uf, (int)i);
+  std::vector<int32_t, NoInitAlloc<int32_t>> root(nl);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nl; i++) { int x = (int)i; while (uf[x] != x) x = uf[x]; root[i] = x; }      // read-only find
   std::vector<int32_t> gmin(nl, INT32_MAX), gmax(nl, -1), gblk(nl, -1), gcount(nl, 0), gsec(nl, INT32_MAX);
   for (int64_t i = 0; i < nl; i++) gcount[root[i]]++;
   int spread = 0;
@@ -411,7 +423,7 @@ static int finalize_impl(dynoba_solver* h) {
   B.tile_count = (size_t)(B.NTA + B.NTB)*(B.WB + 1);
   { // [tiles A | tiles B | rhs A | rhs B] contiguous so that one all-reduce (and one clear) covers everything
     const size_t nrhs = (size_t)(B.NTA + B.NTB)*TILE;
-    double* buf; int rc = dalloc(h, &buf, B.tile_count*TILE2 + nrhs); if (rc) return rc;
+    double* buf; int rc = dalloc(h, &buf, B.tile_count*TILE2 + nrhs, false); if (rc) return rc;
     B.tiles = buf; B.tiles2 = buf + (size_t)B.NTA*(B.WB + 1)*TILE2;
     B.rhs = buf + B.tile_count*TILE2; B.rhs2 = B.rhs + (size_t)B.NTA*TILE;
     if (B.two) { if ((rc = dalloc(h, &B.dp, (size_t)B.n_pad))) return rc; } else B.dp = B.rhs;
@@ -467,11 +479,14 @@ static int finalize_impl(dynoba_solver* h) {
     const int64_t n = b.n; const int stride = pad32(n);
     int lslot = -1, pslot = -1;
     for (int k = 0; k < ti.arity; k++) { if (ti.cls[k] != VC_POSE && lslot < 0) lslot = k; if (ti.cls[k] == VC_POSE && pslot < 0) pslot = k; }
-    b.perm.resize(n); std::iota(b.perm.begin(), b.perm.end(), 0);
-    std::vector<int32_t> frank;
+    // (serial value-initialisation of 10^7-element vectors costs tens of milliseconds each: first-touch them in parallel)
+    b.perm.resize(n);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) b.perm[i] = (int32_t)i;
+    std::unique_ptr<int32_t[]> frank_buf; int32_t* frank = nullptr;
     if (lslot >= 0) {
-      frank.resize(n);
-      std::vector<int64_t> key(n);
+      frank_buf.reset(new int32_t[n]); frank = frank_buf.get();
+      std::unique_ptr<int64_t[]> key_buf(new int64_t[n]); int64_t* key = key_buf.get();
 #pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < n; i++) {
         frank[i] = lrank[lmk_id(ti.cls[lslot], b.idx[i*ti.arity + lslot])];
@@ -545,8 +560,14 @@ static int finalize_impl(dynoba_solver* h) {
       for (int k = 0; k < b.sigma_dim; k++) hsig[(size_t)k*stride + s] = 1.0;
       haux[s] = 0;
     }
-    if (ti.meas == 0) for (int64_t s = 0; s < n; s++) hmeas[s] = 0.0;
-    if (!b.has_aux) for (int64_t s = 0; s < n; s++) haux[s] = 0;
+    if (ti.meas == 0) {
+#pragma omp parallel for schedule(static)
+      for (int64_t s = 0; s < n; s++) hmeas[s] = 0.0;
+    }
+    if (!b.has_aux) {
+#pragma omp parallel for schedule(static)
+      for (int64_t s = 0; s < n; s++) haux[s] = 0;
+    }
 #pragma omp parallel for schedule(static)
     for (int64_t s = 0; s < n; s++) {
       const int64_t o = b.perm[s];
@@ -567,7 +588,7 @@ static int finalize_impl(dynoba_solver* h) {
     if ((rc = dalloc(h, &ds, hsig.size()))) return rc; CK(h2d(ds, hsig.data(), hsig.size()*8));
     if (b.has_aux) { if ((rc = dalloc(h, &dax, haux.size()))) return rc; CK(h2d(dax, haux.data(), haux.size()*4)); }
     d.idx = di; d.meas = dm; d.isig = ds; d.aux = dax;
-    if ((rc = dalloc(h, &d.J, (size_t)ti.dim*ti.jcols*stride))) return rc;
+    if ((rc = dalloc(h, &d.J, (size_t)ti.dim*ti.jcols*stride, false))) return rc;
     if ((rc = dalloc(h, &d.b, (size_t)ti.dim*stride))) return rc;
     if (numeric_grid(b.type, (int)n) > 0) { if ((rc = dalloc(h, &d.num_scratch, (size_t)numeric_grid(b.type, (int)n)))) return rc; }
     lap("  blk upload+alloc");
@@ -681,7 +702,7 @@ static int finalize_impl(dynoba_solver* h) {
         if ((rc = dalloc(h, &dcv, cvars.size()))) return rc; CK(cudaMemcpy(dcv, cvars.data(), cvars.size()*4, cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dlv, lvar.size()))) return rc; CK(cudaMemcpy(dlv, lvar.data(), lvar.size(), cudaMemcpyHostToDevice));
         if ((rc = dalloc(h, &dgw, gwin.size()))) return rc; CK(cudaMemcpy(dgw, gwin.data(), gwin.size(), cudaMemcpyHostToDevice));
-        if ((rc = dalloc(h, &dslots, (size_t)n*NPs*WIN_SLOT_DOUBLES))) return rc;
+        if ((rc = dalloc(h, &dslots, (size_t)n*NPs*WIN_SLOT_DOUBLES, false))) return rc;
         b.win.n_jobs = (int)jobs.size(); b.win.jobs = djobs; b.win.batches = dbat; b.win.chunk_nloc = dnl; b.win.cvars = dcv; b.win.lvar = dlv; b.win.grp_win = dgw; b.win.slots = dslots;
         b.use_window = true;
         { size_t nw = 0; for (int g = 0; g < ng; g++) nw += gwin[g] == 1 || gl[g] < 0; b.all_window = nw == (size_t)ng; }
