@@ -625,7 +625,8 @@ static int finalize_impl(dynoba_solver* h) {
       b.use_window = false; b.all_window = false; b.win = DevWindows{};
       if (win_type && !gl.empty() && !getenv("DYNOBA_NO_WINDOW")) {
         const int ng = (int)gl.size(), NPs = ti.npose;
-        std::vector<unsigned char> gwin(ng, 0), lvar((size_t)NPs*stride, 0);
+        std::vector<unsigned char> gwin(ng, 0);
+        std::vector<unsigned char, NoInitAlloc<unsigned char>> lvar((size_t)NPs*stride);   // only read for window-path factors
         std::vector<int32_t> chunk_nloc, cvars; std::vector<int4> jobs, batches;
         int pose_slot[2] = {0, 0}; { int c = 0; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE && c < 2) pose_slot[c++] = k; }
         // window size: one 512-thread CTA holds 16 tiles of 8x4 blocks; NLOC 24 -> 12 tiles (one stripe), NLOC 40 -> 30 (two)
@@ -633,7 +634,7 @@ static int finalize_impl(dynoba_solver* h) {
         if (const char* e = getenv(NPs == 1 ? "DYNOBA_WIN_CAP1" : "DYNOBA_WIN_CAP2")) cap = std::max(2, std::min(WIN_NLOC_MAX, atoi(e)));
         // greedy chunking, independently inside parallel segments of the group list (a chunk never crosses a segment)
         const int nseg = std::max(1, std::min<int>(omp_get_max_threads(), ng/4096 + 1));
-        struct SegOut { std::vector<int32_t> g0, nloc, cv; };
+        struct SegOut { std::vector<int32_t> g0, nloc, cv, b0; std::vector<int4> bat; };   // b0: first batch of each chunk (+ end)
         std::vector<SegOut> seg(nseg);
 #pragma omp parallel for schedule(static, 1)
         for (int t = 0; t < nseg; t++) {
@@ -649,6 +650,18 @@ static int finalize_impl(dynoba_solver* h) {
             for (size_t i = 0; i < sorted.size(); i++) stamp[sorted[i]] = -1;
             out.g0.push_back(cur_g0); out.nloc.push_back((int32_t)sorted.size());
             sorted.resize(WIN_NLOC_MAX, 0); out.cv.insert(out.cv.end(), sorted.begin(), sorted.end());
+            // batches of the chunk: runs of window-path landmarks (other groups end a run), bounded in landmarks and slots
+            out.b0.push_back((int32_t)out.bat.size());
+            int rg0 = -1, rslots = 0;
+            auto close_batch = [&](int ge) { if (rg0 >= 0) out.bat.push_back(make_int4(rg0, ge, gp[rg0], gp[ge])); rg0 = -1; rslots = 0; };
+            for (int g = cur_g0; g < g_end; g++) {
+              if (gwin[g] != 1) { close_batch(g); continue; }
+              const int ns_ = (gp[g+1] - gp[g])*NPs;
+              if (rg0 >= 0 && (rslots + ns_ > WIN_BATCH_SLOTS || g - rg0 >= WIN_BATCH_LMK)) close_batch(g);
+              if (rg0 < 0) rg0 = g;
+              rslots += ns_;
+            }
+            close_batch(g_end);
             chunk_id++; cur.clear(); cur_g0 = g_end;
           };
           for (int g = ga; g < gb_; g++) {
@@ -679,19 +692,9 @@ static int finalize_impl(dynoba_solver* h) {
           chunk_nloc.push_back(seg[t].nloc[c]);
           cvars.insert(cvars.end(), seg[t].cv.begin() + c*WIN_NLOC_MAX, seg[t].cv.begin() + (c + 1)*WIN_NLOC_MAX);
           const int nl_ = seg[t].nloc[c]; const int ntile = win_ntiles(nl_);
-          const int cg0 = seg[t].g0[c], cg1 = c + 1 < seg[t].g0.size() ? seg[t].g0[c + 1] : (int)((int64_t)ng*(t + 1)/nseg);
-          // batches: runs of window-path landmarks (other groups end a run), bounded in landmarks and slots
+          const size_t sb0 = seg[t].b0[c], sb1 = c + 1 < seg[t].b0.size() ? seg[t].b0[c + 1] : seg[t].bat.size();
           const int b0 = (int)batches.size();
-          int rg0 = -1, rslots = 0;
-          auto close_batch = [&](int g_end) { if (rg0 >= 0) batches.push_back(make_int4(rg0, g_end, gp[rg0], gp[g_end])); rg0 = -1; rslots = 0; };
-          for (int g = cg0; g < cg1; g++) {
-            if (gwin[g] != 1) { close_batch(g); continue; }
-            const int ns_ = (gp[g+1] - gp[g])*NPs;
-            if (rg0 >= 0 && (rslots + ns_ > WIN_BATCH_SLOTS || g - rg0 >= WIN_BATCH_LMK)) close_batch(g);
-            if (rg0 < 0) rg0 = g;
-            rslots += ns_;
-          }
-          close_batch(cg1);
+          batches.insert(batches.end(), seg[t].bat.begin() + sb0, seg[t].bat.begin() + sb1);
           const int b1 = (int)batches.size();
           if (b1 > b0) for (int st = 0; st*WIN_ACC_WARPS < ntile; st++) jobs.push_back(make_int4(chunk_id, st, b0, b1));
         }
