@@ -38,8 +38,8 @@ template <class T> struct NoInitAlloc : std::allocator<T> {
 
 struct HostBlock {
   int type = 0; int64_t n = 0;
-  std::vector<int32_t> idx; std::vector<double> meas, sigma; int sigma_dim = 1; bool bcast = true;
-  double robust_k = 0; std::vector<int32_t> aux; bool has_aux = false;
+  std::vector<int32_t, NoInitAlloc<int32_t>> idx, aux; std::vector<double, NoInitAlloc<double>> meas; std::vector<double> sigma;
+  int sigma_dim = 1; bool bcast = true; double robust_k = 0; bool has_aux = false;
   // finalize products
   std::vector<int32_t, NoInitAlloc<int32_t>> perm;   // sorted position -> original factor index (filled in parallel, never value-initialised)
   DevBlock dev{};
@@ -144,6 +144,20 @@ static void free_device(dynoba_solver* h) {
   for (auto& a : h->allocs) g_devcache.give(a.first, a.second);
   h->allocs.clear();
   h->finalized = false; h->linearized = false;
+}
+
+// copy of a caller's array into the handle: parallel, so that the first touch of the fresh pages (the expensive part of a
+// several-hundred-MB copy) is spread over the cores.  Runs on its own thread count: torchrun pins OMP_NUM_THREADS to 1.
+template <class V, class T> static void par_assign(V& v, const T* src, size_t count) {
+  v.resize(count);
+  const size_t chunk = (size_t)1 << 18;
+  const int64_t nchunk = (int64_t)((count + chunk - 1)/chunk);
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(omp_get_num_procs(), 32), nchunk));
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int64_t c = 0; c < nchunk; c++) {
+    const size_t a = (size_t)c*chunk, e = std::min(count, a + chunk);
+    std::memcpy(v.data() + a, src + a, (e - a)*sizeof(T));
+  }
 }
 
 extern "C" {
@@ -255,13 +269,13 @@ int dynoba_add_factors(dynoba_handle h, int type, int64_t n, const int32_t* idx,
   ARG(sigma && (sigma_dim == 1 || sigma_dim == ti.dim), "sigma_dim must be 1 or the residual dimension");
   ARG(sigma_count == 1 || sigma_count == n, "sigma_count must be 1 or n"); ARG(!ti.needs_aux || n == 0 || aux_idx, "factor type needs aux_idx");
   HostBlock b; b.type = type; b.n = n;
-  b.idx.assign(idx, idx + (size_t)n*ti.arity);
-  if (ti.meas) b.meas.assign(meas, meas + (size_t)n*ti.meas);
+  par_assign(b.idx, idx, (size_t)n*ti.arity);
+  if (ti.meas) par_assign(b.meas, meas, (size_t)n*ti.meas);
   b.sigma_dim = sigma_dim; b.bcast = sigma_count == 1 && n != 1;
   b.sigma.assign(sigma, sigma + (size_t)sigma_count*sigma_dim);
   for (double s : b.sigma) ARG(s > 0, "sigma must be positive");
   b.robust_k = robust_k;
-  if (aux_idx) { b.aux.assign(aux_idx, aux_idx + n); b.has_aux = true; }
+  if (aux_idx) { par_assign(b.aux, aux_idx, (size_t)n); b.has_aux = true; }
   h->blocks.push_back(std::move(b));
   if (h->finalized) free_device(h);
   return DYNOBA_OK;
