@@ -98,21 +98,23 @@ PinnedArena g_arena;
 // allocation fails or when it holds more than DYNOBA_DEVCACHE_GB (default 96) gigabytes.
 namespace {
 struct DevCache {
-  std::mutex mu; std::multimap<size_t, void*> blocks; size_t bytes = 0;
-  void* take(size_t need, size_t* got) {     // smallest cached block of at least `need` bytes, if it is not much larger
+  std::mutex mu; std::multimap<std::pair<int, size_t>, void*> blocks; size_t bytes = 0;   // keyed by (device, bytes)
+  void* take(int dev, size_t need, size_t* got) {   // smallest cached block of this device with at least `need` bytes, if not much larger
     std::lock_guard<std::mutex> l(mu);
-    auto it = blocks.lower_bound(need);
-    if (it == blocks.end() || it->first > need + need/4 + 4096) return nullptr;
-    void* p = it->second; *got = it->first; bytes -= it->first; blocks.erase(it); return p;
+    auto it = blocks.lower_bound(std::make_pair(dev, need));
+    if (it == blocks.end() || it->first.first != dev || it->first.second > need + need/4 + 4096) return nullptr;
+    void* p = it->second; *got = it->first.second; bytes -= it->first.second; blocks.erase(it); return p;
   }
-  void give(void* p, size_t n) {
+  void give(int dev, void* p, size_t n) {
     static const bool off = getenv("DYNOBA_NO_DEVCACHE") != nullptr;
     static const size_t cap = (size_t)(getenv("DYNOBA_DEVCACHE_GB") ? atof(getenv("DYNOBA_DEVCACHE_GB")) : 96.0)*(1ull << 30);
     std::lock_guard<std::mutex> l(mu);
     if (off || bytes + n > cap) { cudaFree(p); return; }
-    blocks.emplace(n, p); bytes += n;
+    blocks.emplace(std::make_pair(dev, n), p); bytes += n;
   }
-  void trim() { std::lock_guard<std::mutex> l(mu); for (auto& b : blocks) cudaFree(b.second); blocks.clear(); bytes = 0; }
+  void trim() {       // (cudaFree takes the pointer's own device; the current device does not matter)
+    std::lock_guard<std::mutex> l(mu); for (auto& b : blocks) cudaFree(b.second); blocks.clear(); bytes = 0;
+  }
 };
 DevCache g_devcache;
 }  // namespace
@@ -124,7 +126,7 @@ template <class T> static int dalloc(dynoba_solver* h, T** p, size_t count, bool
   if (count == 0) count = 1;
   const size_t bytes = (count*sizeof(T) + 255) & ~(size_t)255;
   size_t got = bytes;                        // a cached block may be larger than asked: its true size goes back with it
-  void* q = g_devcache.take(bytes, &got);
+  void* q = g_devcache.take(h->device, bytes, &got);
   if (!q) {
     cudaError_t e = cudaMalloc(&q, bytes);
     if (e != cudaSuccess) { cudaGetLastError(); g_devcache.trim(); CK(cudaMalloc(&q, bytes)); }
@@ -141,7 +143,7 @@ template <class T> static int dalloc(dynoba_solver* h, T** p, size_t count, bool
 }
 static void free_device(dynoba_solver* h) {
   if (!h->allocs.empty()) cudaDeviceSynchronize();      // cudaFree used to imply this; cached blocks must be idle too
-  for (auto& a : h->allocs) g_devcache.give(a.first, a.second);
+  for (auto& a : h->allocs) g_devcache.give(h->device, a.first, a.second);
   h->allocs.clear();
   h->finalized = false; h->linearized = false;
 }
@@ -939,7 +941,7 @@ int dynoba_get_factor_errors(dynoba_handle h, int bi, double* err) {
   CK(cudaStreamSynchronize(h->stream));
   for (int64_t s = 0; s < b.n; s++) err[b.perm[s]] = he[s];
   { auto it = std::find_if(h->allocs.begin(), h->allocs.end(), [&](const std::pair<void*, size_t>& a) { return a.first == (void*)d; });
-    g_devcache.give(it->first, it->second); h->allocs.erase(it); }
+    g_devcache.give(h->device, it->first, it->second); h->allocs.erase(it); }
   return DYNOBA_OK;
 }
 
