@@ -198,3 +198,44 @@ def make_config(name: str, formulation="hybrid", seed=42, scale=1.0, **kw) -> Pr
     p = make_problem(formulation=formulation, seed=seed, **cfg)
     p.meta["config"] = name
     return p
+
+
+def make_all_types_problem(seed=3) -> Problem:
+    from .problem import FLOWPROJ2, HYBRID_STEREO3, MOTIONPOSE3, SMOOTH_POSE6, STEREO3
+    """A graph holding every factor type of SURVEY.md 8a (a3-a9, a15) on random but well-posed inputs."""
+    rng = np.random.default_rng(seed)
+    base = make_problem(n_frames=12, n_objects=2, n_static=150, n_dynamic=80, formulation="hybrid", seed=seed)
+    N = base.meta["n_frames"]; npose = base.n_pose; npt = base.n_point
+    K = np.array([721.5377, 721.5377, 0.0, 609.5593, 172.854, 0.5372])
+    blocks = list(base.blocks)
+    # stereo observations of the first 100 static points from their first frames (positive depth by construction)
+    ptp = base.blocks[0]
+    sel = np.arange(0, min(300, ptp.n))
+    cam = ptp.idx[sel, 0]; pid = ptp.idx[sel, 1]
+    q = lie.transform_to(base.pose[cam], base.point[pid])
+    q[:, 2] = np.abs(q[:, 2]) + 1.0
+    zs = np.stack([K[3] + K[0]*q[:, 0]/q[:, 2], K[3] + K[0]*(q[:, 0] - K[5])/q[:, 2], K[4] + K[1]*q[:, 1]/q[:, 2]], 1)
+    zs += rng.normal(0, 1.0, zs.shape)
+    blocks.append(FactorBlock(STEREO3, np.stack([cam, pid], 1), zs, np.array([1.5, 1.5, 2.0]), 1.345))
+    # a cheirality case: a point behind the camera
+    hyb = [b for b in base.blocks if b.type == HYBRID3][0]
+    hs = np.arange(0, min(200, hyb.n))
+    blocks.append(FactorBlock(HYBRID_STEREO3, hyb.idx[hs], rng.uniform(0, 300, (hs.size, 3)), np.array([2.0]), 0.0,
+                              aux_idx=hyb.aux_idx[hs]))
+    # world-centric pieces on fresh point variables
+    extra_pts = rng.normal(0, 3, (60, 3)) + [0, 0, 10]
+    pts = np.concatenate([base.point, extra_pts]); e0 = npt
+    mot = np.arange(N, npose)
+    ch = np.array([i for i in range(39) if i % 10 != 9])                 # four chains of 10 points
+    tri = np.stack([e0 + ch, e0 + ch + 1, rng.choice(mot, ch.size)], 1)
+    blocks.append(FactorBlock(TERNARY3, tri, None, np.array([0.01]), 1e-4))
+    mp = np.stack([e0 + np.arange(40, 58), e0 + np.arange(41, 59), rng.choice(mot, 18), rng.choice(mot, 18)], 1)
+    blocks.append(FactorBlock(MOTIONPOSE3, mp, None, np.array([0.05]), 1e-3))
+    sp = np.stack([mot[:-2][:20], mot[1:-1][:20], mot[2:][:20]], 1)
+    blocks.append(FactorBlock(SMOOTH_POSE6, sp, None, np.array([0.01, 0.01, 0.01, 0.1, 0.1, 0.1])))
+    # flow-projection star: 30 flows attached to camera 3
+    flows = rng.normal(0, 1.0, (30, 2))
+    kp = np.stack([rng.uniform(100, 1100, 30), rng.uniform(50, 320, 30)], 1); depth = rng.uniform(4, 30, 30)
+    meas = np.concatenate([kp, depth[:, None], np.tile(base.pose[2], (30, 1))], 1)
+    blocks.append(FactorBlock(FLOWPROJ2, np.stack([np.arange(30), np.full(30, 3)], 1), meas, np.array([0.5]), 0.0))
+    return Problem(base.pose, pts, flow=flows, aux_pose=base.aux_pose, calib=K, blocks=blocks, pose_order=base.pose_order)
