@@ -55,29 +55,62 @@ def problem_bandwidth(p: Problem) -> int:
 
 
 def shard_problem(p: Problem, rank: int, world: int) -> Problem:
-    """Landmark shard of rank `rank`: landmarks (with all their factors) dealt round-robin in birth order;
-    pose-only factors live on rank 0.  Poses are replicated."""
+    """Time shard of rank `rank`.  Landmarks that share a factor (the points of a WCME / WCPE tracklet chain) form one
+    group; a group, with all its factors, goes to the rank whose slice of the (frame-ordered) pose axis holds the
+    group's first pose, and a pose-only factor to the rank of its first pose.  Poses are replicated.  Contiguous time
+    slices keep a rank's contribution to the reduced system inside the cells it owns (plus a halo one co-visibility
+    window wide), which is what the library's per-cell reduce moves.  q.meta["kept_points"] = mask of the kept points."""
     if world == 1:
         return p
-    keep_pt = (np.arange(p.n_point) % world) == rank
+    order = np.argsort(p.pose_order, kind="stable") if p.pose_order is not None else np.arange(p.n_pose)
+    pos = np.empty(p.n_pose, dtype=np.int64); pos[order] = np.arange(p.n_pose)
+    npt = p.n_point
+    # ---- landmark groups: connected components over factors with more than one point slot
+    group = np.arange(npt, dtype=np.int64)
+    edges = []
+    for b in p.blocks:
+        ls = [k for k, c in enumerate(SLOT_CLASS[b.type]) if c == 1]
+        for k in ls[1:]:
+            edges.append(np.stack([b.idx[:, ls[0]], b.idx[:, k]], 1))
+    if edges:
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+        e = np.concatenate(edges).astype(np.int64)
+        _, group = connected_components(coo_matrix((np.ones(e.shape[0], dtype=np.int8), (e[:, 0], e[:, 1])), shape=(npt, npt)), directed=False)
+        group = group.astype(np.int64)
+    ngroup = int(group.max(initial=-1)) + 1
+    first = np.full(ngroup, np.iinfo(np.int64).max)
+    for b in p.blocks:
+        cls = SLOT_CLASS[b.type]
+        ls = [k for k, c in enumerate(cls) if c == 1]; ps = [k for k, c in enumerate(cls) if c == 0]
+        if ls and ps:
+            np.minimum.at(first, group[b.idx[:, ls[0]]], pos[b.idx[:, ps]].min(1))
+    first[first == np.iinfo(np.int64).max] = 0
+    owner_of_pos = lambda q: np.minimum(q*world//max(p.n_pose, 1), world - 1)
+    keep_pt = owner_of_pos(first)[group] == rank
     new_idx = np.cumsum(keep_pt) - 1
     blocks = []
     for b in p.blocks:
         cls = SLOT_CLASS[b.type]
-        lslots = [k for k, c in enumerate(cls) if c == 1]
-        if not lslots:
+        ls = [k for k, c in enumerate(cls) if c == 1]; ps = [k for k, c in enumerate(cls) if c == 0]
+        if any(c == 2 for c in cls):          # optical-flow variables are not sharded: such blocks stay on rank 0
             if rank == 0:
                 blocks.append(b)
             continue
-        sel = keep_pt[b.idx[:, lslots[0]]]
+        if ls:
+            sel = keep_pt[b.idx[:, ls[0]]]
+            assert all(np.array_equal(keep_pt[b.idx[:, k]], sel) for k in ls[1:]), "a factor straddles two landmark shards"
+        else:
+            sel = owner_of_pos(pos[b.idx[:, ps]].min(1)) == rank
         idx = b.idx[sel].copy()
-        for k in lslots:
+        for k in ls:
             idx[:, k] = new_idx[idx[:, k]]
         blocks.append(FactorBlock(b.type, idx, None if b.meas is None else b.meas[sel],
                                   b.sigma if b.sigma_bcast else b.sigma[sel], b.robust_k,
                                   None if b.aux_idx is None else b.aux_idx[sel]))
-    q = Problem(p.pose, p.point[keep_pt], aux_pose=p.aux_pose, calib=p.calib, blocks=blocks, pose_order=p.pose_order,
+    q = Problem(p.pose, p.point[keep_pt], flow=p.flow, aux_pose=p.aux_pose, calib=p.calib, blocks=blocks, pose_order=p.pose_order,
                 pose_keys=p.pose_keys, point_keys=None if p.point_keys is None else p.point_keys[keep_pt], meta=dict(p.meta))
+    q.meta["kept_points"] = keep_pt
     return q
 
 
@@ -191,6 +224,9 @@ def main():
     ap.add_argument("--cpu-sample-scale", type=float, default=0.02)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cells", type=int, default=0, help="cells of the reduced solve (0 automatic, -1 plain band)")
+    ap.add_argument("--replicated-solve", action="store_true", help="N > 1: all-reduce the reduced system and solve it on every rank")
+    ap.add_argument("--tune", default="", help="name=value,... performance parameters (dynoba_set_tuning)")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -242,10 +278,24 @@ def main():
                 dist.all_reduce(t)
         return ar
 
+    def _tensor(dev, n):
+        class _A:  # noqa
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (dev, False), "version": 3, "strides": None}
+        return torch.as_tensor(_A(), device=f"cuda:{local}")
+
+    def reduce_cb(dev, n, root, stream):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            dist.reduce(_tensor(dev, n), dst=root)
+
     def new_solver(p):
         s = Solver(p, device=local)
+        s.set_partition(args.cells)
+        for kv in filter(None, args.tune.split(",")):
+            k, v = kv.split("="); s.set_tuning(k, float(v))
         if world > 1:
             s.set_shard(rank, world, make_allreduce(), bw)
+            if not args.replicated_solve:
+                s.set_reduce(reduce_cb)
         return s
 
     prm = dict(relative_error_tol=0.0, absolute_error_tol=0.0)

@@ -19,11 +19,12 @@ c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
 c_u64p = C.POINTER(C.c_uint64)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
 
 EXPORTS = [
     "dynoba_version", "dynoba_status_string", "dynoba_last_error", "dynoba_create", "dynoba_destroy",
     "dynoba_lm_default_params", "dynoba_set_variables", "dynoba_set_aux_poses", "dynoba_set_calibration",
-    "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_finalize", "dynoba_error",
+    "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_set_reduce", "dynoba_set_partition", "dynoba_set_tuning", "dynoba_finalize", "dynoba_error",
     "dynoba_optimize", "dynoba_get_variables", "dynoba_get_keys", "dynoba_num_variables", "dynoba_problem_info",
     "dynoba_linearize", "dynoba_linearize_block", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
     "dynoba_get_reduced_system", "dynoba_retract",
@@ -77,6 +78,9 @@ def load():
         L.dynoba_add_factors.argtypes = [C.c_void_p, C.c_int, C.c_int64, c_ip, c_dp, c_dp, C.c_int, C.c_int64, C.c_double, c_ip]
         L.dynoba_set_pose_order.argtypes = [C.c_void_p, C.c_int64, c_ip]
         L.dynoba_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p, C.c_int]
+        L.dynoba_set_reduce.argtypes = [C.c_void_p, REDUCE_FN, C.c_void_p]
+        L.dynoba_set_partition.argtypes = [C.c_void_p, C.c_int]
+        L.dynoba_set_tuning.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.dynoba_finalize.argtypes = [C.c_void_p]
         L.dynoba_error.argtypes = [C.c_void_p, c_dp]
         L.dynoba_optimize.argtypes = [C.c_void_p, C.POINTER(LmParams), C.POINTER(LmStats)]
@@ -174,6 +178,25 @@ class Solver:
                 return 1
         self._cb = ALLREDUCE_FN(_cb)
         self._ck(self.lib.dynoba_set_shard(self.h, rank, world, self._cb, None, min_bandwidth))
+
+    def set_reduce(self, reduce):
+        """reduce(dev_ptr:int, n:int, root:int, stream:int) -> None sums n doubles at rank `root` (distributed reduced solve)."""
+        def _cb(ctx, dev, n, root, stream):
+            try:
+                reduce(dev, n, root, stream)
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("reduce callback failed:", e)
+                return 1
+        self._cb_red = REDUCE_FN(_cb)
+        self._ck(self.lib.dynoba_set_reduce(self.h, self._cb_red, None))
+
+    def set_partition(self, ncells):
+        """number of cells of the reduced solve (0 automatic, -1 one plain band factorisation)"""
+        self._ck(self.lib.dynoba_set_partition(self.h, int(ncells)))
+
+    def set_tuning(self, name, value):
+        self._ck(self.lib.dynoba_set_tuning(self.h, name.encode(), float(value)))
 
     def reset_values(self):
         """Re-upload the initial values of the ingested problem (device layout is kept)."""

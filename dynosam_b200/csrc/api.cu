@@ -58,10 +58,11 @@ struct dynoba_solver {
   std::vector<HostBlock> blocks;
   bool finalized = false, linearized = false, supported = true;
   std::vector<int32_t> pos, pt_new, fl_new;
-  DevVars cur{}, cand{}; DevBand band{};
+  DevVars cur{}, cand{}; BandPlan plan{}; DevBand& band = plan.band; int ncell_request = 0;
   double *dl_point = nullptr, *dl_flow = nullptr, *partials = nullptr, *scalars = nullptr;
-  int* fail = nullptr; int* chol_flags = nullptr; double* linv = nullptr; int n_partials = 0, n_lin_partials = 0, n_bs_partials = 0;
+  int* fail = nullptr; int n_partials = 0, n_lin_partials = 0, n_bs_partials = 0;
   int rank = 0, world = 1; dynoba_allreduce_fn allreduce = nullptr; void* ar_ctx = nullptr; int min_bw = 0;
+  dynoba_reduce_fn reduce = nullptr; void* red_ctx = nullptr;
   int64_t launches = 0; int64_t jac_bytes = 0;
   GeneralGroups gen{}; int gen_bs_off = 0;
   std::vector<std::pair<void*, size_t>> allocs;   // device allocations (pointer, bytes)
@@ -131,9 +132,9 @@ template <class T> static int dalloc(dynoba_solver* h, T** p, size_t count, bool
     cudaError_t e = cudaMalloc(&q, bytes);
     if (e != cudaSuccess) { cudaGetLastError(); g_devcache.trim(); CK(cudaMalloc(&q, bytes)); }
   }
-  else if (clean) {
-    // a recycled block holds the previous owner's data; several kernels leave entries they own untouched (padding lanes,
-    // partial sums of early-exit CTAs) and count on the zeros a fresh allocation happens to have.  Ordered before any
+  if (clean) {
+    // cudaMalloc does not zero and a recycled block holds the previous owner's data; several kernels leave entries they
+    // own untouched (padding lanes, partial sums of early-exit CTAs) and read them back as zeros.  Ordered before any
     // later use: the solver's streams are non-blocking, so wait for the memset here.
     CK(cudaMemsetAsync(q, 0, bytes, h->stream)); CK(cudaStreamSynchronize(h->stream));
   }
@@ -290,6 +291,25 @@ int dynoba_set_pose_order(dynoba_handle h, int64_t n, const int32_t* rank) {
   return DYNOBA_OK;
 }
 
+int dynoba_set_reduce(dynoba_handle h, dynoba_reduce_fn fn, void* ctx) {
+  ARG(h, "null handle");
+  h->reduce = fn; h->red_ctx = ctx;
+  return DYNOBA_OK;
+}
+int dynoba_set_tuning(dynoba_handle h, const char* name, double value) {
+  ARG(h, "null handle"); ARG(name, "null name");
+  if (!std::strcmp(name, "outer_weight")) { h->plan.outer_weight = value; if (h->finalized) free_device(h); }
+  else if (!std::strcmp(name, "band_ctas_per_chain")) band_set_tuning((int)value);
+  else ARG(false, "unknown tuning parameter");
+  return DYNOBA_OK;
+}
+int dynoba_set_partition(dynoba_handle h, int ncells) {
+  ARG(h, "null handle"); ARG(ncells >= -1 && ncells <= MAX_CELLS, "ncells out of range");
+  h->ncell_request = ncells;
+  if (h->finalized) free_device(h);
+  return DYNOBA_OK;
+}
+
 int dynoba_set_shard(dynoba_handle h, int rank, int world, dynoba_allreduce_fn fn, void* ctx, int min_bandwidth) {
   ARG(h, "null handle"); ARG(world >= 1 && rank >= 0 && rank < world, "bad rank/world"); ARG(world == 1 || fn, "world > 1 needs an all-reduce");
   h->rank = rank; h->world = world; h->allreduce = fn; h->ar_ctx = ctx; h->min_bw = min_bandwidth;
@@ -423,29 +443,18 @@ static int finalize_impl(dynoba_solver* h) {
     for (int64_t i = 0; i < nfl; i++) h->fl_new[of[i]] = (int32_t)i;
   }
   lap("groups + landmark order");
-  // ---- band structure
+  // ---- band structure: cell decomposition of the reduced system (kernels_band.cu)
+  {
+    int bw = 6*spread + 5; if (bw < h->min_bw) bw = h->min_bw;
+    if (band_plan_layout(h->plan, (int)(6*np), bw, h->ncell_request, h->rank, h->world)) { h->err = "band layout failed"; return DYNOBA_ERR_BAD_ARG; }
+    double* dbuf; int* ibuf; char* desc; double* dp = nullptr; int rc;
+    if ((rc = dalloc(h, &dbuf, h->plan.n_doubles, false))) return rc;     // accumulated part: band_clear; work buffers: written before read
+    if ((rc = dalloc(h, &ibuf, h->plan.n_ints, false))) return rc;        // flags: cleared before every factorisation launch
+    if ((rc = dalloc(h, &desc, h->plan.n_desc_bytes))) return rc;
+    if (h->plan.band.ncell > 0) { if ((rc = dalloc(h, &dp, (size_t)h->plan.band.n_pad))) return rc; }
+    band_plan_bind(h->plan, dbuf, ibuf, desc, dp);
+  }
   DevBand& B = h->band;
-  B.n = (int)(6*np);
-  int bw = 6*spread + 5; if (bw < h->min_bw) bw = h->min_bw; if (bw > B.n - 1) bw = std::max(B.n - 1, 0);
-  B.bw = bw; B.NT = std::max((B.n + TILE - 1)/TILE, 1); B.n_pad = B.NT*TILE;
-  B.WB = (bw + TILE - 1)/TILE; if (B.NT > 1 && B.WB < 1) B.WB = 1; if (B.WB > B.NT - 1) B.WB = B.NT - 1;
-  // two-directional factorisation when the system is long enough: split at the middle, separator = WB tiles
-  B.two = 0; B.split_lo = B.split_hi = 0; B.NTA = B.NT; B.NTB = 0; B.tiles2 = nullptr; B.rhs2 = nullptr;
-  int min_nt = 8; if (const char* e = getenv("DYNOBA_TWIST_MIN_TILES")) min_nt = atoi(e);
-  if (!getenv("DYNOBA_NO_TWIST") && B.WB >= 1 && B.NT >= std::max(min_nt, 4*B.WB + 4)) {
-    const int KmA = (B.NT - B.WB)/2;
-    B.two = 1; B.split_lo = KmA*TILE; B.split_hi = B.split_lo + B.WB*TILE; B.NTA = KmA + B.WB; B.NTB = B.NT - KmA;
-  }
-  B.tile_count = (size_t)(B.NTA + B.NTB)*(B.WB + 1);
-  { // [tiles A | tiles B | rhs A | rhs B] contiguous so that one all-reduce (and one clear) covers everything
-    const size_t nrhs = (size_t)(B.NTA + B.NTB)*TILE;
-    double* buf; int rc = dalloc(h, &buf, B.tile_count*TILE2 + nrhs, false); if (rc) return rc;
-    B.tiles = buf; B.tiles2 = buf + (size_t)B.NTA*(B.WB + 1)*TILE2;
-    B.rhs = buf + B.tile_count*TILE2; B.rhs2 = B.rhs + (size_t)B.NTA*TILE;
-    if (B.two) { if ((rc = dalloc(h, &B.dp, (size_t)B.n_pad))) return rc; } else B.dp = B.rhs;
-    if ((rc = dalloc(h, &h->chol_flags, (size_t)(B.NTA + B.NTB)*(2*(B.WB + 1) + 1)))) return rc;
-    if ((rc = dalloc(h, &h->linv, (size_t)(B.NTA + B.NTB)*TILE2))) return rc;
-  }
   // ---- variables
   DevVars& V = h->cur;
   V.np = (int)np; V.np_stride = pad32(np); V.nl = (int)npt; V.nl_stride = pad32(npt); V.nf = (int)nfl; V.nf_stride = pad32(nfl);
@@ -599,10 +608,10 @@ static int finalize_impl(dynoba_solver* h) {
     DevBlock& d = b.dev; d = DevBlock{};
     d.type = b.type; d.n = (int)n; d.stride = stride; d.sigma_dim = b.sigma_dim; d.robust_k = b.robust_k;
     int* di; double* dm; double* ds; int* dax = nullptr; int rc;
-    if ((rc = dalloc(h, &di, hidx.size()))) return rc; CK(h2d(di, hidx.data(), hidx.size()*4));
-    if ((rc = dalloc(h, &dm, hmeas.size()))) return rc; CK(h2d(dm, hmeas.data(), hmeas.size()*8));
-    if ((rc = dalloc(h, &ds, hsig.size()))) return rc; CK(h2d(ds, hsig.data(), hsig.size()*8));
-    if (b.has_aux) { if ((rc = dalloc(h, &dax, haux.size()))) return rc; CK(h2d(dax, haux.data(), haux.size()*4)); }
+    if ((rc = dalloc(h, &di, hidx.size(), false))) return rc; CK(h2d(di, hidx.data(), hidx.size()*4));
+    if ((rc = dalloc(h, &dm, hmeas.size(), false))) return rc; CK(h2d(dm, hmeas.data(), hmeas.size()*8));
+    if ((rc = dalloc(h, &ds, hsig.size(), false))) return rc; CK(h2d(ds, hsig.data(), hsig.size()*8));
+    if (b.has_aux) { if ((rc = dalloc(h, &dax, haux.size(), false))) return rc; CK(h2d(dax, haux.data(), haux.size()*4)); }
     d.idx = di; d.meas = dm; d.isig = ds; d.aux = dax;
     if ((rc = dalloc(h, &d.J, (size_t)ti.dim*ti.jcols*stride, false))) return rc;
     if ((rc = dalloc(h, &d.b, (size_t)ti.dim*stride))) return rc;
@@ -778,7 +787,7 @@ static int finalize_impl(dynoba_solver* h) {
 }
 
 // ------------------------------------------------------------------------------------------------ device steps
-__global__ void pack_fail_kernel(const int* fail, double* scalars) { scalars[3] = (double)(*fail); }
+__global__ void pack_fail_kernel(const int* fail, double* scalars) { scalars[3] = (double)(*fail); for (int i = 0; i < 4; i++) scalars[4 + i] = scalars[i]; }
 
 static int allreduce_dev(dynoba_solver* h, double* p, size_t n) {
   if (h->world <= 1) return DYNOBA_OK;
@@ -806,8 +815,11 @@ static int do_linearize(dynoba_solver* h) {
   h->linearized = true;
   return DYNOBA_OK;
 }
-// S, g_S at the current linearization
-static int build_reduced(dynoba_solver* h, double lambda) {
+// S, g_S at the current linearization.  Multi-GPU: every rank accumulates the contribution of its landmarks into the full
+// layout; the tiles of a cell are then summed at the rank that owns (factors) the cell -- a reduce per cell instead of an
+// all-reduce of the whole band -- and the small right-hand-side region is all-reduced.  full_sum: all-reduce everything
+// (parity hook dynoba_get_reduced_system; also the fallback when the host gave no reduce callback or there are no cells).
+static int build_reduced(dynoba_solver* h, double lambda, bool full_sum = false) {
   CK(cudaMemsetAsync(h->fail, 0, 4, h->stream));
   h->launches += launch_band_clear(h->band, lambda, h->rank == 0, h->stream);
   for (auto& b : h->blocks) {
@@ -818,12 +830,19 @@ static int build_reduced(dynoba_solver* h, double lambda) {
     }
   }
   h->launches += launch_schur_general(h->gen, h->band, lambda, h->fail, h->stream);
-  return allreduce_dev(h, h->band.tiles, h->band.tile_count*TILE2 + (size_t)(h->band.NTA + h->band.NTB)*TILE);
+  if (h->world <= 1) return DYNOBA_OK;
+  if (full_sum || !h->reduce || h->band.ncell == 0) return allreduce_dev(h, h->band.acc, h->band.acc_count);
+  for (auto& r : h->plan.reduce_ranges)
+    if (h->reduce(h->red_ctx, r.p, r.n, r.owner, (void*)h->stream) != 0) { h->err = "reduce callback failed"; return DYNOBA_ERR_COMM; }
+  return allreduce_dev(h, h->plan.rhs_region, h->plan.rhs_count);
 }
 // factor + solve + back-substitute; scalars[1] = linearised cost decrease
 static int solve_step(dynoba_solver* h, double lambda) {
-  h->launches += launch_band_cholesky(h->band, h->chol_flags, h->linv, h->fail, h->stream);
-  h->launches += launch_band_solve(h->band, h->linv, h->stream);
+  h->launches += launch_band_factor(h->plan, h->fail, h->stream);
+  const bool dist = h->world > 1 && h->reduce && h->band.ncell > 0;      // cells are owned by ranks (else: replicated solve)
+  if (dist && h->band.ncell >= 2) { int rc = allreduce_dev(h, h->plan.gq_base, h->plan.gq_count); if (rc) return rc; }
+  h->launches += launch_band_top(h->plan, h->fail, h->stream);
+  if (dist) { int rc = allreduce_dev(h, h->band.dp, (size_t)h->band.n_pad); if (rc) return rc; }
   int used = 0;
   for (auto& b : h->blocks) {
     if (b.pose_only) { h->launches += launch_pose_model(b.dev, h->band, h->partials + b.bs_off, h->stream); used = std::max(used, b.bs_off + (int)((b.n + 127)/128)); }
@@ -848,9 +867,11 @@ static int check_ready(dynoba_solver* h, bool need_supported) {
 }
 
 static int read_scalars(dynoba_solver* h, double* out4, bool reduce) {
+  // the rank-local sums stay in scalars[0..3]; the all-reduce runs on a scratch copy (scalars[4..7]) so that a value
+  // written once per outer iteration (scalars[0], the linearised error at delta = 0) is not summed again on every trial
   pack_fail_kernel<<<1, 1, 0, h->stream>>>(h->fail, h->scalars); h->launches++;
-  if (reduce) { int rc = allreduce_dev(h, h->scalars, 4); if (rc) return rc; }
-  CK(cudaMemcpyAsync(out4, h->scalars, 32, cudaMemcpyDeviceToHost, h->stream));
+  if (reduce) { int rc = allreduce_dev(h, h->scalars + 4, 4); if (rc) return rc; }
+  CK(cudaMemcpyAsync(out4, h->scalars + 4, 32, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return DYNOBA_OK;
 }
@@ -948,21 +969,23 @@ int dynoba_get_factor_errors(dynoba_handle h, int bi, double* err) {
 int dynoba_get_reduced_system(dynoba_handle h, double lambda, double* S, double* g) {
   int rc = check_ready(h, true); if (rc) return rc;
   if (!h->linearized) do_linearize(h);
-  rc = build_reduced(h, lambda); if (rc) return rc;
+  rc = build_reduced(h, lambda, true); if (rc) return rc;
   const DevBand& B = h->band;
-  std::vector<double> ht(B.tile_count*TILE2), hr((size_t)(B.NTA + B.NTB)*TILE);
-  CK(cudaMemcpyAsync(ht.data(), B.tiles, ht.size()*8, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(hr.data(), B.rhs, hr.size()*8, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<double> hacc(B.acc_count);
+  CK(cudaMemcpyAsync(hacc.data(), B.acc, hacc.size()*8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  DevBand HB = B;   // host view of the same layout
-  HB.tiles = ht.data(); HB.tiles2 = ht.data() + (size_t)B.NTA*(B.WB + 1)*TILE2; HB.rhs = hr.data(); HB.rhs2 = hr.data() + (size_t)B.NTA*TILE;
+  std::vector<BandProb> hch = h->plan.chains;            // host view of the same layout
+  for (auto& p : hch) {
+    p.tiles = hacc.data() + (p.tiles - B.acc); p.rhs = hacc.data() + (p.rhs - B.acc);
+    if (p.ff) p.ff = hacc.data() + (p.ff - B.acc); if (p.gf) p.gf = hacc.data() + (p.gf - B.acc);
+  }
+  DevBand HB = B; HB.chains = hch.data(); HB.cells = h->plan.cells.data();
   const int n = B.n; const int64_t np = n/6;
   std::vector<int32_t> inv(np); for (int64_t i = 0; i < np; i++) inv[h->pos[i]] = (int32_t)i;
   auto user = [&](int s) { return 6*inv[s/6] + s%6; };
   if (S) {
     std::fill(S, S + (size_t)n*n, 0.0);
-    for (int j = 0; j < n; j++) for (int i = j; i < n && i <= j + (B.WB + 1)*TILE; i++) {
-      const int I = i >> 5, Jt = j >> 5; if (I - Jt > B.WB) break;
+    for (int j = 0; j < n; j++) for (int i = j; i < n && i <= j + B.bw; i++) {
       const double v = *band_at(HB, i, j);
       S[(size_t)user(i)*n + user(j)] = v; S[(size_t)user(j)*n + user(i)] = v;
     }
@@ -991,7 +1014,7 @@ int dynoba_solve(dynoba_handle h, double lambda, double* delta) {
   ARG(delta, "null delta");
   if (!h->linearized) do_linearize(h);
   rc = build_reduced(h, lambda); if (rc) return rc;
-  solve_step(h, lambda);
+  rc = solve_step(h, lambda); if (rc) return rc;
   double s[4]; rc = read_scalars(h, s, true); if (rc) return rc;
   CK(cudaGetLastError());
   if (s[3] != 0.0) { h->err = "reduced system not positive definite"; return DYNOBA_ERR_INDETERMINATE; }
@@ -1066,7 +1089,7 @@ int dynoba_optimize(dynoba_handle h, const dynoba_lm_params* prm, dynoba_lm_stat
       tick(0); do_linearize(h); tick(1);
       for (;;) {   // tryLambda
         tick(2); rc = build_reduced(h, lambda); if (rc) return rc;
-        tick(3); solve_step(h, lambda);
+        tick(3); rc = solve_step(h, lambda); if (rc) return rc;
         tick(4);
         h->launches += launch_retract(h->cur, h->cand, h->band, h->dl_point, h->dl_flow, h->stream);
         eval_error(h, h->cand, 2);

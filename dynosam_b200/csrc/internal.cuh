@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 #include "factors.cuh"
 
 namespace dynoba {
@@ -37,38 +38,87 @@ struct DevBlock {
   double* num_scratch;  // numeric-Jacobian factor types: per-CTA partial sums of the column-parallel linearize kernel
 };
 
-// Band storage of the reduced (camera + object-motion) system, lower triangle, TILE x TILE tiles:
-// tile (I,J), J <= I <= J+WB at tiles[(J*(WB+1) + (I-J))*TILE2], element (r,c) at c*TILE + r.
+// Storage of the reduced (camera + object-motion) system S, lower triangle, TILE x TILE tiles (column-major inside a
+// tile: element (r, c) at c*TILE + r), and of its Cholesky factor, which overwrites it.
 //
-// Two-directional ("twisted") layout: the system may be stored as TWO band problems that share a middle separator M =
-// positions [split_lo, split_hi):  problem A = positions [0, split_hi) in natural order, problem B = positions
-// [split_lo, n_pad) REVERSED (local index n_pad-1-p).  A is eliminated forward, B is eliminated from the far end
-// backwards at the same time; both leave their Schur complement in M, which is summed and factored last.
-// An entry (i >= j) lives in A when i < split_hi, else in B at (n_pad-1-j, n_pad-1-i).
+// With pose-like variables in frame order S is banded (half-width bw <= WB tiles).  The time axis is cut into `ncell`
+// CELLS  [Qa] A -> M <- B [Qb]  (tools/cell_proto.py is the executable specification):
+//   * chain A = positions [a0, m0 + w) in natural order, chain B = positions [m0, b1) REVERSED (w = WB*TILE): two band
+//     problems that are eliminated at the same time towards the middle separator M = [m0, m0 + w), which both hold as
+//     their trailing columns and in which both leave their Schur complement;
+//   * a boundary separator Q between two cells is eliminated last.  The chain that starts next to it (B of the cell
+//     before, A of the cell after) carries WB extra dense tile rows per column, its "spike" Z = coupling to Q, which
+//     fills in along the chain, and the Q x Q block `ff`.  Original Q x Q entries live in the `ff` of the A chain after it.
+// ncell == 0: one plain band problem (chain 0), no separators.
+struct BandProb {
+  double* tiles;   // [NT][TPC][TILE2]   tile (K, t): t <= WB: band tile (K + t, K);  t = WB + 1 + r: spike tile (Q tile r, K)
+  double* rhs;     // [NT][TILE]         g, then y = L^-1 g, then x
+  double* ff;      // [WB][WB][TILE2]    Q x Q block (lower block triangle), spiked chains only
+  double* gf;      // [WB][TILE]         rhs of Q
+  double* linv;    // [Kend][TILE2]      inverses of the diagonal tiles of L
+  int* flags;      // done [NT*TPC] | pre [NT*TPC] | ydone [NT] | ffcnt [WB*WB]
+  int NT, Kend;    // columns [0, Kend) are factored; columns [Kend, NT) only receive their Schur complement
+  int TPC;         // tiles per column: WB + 1, + WB when spiked
+  int spiked;
+};
+struct CellGeom { int q0, a0, m0, b1, has_qa, has_qb; };   // scalar positions: Qa = [q0, a0) (empty when !has_qa), A interior
+                                                           // [a0, m0), M [m0, m0 + w), B interior [m0 + w, b1), Qb [b1, b1 + w)
+constexpr int MAX_CELLS = 16;
 struct DevBand {
   int n, n_pad, NT, WB, bw;
-  double* tiles;        // problem A (the whole system when two == 0): [NT_A*(WB+1)*TILE2]
-  double* rhs;          // [NT_A*32]   g_S, then y = L^-1 g_S, then x
-  size_t tile_count;    // tiles of A + tiles of B (one allocation, tiles2 follows tiles, then rhs, rhs2)
-  int two, split_lo, split_hi, NTA, NTB;
-  double* tiles2;       // problem B
-  double* rhs2;
-  double* dp;           // [n_pad] solution delta_p in solver order (== rhs when two == 0)
+  int ncell;
+  const BandProb* chains;   // [max(1, 2*ncell)]  chain 2c = A of cell c, 2c + 1 = B   (device array; host mirror for host reads)
+  const CellGeom* cells;    // [ncell]
+  double* acc; size_t acc_count;   // every buffer the Schur kernels accumulate into (tiles, ff, rhs, gf), contiguous
+  double* dp;               // [n_pad] solution delta_p in solver order
 };
-__host__ __device__ __forceinline__ size_t band_index_wb(int WB, int i, int j) {  // requires i >= j
-  const int I = i >> 5, Jt = j >> 5;
-  return ((size_t)Jt*(WB + 1) + (I - Jt))*TILE2 + (size_t)(j & 31)*TILE + (i & 31);
+// descriptor reads: read-only path on the device (the descriptors are written once by the host), plain loads on the host
+__host__ __device__ __forceinline__ int dld(const int& x) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(&x);
+#else
+  return x;
+#endif
 }
-__host__ __device__ __forceinline__ size_t band_index(const DevBand& B, int i, int j) { return band_index_wb(B.WB, i, j); }
+__host__ __device__ __forceinline__ double* dld(double* const& x) {
+#if defined(__CUDA_ARCH__)
+  return reinterpret_cast<double*>(__ldg(reinterpret_cast<const unsigned long long*>(&x)));
+#else
+  return x;
+#endif
+}
+__host__ __device__ __forceinline__ size_t tile_elem(int TPC, int K, int t, int r, int c) {
+  return ((size_t)K*TPC + t)*TILE2 + (size_t)c*TILE + r;
+}
+__host__ __device__ __forceinline__ int band_cell(const DevBand& B, int p) {    // cell whose [q0, b1) holds position p
+  int c = (int)((long long)p*B.ncell/B.n_pad);
+  while (c > 0 && p < dld(B.cells[c].q0)) c--;
+  while (c + 1 < B.ncell && p >= dld(B.cells[c + 1].q0)) c++;
+  return c;
+}
 // address of entry (i >= j) / of rhs element p of the reduced system
 __host__ __device__ __forceinline__ double* band_at(const DevBand& B, int i, int j) {
-  if (!B.two || i < B.split_hi) return B.tiles + band_index_wb(B.WB, i, j);
-  const int np1 = B.n_pad - 1;
-  return B.tiles2 + band_index_wb(B.WB, np1 - j, np1 - i);
+  if (B.ncell == 0) { const int I = i >> 5, J = j >> 5; return dld(B.chains[0].tiles) + tile_elem(B.WB + 1, J, I - J, i & 31, j & 31); }
+  const int c = band_cell(B, j), w = B.WB*TILE;
+  const int q0 = dld(B.cells[c].q0), a0 = dld(B.cells[c].a0), m0 = dld(B.cells[c].m0), b1 = dld(B.cells[c].b1);
+  if (j < a0) {
+    const int sj = j - q0;
+    if (i < a0) { const int si = i - q0; return dld(B.chains[2*c].ff) + ((size_t)(si >> 5)*B.WB + (sj >> 5))*TILE2 + (size_t)(sj & 31)*TILE + (si & 31); }
+    const int li = i - a0;
+    return dld(B.chains[2*c].tiles) + tile_elem(dld(B.chains[2*c].TPC), li >> 5, B.WB + 1 + (sj >> 5), sj & 31, li & 31);
+  }
+  if (i < m0 + w) { const int li = i - a0, lj = j - a0; return dld(B.chains[2*c].tiles) + tile_elem(dld(B.chains[2*c].TPC), lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31); }
+  if (i < b1) { const int li = b1 - 1 - j, lj = b1 - 1 - i; return dld(B.chains[2*c + 1].tiles) + tile_elem(dld(B.chains[2*c + 1].TPC), lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31); }
+  const int s = b1 + w - 1 - i, lc = b1 - 1 - j;
+  return dld(B.chains[2*c + 1].tiles) + tile_elem(dld(B.chains[2*c + 1].TPC), lc >> 5, B.WB + 1 + (s >> 5), s & 31, lc & 31);
 }
 __host__ __device__ __forceinline__ double* rhs_at(const DevBand& B, int p) {
-  if (!B.two || p < B.split_hi) return B.rhs + p;
-  return B.rhs2 + (B.n_pad - 1 - p);
+  if (B.ncell == 0) return dld(B.chains[0].rhs) + p;
+  const int c = band_cell(B, p), w = B.WB*TILE;
+  const int a0 = dld(B.cells[c].a0);
+  if (p < a0) return dld(B.chains[2*c].gf) + (p - dld(B.cells[c].q0));
+  if (p < dld(B.cells[c].m0) + w) return dld(B.chains[2*c].rhs) + (p - a0);
+  return dld(B.chains[2*c + 1].rhs) + (dld(B.cells[c].b1) - 1 - p);
 }
 
 // Landmark groups the per-landmark kernels do not cover (chains of points, landmarks spanning factor blocks):
@@ -123,8 +173,33 @@ int launch_backsub_general(const GeneralGroups& G, const DevBand& B, double lamb
                            double* partials, cudaStream_t s);
 int general_grid(int n_groups);
 int launch_pose_factors(const DevBlock& blk, const DevBand& B, cudaStream_t s);
-int launch_band_cholesky(const DevBand& B, int* flags /*[2*NT*(WB+1) + NT]*/, double* linv /*[NT*TILE2]*/, int* fail, cudaStream_t s);
-int launch_band_solve(const DevBand& B, const double* linv, cudaStream_t s);
+// ---- reduced solve (kernels_band.cu).  band_plan_layout decides the cell decomposition and the sizes of the three
+// device allocations; band_plan_bind places every buffer and uploads the problem descriptors.  The solve runs in three
+// stages so that the multi-GPU host can put its collectives between them (see api.cu: solve_step).
+struct BandPlan {
+  DevBand band;                       // device view (chains / cells point to device arrays)
+  int rank, world;                    // cells are dealt to ranks in contiguous runs; owner(c) = c*world/ncell
+  double outer_weight;                // relative length of the two unspiked end chains (0 = default)
+  int nchain, ncs, WBcs, TPCcs, WBgq, TPCgq, NTgq;
+  size_t n_doubles, n_ints, n_desc_bytes;        // sizes of the allocations band_plan_bind wants
+  size_t acc_count;                   // leading part of the double allocation that band_clear zeroes every trial
+  std::vector<BandProb> chains, cs, gq;          // host mirrors (device pointers inside)
+  std::vector<CellGeom> cells;
+  BandProb *d_chains, *d_cs, *d_gq;   // device descriptor arrays
+  std::vector<BandProb> d_local_chains_host; BandProb* d_local_chains; int n_local_chains;   // chains of this rank's cells
+  std::vector<BandProb> d_local_cs_host; BandProb* d_local_cs; int n_local_cs;
+  std::vector<int> local_cells; int* d_local_cell_ids;
+  double *gq_base; size_t gq_count;   // [tiles | rhs] of the boundary-separator system (all-reduced over ranks)
+  double *spike_scratch; int* flags_base; size_t flags_count;
+  // reduce ranges (multi-GPU): per cell, the accumulated tiles / ff of its two chains, owned by owner(c)
+  struct Range { double* p; size_t n; int owner; };
+  std::vector<Range> reduce_ranges; double* rhs_region; size_t rhs_count;
+};
+int band_plan_layout(BandPlan& P, int n, int bw, int ncell_request, int rank, int world);   // 0 = ok
+void band_plan_bind(BandPlan& P, double* dbase, int* ibase, void* desc_base, double* dp);
+void band_set_tuning(int band_ctas_per_chain);
+int launch_band_factor(const BandPlan& P, int* fail, cudaStream_t s);       // chains, cell separator systems, local part of the boundary system
+int launch_band_top(const BandPlan& P, int* fail, cudaStream_t s);          // boundary system factor + solve, back-substitution, dp of the local cells
 int launch_backsub_simple(const DevBlock& blk, const DevBand& B, double lambda, double* dl_point, int nl_stride,
                           double* dl_flow, int nf_stride, double* partials, cudaStream_t s);
 int backsub_grid(int n_groups);

@@ -3,20 +3,24 @@
 // Replaces GTSAM's multifrontal Cholesky on the COLAMD ordering ([GTSAM-ext]) for the
 // reduced system that is left after the landmarks are eliminated.  With pose-like variables ordered by frame
 // the system is banded (half-width = the co-visibility window, <= max track age), stored as 32x32 tiles.
-// tcgen05/UMMA has no fp64 path, so the tile kernels are fp64 FMA code.
+// tcgen05/UMMA has no fp64 path: tile updates run on mma.sync.m8n8k4.f64 (DMMA), triangular work on fp64 FMAs.
 //
-// Factorisation = one persistent DATAFLOW kernel (no grid-wide barriers), band_cholesky_dataflow_kernel_v3:
-//   * worker warps own one tile task at a time: every left-looking update T_IK -= L_IJ L_KJ^T (fp64 tensor-core MMA,
-//     operands prefetched with cp.async) as soon as the per-tile "done" flags of the operand tiles are released, then
-//     the TRSM against L_KK;
-//   * one spine CTA per band problem owns the sequential chain potrf(K,K) -> trsm(K+1,K) -> update+potrf(K+1,K+1) and
-//     the two tiles below it, in shared memory / registers, so the chain never waits on an L2 round trip.
-// band_cholesky_dataflow_kernel (4-warp spine, DYNOBA_SPINE=2) is the previous generation, kept for A/B runs.
-// Solve = explicit inverses of the diagonal tiles (one warp each, fully parallel); the forward substitution is folded
-// into the factorisation as one task per column, the backward sweep runs on a cluster of 8 CTAs per band problem.
+// A band Cholesky is one long dependency chain (potrf(K,K) -> trsm -> update -> potrf(K+1,K+1)), so the time axis is
+// cut into CELLS (nested dissection in time; internal.cuh, tools/cell_proto.py): every cell is two chains that are
+// eliminated towards a middle separator, chains next to a boundary separator carry their fill ("spike") with them,
+// and the separators are solved last.  All chains of all cells of this GPU run in ONE persistent dataflow kernel
+// (no grid-wide barriers), band_cholesky_dataflow_kernel_v3:
+//   * one spine CTA per chain owns the sequential chain and the two tiles below it, in shared memory / registers;
+//   * worker warps own one tile task at a time: every left-looking update T_IK -= L_IJ L_KJ^T as soon as the per-tile
+//     "done" flags of the operand tiles are released, then the TRSM against L_KK; the spike tiles Z and the separator
+//     block FF -= Z Z^T are more tasks of the same kind; one task per column folds the forward substitution in.
+// The same kernel then factors the cell separator systems [M | Qa | Qb] (dense, M eliminated) and the boundary system.
+// Solve = explicit inverses of the diagonal tiles (one warp each, fully parallel), backward sweep on a cluster of 8 CTAs
+// per chain.
 #include <algorithm>
 #include <cstdlib>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 #include <cooperative_groups.h>
 #include "internal.cuh"
@@ -25,8 +29,9 @@ namespace cg = cooperative_groups;
 
 namespace dynoba {
 
-constexpr int CH_WARPS = 4;
 constexpr int TS = 40, TSZ = TILE*TS;      // column stride of shared-memory tiles that feed MMA operand fragments: conflict-free loads
+constexpr int FF_CH = 16;                  // columns per FF accumulation task
+constexpr int MAX_PROBS = 2*MAX_CELLS;
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -43,57 +48,21 @@ __device__ __forceinline__ void wait_flag(const int* f, int lane) {
   }
   __syncwarp();
 }
-// optional timeline trace (DYNOBA_CHOL_TRACE): global timer at the moment a flag of problem 0 is released
-__device__ long long* g_trace = nullptr;
-__device__ int* g_trace_base = nullptr;
-__device__ long long g_trace_len = 0;
-__device__ __forceinline__ void trace_flag(int* f) {
-  if (g_trace) {
-    const long long off = f - g_trace_base;
-    if (off >= 0 && off < g_trace_len) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_trace[off] = t; }
+__device__ __forceinline__ void wait_flag_ge(const int* f, int v, int lane) {
+  if (lane == 0) {
+    int spins = 0;
+    while (ld_acquire(f) < v) { if (++spins > 8) __nanosleep(64); }
   }
+  __syncwarp();
 }
-__device__ long long* g_strace = nullptr;     // [NT][16] spine event times of problem 0 (DYNOBA_CHOL_TRACE)
-__device__ __forceinline__ void strace(int col, int slot, int lane) {
-  if (g_strace && blockIdx.x == 0 && lane == 0 && col >= 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_strace[(size_t)col*16 + slot] = t; }
-}
-__device__ __forceinline__ void set_flag(int* f, int lane) {
+__device__ __forceinline__ void set_flag_value(int* f, int v, int lane) {
   // the lanes' tile stores are ordered before lane 0's release by the warp barrier (release is cumulative).  No
   // __threadfence(): that is MEMBAR.SC.GPU + ERRBAR + CCTL.IVALL, microseconds per flag on the two-die part.
   __syncwarp();
-  if (lane == 0) { st_release(f, 1); trace_flag(f); }
+  if (lane == 0) st_release(f, v);
 }
+__device__ __forceinline__ void set_flag(int* f, int lane) { set_flag_value(f, 1, lane); }
 
-// warp-level Cholesky of a 32x32 tile held one row per lane; returns false when a pivot is not positive
-__device__ __forceinline__ bool warp_potrf(double (&row)[TILE], int lane) {
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < TILE; k++) {
-    const double d = __shfl_sync(0xffffffffu, row[k], k);
-    if (!(d > 0.0)) ok = false;
-    const double inv = rsqrt(d);
-    const double l = (lane == k) ? d*inv : row[k]*inv;   // column k of L, valid for lane >= k
-    row[k] = l;
-#pragma unroll
-    for (int c = k + 1; c < TILE; c++) {
-      const double lc = __shfl_sync(0xffffffffu, l, c);
-      row[c] -= l*lc;     // only the lower triangle (lane >= c) is meaningful
-    }
-  }
-  return ok;
-}
-
-// acc(row = lane, 32 cols) -= A(row = lane, 32 k) * B^T with B staged in shared memory as sB[k*32 + c] = B[c][k]
-__device__ __forceinline__ void tile_gemm_sub(double (&acc)[TILE], const double (&a)[TILE], const double* sB) {
-#pragma unroll
-  for (int k = 0; k < TILE; k++) {
-#pragma unroll
-    for (int c = 0; c < TILE; c += 2) {
-      const double2 b = *reinterpret_cast<const double2*>(sB + k*TILE + c);
-      acc[c] -= a[k]*b.x; acc[c + 1] -= a[k]*b.y;
-    }
-  }
-}
 // x(row = lane) <- x * L^-T with L staged as sL[k*32 + c] = L[c][k]; sinv[c] = 1 / L[c][c].  Blocked by 8 columns: the
 // serial chain is 8 x (mul, fma) per panel, the rank-8 update of the columns behind a panel has 24/16/8 independent chains.
 __device__ __forceinline__ void tile_trsm(double (&x)[TILE], const double* sL, const double* sinv) {
@@ -135,290 +104,6 @@ __device__ __forceinline__ void tile_stage(double* s, const double (&r)[TILE], i
   __syncwarp();
 }
 
-
-// Blocked variant for the spine: 4 panels of 8 columns.  Inside a panel the right-looking updates only touch the
-// panel's columns (<= 7 shuffles per step); the rank-8 update of the trailing columns reads the panel from
-// shared memory (sP[row*8 + j], 4 x LDS.128 per trailing column) instead of 8 shuffles per column.
-__device__ __forceinline__ bool warp_potrf_blocked(double (&row)[TILE], int lane, double* sP) {
-  bool ok = true;
-#pragma unroll
-  for (int p = 0; p < 4; p++) {
-#pragma unroll
-    for (int kk = 0; kk < 8; kk++) {
-      const int k = 8*p + kk;
-      const double d = __shfl_sync(0xffffffffu, row[k], k);
-      if (!(d > 0.0)) ok = false;
-      const double inv = rsqrt(d);
-      const double l = (lane == k) ? d*inv : row[k]*inv;
-      row[k] = l;
-#pragma unroll
-      for (int c = k + 1; c < 8*p + 8; c++) {
-        const double lc = __shfl_sync(0xffffffffu, l, c);
-        row[c] -= l*lc;
-      }
-    }
-    if (p < 3) {
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sP + lane*8 + j) = make_double2(row[8*p + j], row[8*p + j + 1]);
-      __syncwarp();
-#pragma unroll
-      for (int c = 8*p + 8; c < TILE; c++) {
-        double acc = row[c];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          const double2 b = *reinterpret_cast<const double2*>(sP + c*8 + j);
-          acc -= row[8*p + j]*b.x; acc -= row[8*p + j + 1]*b.y;
-        }
-        row[c] = acc;
-      }
-    }
-  }
-  return ok;
-}
-constexpr int LT_STRIDE = 34;   // padded row stride of the row-major copy of L_KK used by the spine TRSM
-// x(row = lane) <- x * L^-T with L staged row-major: sLt[c*LT_STRIDE + k] = L[c][k]; sinv[c] = 1 / L[c][c]
-__device__ __forceinline__ void tile_trsm_rm(double (&x)[TILE], const double* sLt, const double* sinv) {
-#pragma unroll
-  for (int c = 0; c < TILE; c++) {
-    double s = x[c];
-#pragma unroll
-    for (int k = 0; k + 1 < c; k += 2) {
-      const double2 l = *reinterpret_cast<const double2*>(sLt + c*LT_STRIDE + k);
-      s -= x[k]*l.x; s -= x[k + 1]*l.y;
-    }
-    if (c & 1) s -= x[c - 1]*sLt[c*LT_STRIDE + c - 1];
-    x[c] = s*sinv[c];
-  }
-}
-// acc[j] (16 columns c0..c0+15 of row = lane) -= sum_k a[k] * B[c0+j][k], B staged as sB[k*32 + c]
-__device__ __forceinline__ void tile_gemm_sub_half(double (&acc)[16], const double (&a)[TILE], const double* sB, int c0) {
-#pragma unroll
-  for (int k = 0; k < TILE; k++) {
-#pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-      const double2 b = *reinterpret_cast<const double2*>(sB + k*TILE + c0 + j);
-      acc[j] -= a[k]*b.x; acc[j + 1] -= a[k]*b.y;
-    }
-  }
-}
-__device__ __forceinline__ void named_bar(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void named_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
-}
-
-// Panel-fused spine: warp 0 factors the diagonal tile in 4 panels of 8 columns and PUBLISHES each finished panel
-// (sPan[p][row*8 + j] = L[row][8p + j], sIv[k] = 1 / L[k][k]) with a non-blocking barrier arrival; the TRSM warps
-// follow one panel behind (warp_trsm_follow), so the triangular solves of the sub-diagonal tiles overlap the potrf
-// instead of starting after it.
-__device__ __forceinline__ bool warp_potrf_publish(double (&row)[TILE], int lane, double* sPan, double* sIv) {
-  bool ok = true;
-#pragma unroll
-  for (int p = 0; p < 4; p++) {
-    double* sP = sPan + p*256;
-#pragma unroll
-    for (int kk = 0; kk < 8; kk++) {
-      const int k = 8*p + kk;
-      const double d = __shfl_sync(0xffffffffu, row[k], k);
-      if (!(d > 0.0)) ok = false;
-      const double inv = rsqrt(d);
-      const double l = (lane == k) ? d*inv : row[k]*inv;
-      row[k] = l;
-      if (lane == k) sIv[k] = inv;
-#pragma unroll
-      for (int c = k + 1; c < 8*p + 8; c++) {
-        const double lc = __shfl_sync(0xffffffffu, l, c);
-        row[c] -= l*lc;
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sP + lane*8 + j) = make_double2(row[8*p + j], row[8*p + j + 1]);
-    __syncwarp();
-    named_arrive(4 + p, 96);
-    if (p < 3) {
-#pragma unroll
-      for (int c = 8*p + 8; c < TILE; c++) {
-        double acc = row[c];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          const double2 b = *reinterpret_cast<const double2*>(sP + c*8 + j);
-          acc -= row[8*p + j]*b.x; acc -= row[8*p + j + 1]*b.y;
-        }
-        row[c] = acc;
-      }
-    }
-  }
-  return ok;
-}
-// x(row = lane) <- x * L^-T, consuming the panels warp 0 publishes
-__device__ __forceinline__ void warp_trsm_follow(double (&x)[TILE], const double* sPan, const double* sIv) {
-#pragma unroll
-  for (int p = 0; p < 4; p++) {
-    const double* sP = sPan + p*256;
-    named_bar(4 + p, 96);
-#pragma unroll
-    for (int kk = 0; kk < 8; kk++) {
-      const int k = 8*p + kk;
-      const double l = x[k]*sIv[k];
-      x[k] = l;
-#pragma unroll
-      for (int c = k + 1; c < 8*p + 8; c++) x[c] -= l*sP[c*8 + kk];
-    }
-    if (p < 3) {
-#pragma unroll
-      for (int c = 8*p + 8; c < TILE; c++) {
-        double acc = x[c];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          const double2 b = *reinterpret_cast<const double2*>(sP + c*8 + j);
-          acc -= x[8*p + j]*b.x; acc -= x[8*p + j + 1]*b.y;
-        }
-        x[c] = acc;
-      }
-    }
-  }
-}
-
-__device__ long long g_spine_dbg[16];
-#define TS(i) do { const long long t_ = clock64(); if (lane == 0) dbgacc[i] += t_ - tlast; tlast = t_; } while (0)
-
-// One band problem handed to the factorisation kernel: columns [Kbeg, Kend) are factored; tiles in columns >= Kend
-// only receive the updates from the factored columns (their Schur complement), updates from columns < Kbeg are
-// assumed applied already (second phase of the two-directional scheme).
-struct CholProb { double* tiles; double* rhs; int NT, Kbeg, Kend; int* done; int* pre; int* ydone; };
-struct CholJob { CholProb p[2]; int np, WB, skew; };
-
-__device__ __forceinline__ void chol_worker(const struct CholJob& job, int wid, int nworkers, double* sb, double* sinv, double* stage, int lane, int dd0_lag);
-
-// Tile roles (dd = I - K):
-//   dd == 0, 1 : workers apply the updates from columns J <= K-2 ("pre"), the spine applies J = K-1 and finishes
-//   dd == 2    : workers apply J <= K-1 ("pre"), the spine does the TRSM
-//   dd >= 3    : workers apply J <= K-1 and do the TRSM once done(K,K) is released
-// plus one "rhs" task per column that folds the forward substitution y_K = L_KK^-1 (g_K - sum_J L_KJ y_J) in.
-// flags: done[o], pre[o] for tile o = K*(WB+1) + dd;  ydone[K]
-__global__ void __launch_bounds__(CH_WARPS*32)
-band_cholesky_dataflow_kernel(CholJob job, int* __restrict__ fail) {
-  extern __shared__ __align__(16) double chol_smem[];   // [CH_WARPS + 1][TILE2] + [CH_WARPS][32] (+ padding that pins CTAs/SM)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int WB = job.WB, W1 = WB + 1;
-  double* sb = chol_smem + (size_t)warp*TILE2;
-  double* sinv = chol_smem + (size_t)(CH_WARPS + 1)*TILE2 + warp*TILE;
-
-  if ((int)blockIdx.x < job.np) {
-    // ------------------------------------------------------------------ spine CTA (4 warps, block-wide barriers)
-    //   warp 0: potrf(K,K);  warp 1: TRSM (K+1,K);  warp 2: TRSM (K+2,K);  then all four warps split the two
-    //   tile updates T(K+1,K+1) -= L(K+1,K) L(K+1,K)^T and T(K+2,K+1) -= L(K+2,K) L(K+1,K)^T by column halves.
-    const CholProb P = job.p[blockIdx.x];
-    int* done = P.done; int* pre = P.pre;
-    const int NT = P.NT;
-    double* sLt  = chol_smem;                       // [32*LT_STRIDE] row-major L_KK
-    double* sX1  = chol_smem + 1152;                // [1024] L(K+1,K), sX1[k*32 + r]
-    double* sX2  = sX1 + TILE2;                     // [1024] L(K+2,K)
-    double* sD   = sX2 + TILE2;                     // [1024] next diagonal tile hand-off
-    double* sXn  = sD + TILE2;                      // [1024] next x1 hand-off
-    double* sP   = sXn + TILE2;                     // [256]  potrf panel
-    double* sIv  = sP + 256;                        // [32]   1 / diag(L_KK)
-    double r[TILE];                                 // warp 0: diagonal tile row; warp 1: x1 row; warp 2: x2 row
-    long long dbgacc[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long tlast = clock64();
-    if (P.Kbeg >= P.Kend) return;
-    if (warp == 0) { wait_flag(pre + (size_t)P.Kbeg*W1, lane); tile_load(P.tiles + (size_t)P.Kbeg*W1*TILE2, r, lane); }
-    if (warp == 1 && P.Kbeg + 1 < NT) { wait_flag(pre + (size_t)P.Kbeg*W1 + 1, lane); tile_load(P.tiles + ((size_t)P.Kbeg*W1 + 1)*TILE2, r, lane); }
-    double* sPan = sLt;                             // [4][256] published potrf panels (the row-major L_KK copy is gone)
-    for (int K = P.Kbeg; K < P.Kend; K++) {
-      const size_t oD = (size_t)K*W1;
-      const bool last = K + 1 >= NT;
-      const bool has2 = (K + 2 < NT) && (WB >= 2), hasn = (K + 2 < NT);
-      double h[16];
-      if (warp == 0) {
-        TS(11);
-        if (!warp_potrf_publish(r, lane, sPan, sIv) && lane == 0) atomicOr(fail, 2);
-        TS(0);
-        tile_store(P.tiles + oD*TILE2, r, lane);
-        set_flag(done + oD, lane);
-        TS(1);
-        if (!last) {
-          wait_flag(pre + oD + W1, lane);
-          const double* t = P.tiles + (oD + W1)*TILE2;
-#pragma unroll
-          for (int j = 0; j < 16; j++) h[j] = __ldcg(t + (16 + j)*TILE + lane);
-        }
-        TS(2);
-      } else if (!last && warp == 1) {
-        warp_trsm_follow(r, sPan, sIv);
-        tile_store(P.tiles + (oD + 1)*TILE2, r, lane);
-        tile_stage(sX1, r, lane);
-        set_flag(done + oD + 1, lane);
-      } else if (!last && warp == 2) {
-        if (has2) { wait_flag(pre + oD + 2, lane); tile_load(P.tiles + (oD + 2)*TILE2, r, lane); }
-        else {
-#pragma unroll
-          for (int c = 0; c < TILE; c++) r[c] = 0.0;
-        }
-        warp_trsm_follow(r, sPan, sIv);                 // always follows: the panel barriers count three warps
-        if (has2) {
-          tile_store(P.tiles + (oD + 2)*TILE2, r, lane);
-          tile_stage(sX2, r, lane);
-          set_flag(done + oD + 2, lane);
-        }
-      } else if (!last) {
-        wait_flag(pre + oD + W1, lane);
-        const double* t = P.tiles + (oD + W1)*TILE2;
-#pragma unroll
-        for (int j = 0; j < 16; j++) h[j] = __ldcg(t + j*TILE + lane);
-      }
-      if (last) break;
-      named_bar(2, 128);
-      if (warp == 0) TS(4);
-      if (warp == 0 || warp == 3) {
-        const int c0 = warp == 0 ? 16 : 0;
-        double a[TILE];
-#pragma unroll
-        for (int k = 0; k < TILE; k++) a[k] = sX1[k*TILE + lane];
-        tile_gemm_sub_half(h, a, sX1, c0);
-#pragma unroll
-        for (int j = 0; j < 16; j++) sD[(c0 + j)*TILE + lane] = h[j];
-      } else if (hasn) {
-        const int c0 = warp == 1 ? 16 : 0;
-        wait_flag(pre + oD + W1 + 1, lane);
-        const double* t = P.tiles + (oD + W1 + 1)*TILE2;
-#pragma unroll
-        for (int j = 0; j < 16; j++) h[j] = __ldcg(t + (c0 + j)*TILE + lane);
-        if (has2) {
-          double a[TILE];
-#pragma unroll
-          for (int k = 0; k < TILE; k++) a[k] = sX2[k*TILE + lane];
-          tile_gemm_sub_half(h, a, sX1, c0);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j++) sXn[(c0 + j)*TILE + lane] = h[j];
-      }
-      if (warp == 0) TS(5);
-      named_bar(3, 128);
-      if (warp == 0) {
-#pragma unroll
-        for (int c = 0; c < TILE; c++) r[c] = sD[c*TILE + lane];
-        TS(6);
-      } else if (warp == 1 && hasn) {
-#pragma unroll
-        for (int c = 0; c < TILE; c++) r[c] = sXn[c*TILE + lane];
-      }
-    }
-    // columns >= Kend are not factored here: hand the two partially updated tiles of column Kend back
-    if (P.Kend < NT) {
-      if (warp == 0) tile_store(P.tiles + (size_t)P.Kend*W1*TILE2, r, lane);
-      if (warp == 1 && P.Kend + 1 < NT) tile_store(P.tiles + ((size_t)P.Kend*W1 + 1)*TILE2, r, lane);
-    }
-    if (blockIdx.x == 0 && warp == 0 && lane == 0) for (int i = 0; i < 12; i++) g_spine_dbg[i] = dbgacc[i];
-    return;
-  }
-  // -------------------------------------------------------------------- workers
-  chol_worker(job, ((int)blockIdx.x - job.np)*CH_WARPS + warp, ((int)gridDim.x - job.np)*CH_WARPS, sb, sinv, nullptr, lane, 2);
-}
-
-// Worker warp `wid` of `nworkers`: tile tasks in column-major order (see the role table above the kernels).
 // ---- fp64 tensor-core tile update for the workers: T(32x32) -= LI LK^T as 128 x mma.m8n8k4 (DMMA).  The FMA version
 // reads its B operand from shared memory (one LDS.128 per two FMAs) and saturates the SM's shared-memory pipe with four
 // warps at about half the fp64 rate; the MMA fragments live in registers, so the inner loop has no memory operation.
@@ -483,37 +168,107 @@ __device__ __forceinline__ bool flags_ready(const int* fa, const int* fb, int la
   return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
 
-// dd0_lag: the diagonal tile (dd == 0) receives the worker updates from columns J <= K - dd0_lag only (the spine owns the rest).
-// stage: per-warp [2][2][TSZ] shared-memory operand buffers for the asynchronous prefetch of the next update, or nullptr.
-__device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nworkers, double* sb, double* sinv, double* stage, int lane, int dd0_lag) {
-  const int WB = job.WB, W1 = WB + 1;
-  const int W2 = W1 + 1;                                 // tile tasks + the rhs task of the column
-  int ncols = 0;
-  for (int q = 0; q < job.np; q++) ncols = max(ncols, job.p[q].NT - job.p[q].Kbeg);
-  // Task order: skewed wavefronts s = skew*K + dd instead of column-major.  A worker processes its tasks in order and
-  // blocks on operands, so a task's lead over the spine has to cover its own serial work; the (WB - dd) updates of a tile
-  // near the diagonal need more lead than the short tasks far from it.  With the skew the tiles of one column are handed
-  // out over WB/skew columns, longest first.  Every operand of task (K, dd) has a strictly smaller s, so in-order
-  // blocking cannot deadlock.  (Measured on C5: skew 2 is 1-2 % faster than column-major or a near/far split of the
-  // worker pool; the column period is set by the row-chain hop latency, see DESIGN.md.)
-  const int skew = job.skew, nj = (W2 + skew - 1)/skew;
+// One launch of the factorisation kernel: np band problems of the same tile bandwidth WB.
+struct CholJob { const BandProb* p; int np, WB, skew, any_spiked, ncols, band_ctas; };   // band_ctas: worker CTAs of pool A
+__device__ __forceinline__ int* flag_done(const BandProb& P) { return P.flags; }
+__device__ __forceinline__ int* flag_pre(const BandProb& P) { return P.flags + (size_t)P.NT*P.TPC; }
+__device__ __forceinline__ int* flag_ydone(const BandProb& P) { return P.flags + (size_t)2*P.NT*P.TPC; }
+__device__ __forceinline__ int* flag_ffcnt(const BandProb& P) { return P.flags + (size_t)2*P.NT*P.TPC + P.NT; }
+
+// acc -= sum_{J = Jlo..Jhi} A_J B_J^T  with A_J = tile (J, A0 - A1*J), B_J = tile (J, B0 - B1*J) of problem P (same: A == B);
+// waits for the operand tiles' done flags.  stage: per-warp [2][2][TSZ] shared-memory operand buffers -- while update J
+// runs on the tensor pipe, the operand tiles of J+1 (when their flags are already up) stream into the other stage with
+// cp.async, so the L2 latency leaves the critical path.
+__device__ __forceinline__ void accumulate_updates(const BandProb& P, double (&acc)[TILE], int Jlo, int Jhi, int A0, int A1, int B0, int B1,
+                                                   bool same, double* stage, int lane) {
+  const int* done = flag_done(P);
+  const int TPC = P.TPC;
+  int st = 0; bool have = false;
+  for (int J = Jlo; J <= Jhi; J++) {
+    const size_t oA = (size_t)J*TPC + (A0 - A1*J), oB = (size_t)J*TPC + (B0 - B1*J);
+    if (!have) {
+      wait_flag(done + oB, lane);
+      if (!same) wait_flag(done + oA, lane);
+      tile_prefetch(stage + (size_t)(st*2 + 1)*TSZ, P.tiles + oB*TILE2, lane);
+      if (!same) tile_prefetch(stage + (size_t)(st*2)*TSZ, P.tiles + oA*TILE2, lane);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    bool next = false;
+    if (J + 1 <= Jhi) {
+      const size_t nA = (size_t)(J + 1)*TPC + (A0 - A1*(J + 1)), nB = (size_t)(J + 1)*TPC + (B0 - B1*(J + 1));
+      next = flags_ready(done + nB, done + (same ? nB : nA), lane);
+      if (next) {
+        tile_prefetch(stage + (size_t)((st ^ 1)*2 + 1)*TSZ, P.tiles + nB*TILE2, lane);
+        if (!same) tile_prefetch(stage + (size_t)((st ^ 1)*2)*TSZ, P.tiles + nA*TILE2, lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    }
+    if (next) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    double fb[TILE];
+    sfrag_load(stage + (size_t)(st*2 + 1)*TSZ, fb, lane);
+    if (same) frag_gemm_sub(acc, fb, fb);
+    else {
+      double fa[TILE];
+      sfrag_load(stage + (size_t)(st*2)*TSZ, fa, lane);
+      frag_gemm_sub(acc, fa, fb);
+    }
+    __syncwarp();            // the stage is free for the prefetch after next
+    st ^= 1; have = next;
+  }
+}
+
+// Band worker warp `wid` of `nworkers` (pool A).  Tasks of column K of a problem (slot dd):
+//   dd <= WB        band tile (K + dd, K).  dd == 0, 1: workers apply the updates from columns J <= K-3 / K-2 ("pre"), the
+//                   spine applies the rest and finishes; dd == 2: workers apply J <= K-1 ("pre"), the spine does the TRSM;
+//                   dd >= 3: workers apply J <= K-1 and do the TRSM once done(K,K) is released
+//   dd == WB + 1    rhs task: folds the forward substitution y_K = L_KK^-1 (g_K - sum_J L_KJ y_J) in
+// Task order: skewed wavefronts s = skew*K + dd instead of column-major.  A worker processes its tasks in order and
+// blocks on operands, so a task's lead over the spine has to cover its own serial work; the (WB - dd) updates of a tile
+// near the diagonal need more lead than the short tasks far from it.  Every operand of a task has a strictly smaller s,
+// so in-order blocking cannot deadlock (all CTAs are co-resident: cooperative launch).
+__device__ __forceinline__ void tile_finish_trsm(const BandProb& P, double (&acc)[TILE], int K, double* tp, int* doneflag, double* sb, double* sinv, int lane) {
+  // accumulator fragments -> one row per lane, through the warp's shared-memory tile
+  __syncwarp();
+  cfrag_store(sb, acc, lane);
+  __syncwarp();
+#pragma unroll
+  for (int cc = 0; cc < TILE; cc++) acc[cc] = sb[cc*TILE + lane];
+  const size_t oD = (size_t)K*P.TPC;
+  wait_flag(flag_done(P) + oD, lane);
+  __syncwarp();
+#pragma unroll
+  for (int cc = 0; cc < TILE; cc++) sb[cc*TILE + lane] = __ldcg(P.tiles + oD*TILE2 + cc*TILE + lane);
+  __syncwarp();
+  sinv[lane] = 1.0/sb[lane*TILE + lane];
+  __syncwarp();
+  tile_trsm(acc, sb, sinv);
+  tile_store(tp, acc, lane);
+  set_flag(doneflag, lane);
+}
+
+__device__ __forceinline__ void band_worker(const CholJob& job, int wid, int nworkers, double* sb, double* sinv, double* stage, int lane) {
+  const int WB = job.WB, W1 = WB + 1, R = W1 + 1;          // task slots per column
+  const int ncols = job.ncols;
+  const int skew = job.skew, nj = (R + skew - 1)/skew;
   const long long per_s = (long long)job.np*nj;
-  const long long ntasks = ((long long)skew*ncols + W2)*per_s;
+  const long long ntasks = ((long long)skew*ncols + R)*per_s;
   for (long long t = wid; t < ntasks; t += nworkers) {
     const int sidx = (int)(t/per_s); const int u = (int)(t - (long long)sidx*per_s);
     const int q = u/nj, j = u - q*nj;
-    const int dd = sidx%skew + skew*j, c = sidx/skew - j;
-    if (dd > W1 || c < 0 || c >= ncols) continue;
-    const CholProb P = job.p[q];
-    int* done = P.done; int* pre = P.pre; int* ydone = P.ydone;
-    const int NT = P.NT, K = P.Kbeg + c, I = K + dd;
+    const int dd = sidx%skew + skew*j, K = sidx/skew - j;
+    if (dd >= R || K < 0 || K >= ncols) continue;
+    const BandProb P = job.p[q];
+    const int NT = P.NT, TPC = P.TPC;
     if (K >= NT) continue;
+    int* done = flag_done(P); int* pre = flag_pre(P);
     if (dd == W1) {
-      // ---- rhs task: y_K = L_KK^-1 (g_K - sum_{J<K} L_KJ y_J); rows >= Kend only collect the factored columns' part
+      // ---- rhs task; rows >= Kend only collect the factored columns' part
+      int* ydone = flag_ydone(P);
       double v = P.rhs[(size_t)K*TILE + lane];
       const int Jend = min(K, P.Kend);
-      for (int J = max(P.Kbeg, K - WB); J < Jend; J++) {
-        const size_t oK = (size_t)J*W1 + (K - J);
+      for (int J = max(0, K - WB); J < Jend; J++) {
+        const size_t oK = (size_t)J*TPC + (K - J);
         wait_flag(done + oK, lane);
         double a[TILE];
         tile_load(P.tiles + oK*TILE2, a, lane);
@@ -523,9 +278,9 @@ __device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nwo
         for (int k = 0; k < TILE; k++) v -= a[k]*__shfl_sync(0xffffffffu, yj, k);
       }
       if (K >= P.Kend) { P.rhs[(size_t)K*TILE + lane] = v; continue; }
-      wait_flag(done + (size_t)K*W1, lane);
+      wait_flag(done + (size_t)K*TPC, lane);
       double l[TILE];
-      tile_load(P.tiles + (size_t)K*W1*TILE2, l, lane);
+      tile_load(P.tiles + (size_t)K*TPC*TILE2, l, lane);
       double y = 0.0, mydiag = 1.0;
 #pragma unroll
       for (int cc = 0; cc < TILE; cc++) if (lane == cc) mydiag = l[cc];
@@ -540,92 +295,69 @@ __device__ __forceinline__ void chol_worker(const CholJob& job, int wid, int nwo
       set_flag(ydone + K, lane);
       continue;
     }
+    const int I = K + dd;
     if (I >= NT) continue;
-    const size_t o = (size_t)K*W1 + dd;
     double acc[TILE];                       // accumulator fragments while the updates run, one row per lane afterwards
+    const size_t o = (size_t)K*TPC + dd;
     double* tp = P.tiles + o*TILE2;
     cfrag_load(tp, acc, lane);
-    const int Jlo = max(P.Kbeg, I - WB);
-    // the spine finishes the tiles of columns <= Kend itself: it owns the last (dd0_lag - 1) updates of a diagonal tile and
-    // the last update of a first sub-diagonal tile
-    const int Jhi = min(dd == 0 ? (K <= P.Kend ? K - dd0_lag : K - 1) : (dd == 1 ? K - 2 : K - 1), P.Kend - 1);
-    if (stage) {
-      // software pipeline: while update J runs on the tensor pipe, the operand tiles of J+1 (when their flags are already
-      // up) stream into the other shared-memory stage with cp.async -- the L2 latency leaves the critical path
-      int st = 0; bool have = false;
-      for (int J = Jlo; J <= Jhi; J++) {
-        const size_t oI = (size_t)J*W1 + (I - J), oK = (size_t)J*W1 + (K - J);
-        if (!have) {
-          wait_flag(done + oK, lane);
-          if (dd != 0) wait_flag(done + oI, lane);
-          tile_prefetch(stage + (size_t)(st*2 + 1)*TSZ, P.tiles + oK*TILE2, lane);
-          if (dd != 0) tile_prefetch(stage + (size_t)(st*2)*TSZ, P.tiles + oI*TILE2, lane);
-          asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        bool next = false;
-        if (J + 1 <= Jhi) {
-          const size_t nI = (size_t)(J + 1)*W1 + (I - J - 1), nK = (size_t)(J + 1)*W1 + (K - J - 1);
-          next = flags_ready(done + nK, done + (dd != 0 ? nI : nK), lane);
-          if (next) {
-            tile_prefetch(stage + (size_t)((st ^ 1)*2 + 1)*TSZ, P.tiles + nK*TILE2, lane);
-            if (dd != 0) tile_prefetch(stage + (size_t)((st ^ 1)*2)*TSZ, P.tiles + nI*TILE2, lane);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-          }
-        }
-        if (next) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        double fb[TILE];
-        sfrag_load(stage + (size_t)(st*2 + 1)*TSZ, fb, lane);
-        if (dd == 0) frag_gemm_sub(acc, fb, fb);
-        else {
-          double fa[TILE];
-          sfrag_load(stage + (size_t)(st*2)*TSZ, fa, lane);
-          frag_gemm_sub(acc, fa, fb);
-        }
-        __syncwarp();            // the stage is free for the prefetch after next
-        st ^= 1; have = next;
-      }
-    } else
-    for (int J = Jlo; J <= Jhi; J++) {
-      const size_t oI = (size_t)J*W1 + (I - J), oK = (size_t)J*W1 + (K - J);
-      double fb[TILE];
-      wait_flag(done + oK, lane);
-      frag_load(P.tiles + oK*TILE2, fb, lane);
-      if (dd == 0) frag_gemm_sub(acc, fb, fb);
-      else {
-        double fa[TILE];
-        wait_flag(done + oI, lane);
-        frag_load(P.tiles + oI*TILE2, fa, lane);
-        frag_gemm_sub(acc, fa, fb);
-      }
-    }
+    // the spine finishes the tiles of columns <= Kend itself: it owns the last two updates of a diagonal tile and the last
+    // update of a first sub-diagonal tile
+    const int Jhi = min(dd == 0 ? (K <= P.Kend ? K - 3 : K - 1) : (dd == 1 ? K - 2 : K - 1), P.Kend - 1);
+    accumulate_updates(P, acc, max(0, I - WB), Jhi, I, 1, K, 1, dd == 0, stage, lane);
     if (dd <= 2 || K >= P.Kend) {
       cfrag_store(tp, acc, lane);
       set_flag(pre + o, lane);
-    } else {
-      // accumulator fragments -> one row per lane, through the warp's shared-memory tile
-      __syncwarp();
-      cfrag_store(sb, acc, lane);
-      __syncwarp();
-#pragma unroll
-      for (int cc = 0; cc < TILE; cc++) acc[cc] = sb[cc*TILE + lane];
-      const size_t oD = (size_t)K*W1;
-      wait_flag(done + oD, lane);
-      __syncwarp();
-#pragma unroll
-      for (int cc = 0; cc < TILE; cc++) sb[cc*TILE + lane] = __ldcg(P.tiles + oD*TILE2 + cc*TILE + lane);
-      __syncwarp();
-      sinv[lane] = 1.0/sb[lane*TILE + lane];
-      __syncwarp();
-      tile_trsm(acc, sb, sinv);
-      tile_store(tp, acc, lane);
-      set_flag(done + o, lane);
+    } else tile_finish_trsm(P, acc, K, tp, done + o, sb, sinv, lane);
+  }
+}
+
+// Spike worker warp (pool B; only launched when a chain of the job is spiked).  Its tasks never feed the spine, so they
+// live in their own pool: a 30-update spike task in front of a band task in the same in-order queue would stall the
+// chain.  Column-major order; per column K of a spiked chain
+//   slots [0, WB)         Z_r(K) = (Z_r(K) - sum_J Z_r(J) L(K,J)^T) L_KK^-T
+//   slots [WB, WB + NFF)  once per FF_CH columns: FF(r, r2) -= sum_{J in chunk} Z_r(J) Z_r2(J)^T, chunks chained by a counter
+// Operands are tiles of pool A / the spine (never waiting on pool B) or earlier tasks of this order: no deadlock.
+__device__ __forceinline__ void spike_worker(const CholJob& job, int wid, int nworkers, double* sb, double* sinv, double* stage, int lane) {
+  const int WB = job.WB, W1 = WB + 1, NFF = WB*(WB + 1)/2, R = WB + NFF;
+  const long long per_col = (long long)job.np*R;
+  const long long ntasks = (long long)job.ncols*per_col;
+  for (long long t = wid; t < ntasks; t += nworkers) {
+    const int K = (int)(t/per_col); const int u = (int)(t - (long long)K*per_col);
+    const int q = u/R, slot = u - q*R;
+    const BandProb P = job.p[q];
+    if (!P.spiked || K >= P.NT) continue;
+    const int TPC = P.TPC;
+    double acc[TILE];
+    if (slot >= WB) {
+      if (K >= P.Kend || !(((K + 1) % FF_CH) == 0 || K == P.Kend - 1)) continue;
+      const int e = slot - WB;
+      int r = (int)((sqrtf(8.0f*(float)e + 1.0f) - 1.0f)*0.5f);
+      while (r*(r + 1)/2 > e) r--;
+      while ((r + 1)*(r + 2)/2 <= e) r++;
+      const int r2 = e - r*(r + 1)/2, chunk = K/FF_CH;
+      int* cnt = flag_ffcnt(P) + r*WB + r2;
+      double* tp = P.ff + ((size_t)r*WB + r2)*TILE2;
+      wait_flag_ge(cnt, chunk, lane);
+      cfrag_load(tp, acc, lane);
+      accumulate_updates(P, acc, chunk*FF_CH, K, W1 + r, 0, W1 + r2, 0, r == r2, stage, lane);
+      cfrag_store(tp, acc, lane);
+      set_flag_value(cnt, chunk + 1, lane);
+      continue;
     }
+    const size_t o = (size_t)K*TPC + W1 + slot;
+    double* tp = P.tiles + o*TILE2;
+    cfrag_load(tp, acc, lane);
+    accumulate_updates(P, acc, max(0, K - WB), min(K - 1, P.Kend - 1), W1 + slot, 0, K, 1, false, stage, lane);
+    if (K >= P.Kend) {                      // spike tile of a separator column: its Schur complement, final
+      cfrag_store(tp, acc, lane);
+      set_flag(flag_done(P) + o, lane);
+    } else tile_finish_trsm(P, acc, K, tp, flag_done(P) + o, sb, sinv, lane);
   }
 }
 
 // =====================================================================================================================
-// Spine v3.  One CTA of 8 warps per band problem; the compute warps work out of shared memory / registers only and
+// Spine.  One CTA of 8 warps per band problem; the compute warps work out of shared memory / registers only and
 // never touch global memory, fences or flags -- three I/O warps do that one column ahead / behind:
 // (warp w issues on scheduler w % 4: each A warp shares its scheduler with a mostly sleeping I/O warp)
 //   A pair (warps 0, 1)  alternate per column between  potrf(K,K)  and  accumulating the next diagonal tile
@@ -669,11 +401,10 @@ __device__ __forceinline__ void ev_wait(volatile int* ev, int i, int v, int lane
 // back from shared memory by EVERY lane and factored redundantly in registers, each lane solving its own row against it
 // on the way (no shuffles); the serial chain per column is rsqrt -> scale -> one FMA.  Finished panels are published:
 // sPan[p][row*PSTR + j] = L[row][8p + j], sIv[k] = 1 / L[k][k], event EV_PAN + p.
-__device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, double* sPan, double* sIv, volatile int* ev, int cval, long long (&prof)[3]) {
+__device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, double* sPan, double* sIv, volatile int* ev, int cval) {
   bool ok = true;
 #pragma unroll 1
   for (int p = 0; p < 4; p++) {
-    const long long tp0 = clock64();
     double* sP = sPan + p*PANSZ;
     double x[8];
     SPINE_BLOCK_SWITCH(p, {
@@ -689,7 +420,6 @@ __device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, doubl
 #pragma unroll
       for (int j = 0; j <= i; j++) G[i*(i + 1)/2 + j] = sP[(8*p + i)*PSTR + j];
     __syncwarp();
-    const long long tp1 = clock64();
     double myinv = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -708,7 +438,6 @@ __device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, doubl
         for (int i = j; i < 8; i++) G[i*(i + 1)/2 + j] -= G[i*(i + 1)/2 + k]*ljk;
       }
     }
-    const long long tp2 = clock64();
     if (lane < 8) sIv[8*p + lane] = myinv;
 #pragma unroll
     for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sP + lane*PSTR + j) = make_double2(x[j], x[j + 1]);
@@ -730,8 +459,6 @@ __device__ __forceinline__ bool spine_potrf(double (&row)[TILE], int lane, doubl
         }
       }
     }
-    const long long tp3 = clock64();
-    prof[0] += tp1 - tp0; prof[1] += tp2 - tp1; prof[2] += tp3 - tp2;
   }
   return ok;
 }
@@ -829,24 +556,20 @@ __device__ __forceinline__ void cfrag_to_rows(double (&r)[TILE], double* scr, in
 }
 
 __global__ void __launch_bounds__(SP_WARPS*32)
-band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fail) {
+band_cholesky_dataflow_kernel_v3(CholJob job, int* __restrict__ fail) {
   extern __shared__ __align__(16) double chol_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= job.np) {
-    if (warp >= wk_warps) return;
-    if (wk_warps <= 4) {       // room for the prefetch buffers: [warp][2 stages][2 tiles][TSZ] | [TILE2] | [TILE]
-      double* base = chol_smem + (size_t)warp*(4*TSZ + TILE2 + TILE);
-      chol_worker(job, ((int)blockIdx.x - job.np)*wk_warps + warp, ((int)gridDim.x - job.np)*wk_warps,
-                  base + 4*TSZ, base + 4*TSZ + TILE2, base, lane, 3);
-    } else {
-      chol_worker(job, ((int)blockIdx.x - job.np)*wk_warps + warp, ((int)gridDim.x - job.np)*wk_warps,
-                  chol_smem + (size_t)warp*TILE2, chol_smem + (size_t)SP_WARPS*TILE2 + warp*TILE, nullptr, lane, 3);
-    }
+    if (warp >= 4) return;       // four worker warps per CTA (one per scheduler): [warp][2 stages][2 tiles][TSZ] | [TILE2] | [TILE]
+    double* base = chol_smem + (size_t)warp*(4*TSZ + TILE2 + TILE);
+    const int w = (int)blockIdx.x - job.np;
+    if (w < job.band_ctas) band_worker(job, w*4 + warp, job.band_ctas*4, base + 4*TSZ, base + 4*TSZ + TILE2, base, lane);
+    else spike_worker(job, (w - job.band_ctas)*4 + warp, ((int)gridDim.x - job.np - job.band_ctas)*4, base + 4*TSZ, base + 4*TSZ + TILE2, base, lane);
     return;
   }
-  const CholProb P = job.p[blockIdx.x];
-  const int WB = job.WB, W1 = WB + 1, NT = P.NT, Kbeg = P.Kbeg, Kend = P.Kend;
-  if (Kbeg >= Kend) return;
+  const BandProb P = job.p[blockIdx.x];
+  const int WB = job.WB, TPC = P.TPC, NT = P.NT, Kend = P.Kend;
+  if (Kend <= 0) return;
   double* sPan = chol_smem;                   // [2][4][PANSZ]
   double* sIv = sPan + 2*4*PANSZ;             // [2][32]
   double* sX1 = sIv + 2*TILE;                 // [2][TSZ]  k-major, column stride TS
@@ -855,97 +578,77 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
   double* sXnin = sDin + 2*TSZ;               // [2][TSZ]
   double* sScr = sXnin + 2*TSZ;               // [4][TILE2] layout-conversion scratch of the A / B warps
   volatile int* ev = reinterpret_cast<volatile int*>(sScr + 4*TILE2);
-  if (threadIdx.x < EV_N) ev[threadIdx.x] = Kbeg;
+  if (threadIdx.x < EV_N) ev[threadIdx.x] = 0;
   __syncthreads();
-  int* done = P.done; int* pre = P.pre;
+  int* done = flag_done(P); int* pre = flag_pre(P);
   const bool x2 = WB >= 2;
   double r[TILE];
   if (warp == 0 || warp == 1) {
     // ---------------------------------------------------------------- A pair: potrf / next diagonal tile
     const int i = warp;
-    long long dbg[4] = {0, 0, 0, 0}, prof[3] = {0, 0, 0};
-    for (int c = Kbeg - 1; c < Kend; c++) {
-      if (c >= Kbeg && (c & 1) == i) {
-        const long long t0 = clock64();
+    for (int c = -1; c < Kend; c++) {
+      if (c >= 0 && (c & 1) == i) {
         ev_wait(ev, EV_ST_L, c - 1, lane);
-        const long long t1 = clock64();
-        strace(c, 0, lane);
-        if (!spine_potrf(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, prof) && lane == 0) atomicOr(fail, 2);
-        dbg[0] += clock64() - t1; dbg[1] += t1 - t0;
-        strace(c, 1, lane);
+        if (!spine_potrf(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1) && lane == 0) atomicOr(fail, 2);
       } else if (((c + 1) & 1) == i && c + 1 < NT) {
-        const long long t0 = clock64();
         ev_wait(ev, EV_DIN, c + 2, lane);
         cfrag_load_s<TS>(sDin + ((c + 1) & 1)*TSZ, r, lane);      // r: accumulator fragments until cfrag_to_rows
         ev_signal(ev, EV_TK_D, c + 2, lane);
-        const long long t1 = clock64();
-        strace(c + 1, 2, lane);
         // term 0: X2(c-1) = L(c+1, c-1), staged two columns ago and still in its buffer; term 1: X1(c), panel by panel
 #pragma unroll 1
         for (int t = 0; t < 2; t++) {
-          if (t == 0 ? !(x2 && c - 1 >= Kbeg) : !(c >= Kbeg)) continue;
-          if (t == 0) { ev_wait(ev, EV_X2, c, lane); strace(c + 1, 3, lane); } else strace(c + 1, 4, lane);
+          if (t == 0 ? !(x2 && c - 1 >= 0) : !(c >= 0)) continue;
+          if (t == 0) ev_wait(ev, EV_X2, c, lane);
           const double* xa = t == 0 ? sX2 + ((c - 1) & 1)*TSZ : sX1 + (c & 1)*TSZ;
           spine_rank32(r, xa, xa, true, ev, t == 0 ? -1 : EV_X1P, c + 1, lane);
         }
         cfrag_to_rows(r, sScr + i*TILE2, lane);
-        const long long t2 = t1;
-        strace(c + 1, 5, lane);
-        dbg[2] += t1 - t0; dbg[3] += clock64() - t2;
-        if (c + 1 == Kend) tile_store(P.tiles + (size_t)Kend*W1*TILE2, r, lane);   // not factored here: hand it back
+        if (c + 1 == Kend) tile_store(P.tiles + (size_t)Kend*TPC*TILE2, r, lane);   // not factored here: hand it back
       }
     }
-    if (blockIdx.x == 0 && lane == 0) { for (int k = 0; k < 4; k++) g_spine_dbg[i*4 + k] = dbg[k]; if (i == 0) for (int k = 0; k < 3; k++) g_spine_dbg[8 + k] = prof[k]; }
   } else if (warp == 2 || warp == 3) {
     // ---------------------------------------------------------------- B pair: X1 TRSM / next X1 input
     const int i = warp - 2;
-    for (int c = Kbeg - 1; c < Kend; c++) {
-      if (c >= Kbeg && (c & 1) == i) {
+    for (int c = -1; c < Kend; c++) {
+      if (c >= 0 && (c & 1) == i) {
         if (c + 1 < NT) {
           ev_wait(ev, EV_ST_X1, c - 1, lane);
-          strace(c, 6, lane);
           spine_trsm(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, sX1 + (c & 1)*TSZ, EV_X1P);
-          strace(c, 7, lane);
         }
       } else if (((c + 1) & 1) == i && c + 2 < NT) {
         ev_wait(ev, EV_XNIN, c + 2, lane);
         cfrag_load_s<TS>(sXnin + ((c + 1) & 1)*TSZ, r, lane);
         ev_signal(ev, EV_TK_XN, c + 2, lane);
-        strace(c + 1, 8, lane);
-        if (x2 && c >= Kbeg) {
+        if (x2 && c >= 0) {
           ev_wait(ev, EV_X2, c + 1, lane);
-          strace(c + 1, 9, lane);
           spine_rank32(r, sX2 + (c & 1)*TSZ, sX1 + (c & 1)*TSZ, false, ev, EV_X1P, c + 1, lane);
-          strace(c + 1, 10, lane);
         }
         cfrag_to_rows(r, sScr + (2 + i)*TILE2, lane);
-        if (c + 1 == Kend) tile_store(P.tiles + ((size_t)Kend*W1 + 1)*TILE2, r, lane);
+        if (c + 1 == Kend) tile_store(P.tiles + ((size_t)Kend*TPC + 1)*TILE2, r, lane);
       }
     }
   } else if (warp == 6) {
     // ---------------------------------------------------------------- C: X2 TRSM
-    if (x2) for (int c = Kbeg; c < Kend; c++) if (c + 2 < NT) {
-      wait_flag(pre + (size_t)c*W1 + 2, lane);
-      tile_load(P.tiles + ((size_t)c*W1 + 2)*TILE2, r, lane);
-      strace(c, 11, lane);
+    if (x2) for (int c = 0; c < Kend; c++) if (c + 2 < NT) {
+      wait_flag(pre + (size_t)c*TPC + 2, lane);
+      tile_load(P.tiles + ((size_t)c*TPC + 2)*TILE2, r, lane);
       spine_trsm(r, lane, sPan + (c & 1)*4*PANSZ, sIv + (c & 1)*TILE, ev, c + 1, sX2 + (c & 1)*TSZ, -1);
       ev_signal(ev, EV_X2, c + 1, lane);
-      strace(c, 12, lane);
       // publish X2(c) from its staged copy (this warp runs on its own clock: the store is off the spine's critical path)
       {
         const double* sx = sX2 + (c & 1)*TSZ;
-        double* t = P.tiles + ((size_t)c*W1 + 2)*TILE2;
+        double* t = P.tiles + ((size_t)c*TPC + 2)*TILE2;
 #pragma unroll
         for (int col = 0; col < TILE; col++) t[col*TILE + lane] = sx[col*TS + lane];
       }
-      set_flag(done + (size_t)c*W1 + 2, lane);
+      set_flag(done + (size_t)c*TPC + 2, lane);
     }
   } else if (warp == 7) {
     // ---------------------------------------------------------------- IO0: L(c,c), X1(c) -> global
-    for (int c = Kbeg; c < Kend; c++) {
+    for (int c = 0; c < Kend; c++) {
       ev_wait(ev, EV_PAN + 3, c + 1, lane);
       const double* pan = sPan + (c & 1)*4*PANSZ;
-      double* t = P.tiles + (size_t)c*W1*TILE2;
+      double* t = P.tiles + (size_t)c*TPC*TILE2;
 #pragma unroll
       for (int p = 0; p < 4; p++)
 #pragma unroll
@@ -953,23 +656,23 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
           const double2 v = *reinterpret_cast<const double2*>(pan + p*PANSZ + lane*PSTR + j);
           t[(8*p + j)*TILE + lane] = v.x; t[(8*p + j + 1)*TILE + lane] = v.y;
         }
-      set_flag(done + (size_t)c*W1, lane);
+      set_flag(done + (size_t)c*TPC, lane);
       ev_signal(ev, EV_ST_L, c + 1, lane);
       if (c + 1 < NT) {
         ev_wait(ev, EV_X1P + 3, c + 1, lane);
         const double* sx = sX1 + (c & 1)*TSZ;
 #pragma unroll
         for (int col = 0; col < TILE; col++) t[TILE2 + col*TILE + lane] = sx[col*TS + lane];
-        set_flag(done + (size_t)c*W1 + 1, lane);
+        set_flag(done + (size_t)c*TPC + 1, lane);
         ev_signal(ev, EV_ST_X1, c + 1, lane);
       }
     }
   } else if (warp == 5) {
     // ---------------------------------------------------------------- IO1: inputs of column c+1 -> shared memory
-    for (int c = Kbeg - 1; c < Kend; c++) if (c + 1 < NT) {
-      const double* t = P.tiles + (size_t)(c + 1)*W1*TILE2;
+    for (int c = -1; c < Kend; c++) if (c + 1 < NT) {
+      const double* t = P.tiles + (size_t)(c + 1)*TPC*TILE2;
       ev_wait(ev, EV_TK_D, c, lane);
-      wait_flag(pre + (size_t)(c + 1)*W1, lane);
+      wait_flag(pre + (size_t)(c + 1)*TPC, lane);
       tile_load(t, r, lane);
       double* sd = sDin + ((c + 1) & 1)*TSZ;
 #pragma unroll
@@ -977,7 +680,7 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
       ev_signal(ev, EV_DIN, c + 2, lane);
       if (c + 2 < NT) {
         ev_wait(ev, EV_TK_XN, c, lane);
-        wait_flag(pre + (size_t)(c + 1)*W1 + 1, lane);
+        wait_flag(pre + (size_t)(c + 1)*TPC + 1, lane);
         tile_load(t + TILE2, r, lane);
         double* sx = sXnin + ((c + 1) & 1)*TSZ;
 #pragma unroll
@@ -989,35 +692,15 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int wk_warps, int* __restrict__ fa
   // warp 4 has no role: it leaves scheduler 0 to the A warp that issues there
 }
 
-// sums the two Schur complements left in the middle separator: A.M += flip(B.M), A.rhs_M += flip(B.rhs_M)
-__global__ void merge_middle_kernel(DevBand B) {
-  const int np1 = B.n_pad - 1, lo = B.split_lo, hi = B.split_hi, s = hi - lo;
-  const long long total = (long long)s*s;
-  for (long long e = (long long)blockIdx.x*blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x*blockDim.x) {
-    const int i = lo + (int)(e/s), j = lo + (int)(e%s);
-    if (j > i) continue;
-    B.tiles[band_index_wb(B.WB, i, j)] += B.tiles2[band_index_wb(B.WB, np1 - j, np1 - i)];
-  }
-  for (int p = lo + blockIdx.x*blockDim.x + threadIdx.x; p < hi; p += gridDim.x*blockDim.x) B.rhs[p] += B.rhs2[np1 - p];
-}
-// x_M (solved in A) -> the reversed copy that primes B's backward sweep
-__global__ void prime_back_kernel(DevBand B) {
-  const int np1 = B.n_pad - 1;
-  for (int p = B.split_lo + blockIdx.x*blockDim.x + threadIdx.x; p < B.split_hi; p += gridDim.x*blockDim.x) B.rhs2[np1 - p] = B.rhs[p];
-}
-__global__ void gather_solution_kernel(DevBand B) {
-  const int np1 = B.n_pad - 1;
-  for (int p = blockIdx.x*blockDim.x + threadIdx.x; p < B.n_pad; p += gridDim.x*blockDim.x)
-    B.dp[p] = p < B.split_hi ? B.rhs[p] : B.rhs2[np1 - p];
-}
-
 // explicit inverse of every diagonal tile: Linv[K] = L_KK^-1 (lower triangular), one warp per tile
-__global__ void __launch_bounds__(128) diag_inverse_kernel(const double* __restrict__ tiles, int NT, int WB, double* __restrict__ linv) {
+__global__ void __launch_bounds__(128) diag_inverse_kernel(const BandProb* __restrict__ probs) {
   __shared__ double sL[4][TILE2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const BandProb P = probs[blockIdx.y];
   const int K = blockIdx.x*4 + warp;
-  if (K >= NT) return;
-  const double* t = tiles + (size_t)K*(WB + 1)*TILE2;
+  if (K >= P.Kend) return;
+  const double* t = P.tiles + (size_t)K*P.TPC*TILE2;
+  double* linv = P.linv;
   double* s = sL[warp];
 #pragma unroll
   for (int c = 0; c < TILE; c++) s[c*TILE + lane] = t[c*TILE + lane];
@@ -1036,28 +719,13 @@ __global__ void __launch_bounds__(128) diag_inverse_kernel(const double* __restr
   for (int r = 0; r < TILE; r++) o[lane*TILE + r] = (r >= lane) ? x[r] : 0.0;   // element (r, j=lane) at j*32 + r
 }
 
-// butterfly: on entry lane r holds v[c] (c = 0..31); on exit every lane c returns sum over r of v_r[c]
-__device__ __forceinline__ double warp_transpose_sum(double (&v)[TILE], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; i++) {
-      const double send = up ? v[i] : v[i + o];
-      const double recv = __shfl_xor_sync(0xffffffffu, send, o);
-      v[i] = (up ? v[i + o] : v[i]) + recv;
-    }
-  }
-  return v[0];
-}
-
 // backward sweep  x_J = Linv_JJ^T (y_J - sum_{I>J} L_IJ^T x_I) for J = Jtop-1 ... Jbot; rhs overwritten.
 // One thread-block CLUSTER of 8 CTAs (8 SMs) per band problem: the off-diagonal tiles of a column are spread over
 // 8 x 4 warps so the 240 KB a column reads come through eight SMs' load paths; per-CTA partial sums are all-gathered
 // through distributed shared memory and every CTA finishes x_J itself (one cluster barrier per column).
 // Columns >= Jtop are already solved (the middle separator of the two-directional scheme): their x primes the ring.
 struct BackProb { const double* tiles; double* rhs; const double* linv; int NT, Jtop, Jbot; };
-struct BackJob { BackProb p[2]; int WB; };
+struct BackJob { const BandProb* p; int WB; };
 constexpr int BW_CL = 8, BW_TW = 4;      // cluster size, tile warps per CTA
 constexpr int BW_PS = 34;                // padded column stride of warp 0's shared-memory tiles (conflict-free LDS.128 per column)
 // dot product of 32 register values with a 32-vector in shared memory (broadcast reads)
@@ -1080,8 +748,9 @@ band_backward_cluster_kernel(BackJob job) {
   extern __shared__ __align__(16) double sm[];
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();
-  const BackProb P = job.p[blockIdx.x/BW_CL];
-  const int NT = P.NT, WB = job.WB, W1 = WB + 1, ring = WB + 2;
+  const BandProb Q = job.p[blockIdx.x/BW_CL];
+  const BackProb P = { Q.tiles, Q.rhs, Q.linv, Q.NT, Q.Kend, 0 };     // columns >= Kend are solved already: their x primes the ring
+  const int NT = P.NT, WB = job.WB, W1 = Q.TPC /* column stride in tiles */, ring = WB + 2;
   double* xs = sm;                                   // [ring][32] solved blocks (replicated in every CTA)
   double* lpart = sm + (size_t)ring*TILE;            // [2][BW_TW][32] partial sums of this CTA's tile warps, per column
   double* cpart = lpart + 2*BW_TW*TILE;              // [2][2][BW_CL][32] all-gathered per-CTA partials (pair parity, column)
@@ -1210,7 +879,165 @@ band_backward_cluster_kernel(BackJob job) {
   }
 }
 
-static int g_max_blocks = 0, g_spine_ver = 3, g_wk_warps = 4, g_skew = 2;
+// =====================================================================================================================
+// Separator plumbing (element-wise kernels; tools/cell_proto.py stages 2-4)
+
+// g_Q -= sum_{J < Kend} Z(J) y_J of every spiked chain: partial sums per chunk of SF_CH columns, then a fixed-order sum
+constexpr int SF_CH = 8;
+__global__ void __launch_bounds__(256) spike_forward_partial_kernel(const BandProb* __restrict__ probs, int WB, double* __restrict__ scratch, int maxchunks) {
+  const BandProb P = probs[blockIdx.y];
+  const int J0 = blockIdx.x*SF_CH;
+  if (!P.spiked || J0 >= P.Kend) return;
+  __shared__ double sy[SF_CH][TILE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nJ = min(SF_CH, P.Kend - J0);
+  if (warp < nJ) sy[warp][lane] = P.rhs[(size_t)(J0 + warp)*TILE + lane];
+  __syncthreads();
+  for (int r = warp; r < WB; r += 8) {
+    double s = 0.0;
+    for (int jj = 0; jj < nJ; jj++) {
+      const double* z = P.tiles + ((size_t)(J0 + jj)*P.TPC + WB + 1 + r)*TILE2;
+#pragma unroll 8
+      for (int c = 0; c < TILE; c++) s += z[c*TILE + lane]*sy[jj][c];
+    }
+    scratch[(((size_t)blockIdx.y*maxchunks + blockIdx.x)*WB + r)*TILE + lane] = s;
+  }
+}
+__global__ void spike_forward_reduce_kernel(const BandProb* __restrict__ probs, int WB, const double* __restrict__ scratch, int maxchunks) {
+  const BandProb P = probs[blockIdx.y];
+  if (!P.spiked) return;
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;       // element of gf: r*32 + lane
+  if (e >= WB*TILE) return;
+  const int nchunk = (P.Kend + SF_CH - 1)/SF_CH;
+  double s = 0.0;
+  for (int k = 0; k < nchunk; k++) s += scratch[((size_t)blockIdx.y*maxchunks + k)*WB*TILE + e];
+  P.gf[e] -= s;
+}
+// y_J -= sum_r Z_r(J)^T x_Q[r] for every factored column J of every spiked chain (x_Q in the chain's order in P.gf)
+__global__ void __launch_bounds__(256) spike_backward_kernel(const BandProb* __restrict__ probs, int WB) {
+  extern __shared__ double sx[];        // [WB][32]
+  const BandProb P = probs[blockIdx.y];
+  if (!P.spiked || (int)blockIdx.x*8 >= P.Kend) return;
+  for (int i = threadIdx.x; i < WB*TILE; i += blockDim.x) sx[i] = P.gf[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int J = blockIdx.x*8 + warp;
+  if (J >= P.Kend) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int r = 0; r < WB; r++) {
+    const double2* z = reinterpret_cast<const double2*>(P.tiles + ((size_t)J*P.TPC + WB + 1 + r)*TILE2 + lane*TILE);   // column `lane`
+    const double* x = sx + r*TILE;
+#pragma unroll
+    for (int k = 0; k < TILE/2; k++) { const double2 u = z[k]; s0 += u.x*x[2*k]; s1 += u.y*x[2*k + 1]; }
+  }
+  P.rhs[(size_t)J*TILE + lane] -= s0 + s1;
+}
+
+struct CellRefs { const BandProb* chains; const BandProb* cs; const BandProb* gq; const CellGeom* cells; const int* local_cells; int WB; };
+
+// entry (i >= j) of the cell separator system [M | Qa | Qb] of cell c from the chains' storage after their factorisation
+__device__ __forceinline__ double cs_value(const BandProb& A, const BandProb& Bc, int WB, bool has_qa, int i, int j) {
+  const int w = WB*TILE, zi = i/w, zj = j/w, ii = i - zi*w, jj = j - zj*w;
+  const bool iQa = has_qa && zi == 1, jQa = has_qa && zj == 1;
+  if (zj == 0) {
+    if (zi == 0) {
+      const int li = w - 1 - jj, lj = w - 1 - ii;
+      return A.tiles[tile_elem(A.TPC, A.Kend + (jj >> 5), (ii >> 5) - (jj >> 5), ii & 31, jj & 31)] +
+             Bc.tiles[tile_elem(Bc.TPC, Bc.Kend + (lj >> 5), (li >> 5) - (lj >> 5), li & 31, lj & 31)];
+    }
+    if (iQa) return A.tiles[tile_elem(A.TPC, A.Kend + (jj >> 5), WB + 1 + (ii >> 5), ii & 31, jj & 31)];
+    const int s = w - 1 - ii, lc = w - 1 - jj;
+    return Bc.tiles[tile_elem(Bc.TPC, Bc.Kend + (lc >> 5), WB + 1 + (s >> 5), s & 31, lc & 31)];
+  }
+  if (jQa) return iQa ? A.ff[((size_t)(ii >> 5)*WB + (jj >> 5))*TILE2 + (size_t)(jj & 31)*TILE + (ii & 31)] : 0.0;
+  const int si = w - 1 - ii, sj = w - 1 - jj;      // sj >= si
+  return Bc.ff[((size_t)(sj >> 5)*WB + (si >> 5))*TILE2 + (size_t)(si & 31)*TILE + (sj & 31)];
+}
+// grid (tiles of the cell system, local cells): one CTA of 256 threads per tile (K, dd)
+__global__ void __launch_bounds__(256) cs_assemble_kernel(CellRefs R, int TPCcs) {
+  const int c = R.local_cells[blockIdx.y];
+  const BandProb S = R.cs[c], A = R.chains[2*c], Bc = R.chains[2*c + 1];
+  const bool has_qa = R.cells[c].has_qa != 0;
+  const int K = blockIdx.x/TPCcs, dd = blockIdx.x%TPCcs;
+  if (K + dd >= S.NT) return;
+  double* t = S.tiles + ((size_t)K*S.TPC + dd)*TILE2;
+  for (int e = threadIdx.x; e < TILE2; e += 256) {
+    const int cj = e >> 5, ri = e & 31, i = (K + dd)*TILE + ri, j = K*TILE + cj;
+    t[e] = i >= j ? cs_value(A, Bc, R.WB, has_qa, i, j) : 0.0;
+  }
+  if (dd == 0 && threadIdx.x < TILE) {
+    const int w = R.WB*TILE, p = K*TILE + threadIdx.x, z = p/w, pp = p - z*w;
+    double v;
+    if (z == 0) v = A.rhs[(size_t)A.Kend*TILE + pp] + Bc.rhs[(size_t)Bc.Kend*TILE + (w - 1 - pp)];
+    else if (has_qa && z == 1) v = A.gf[pp];
+    else v = Bc.gf[w - 1 - pp];
+    S.rhs[p] = v;
+  }
+}
+// adds the Schur complement cell c leaves on its boundary separators into the boundary system (one launch per cell, in
+// cell order: two neighbouring cells add into the same diagonal block)
+__global__ void gq_add_cell_kernel(CellRefs R, int c, int TPCgq) {
+  const BandProb S = R.cs[c], G = R.gq[0];
+  const CellGeom g = R.cells[c];
+  const int w = R.WB*TILE, nz = g.has_qa + g.has_qb;             // trailing zones of the cell system
+  const long long total = (long long)nz*w*nz*w;
+  for (long long e = (long long)blockIdx.x*blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x*blockDim.x) {
+    const int ti = (int)(e/(nz*w)), tj = (int)(e%(nz*w));
+    if (tj > ti) continue;
+    const int i = w + ti, j = w + tj;                            // cell-system coordinates
+    const int zi = ti/w, zj = tj/w;
+    const int qi = (g.has_qa ? c - 1 + zi : c), qj = (g.has_qa ? c - 1 + zj : c);
+    const int gi = qi*w + (ti - zi*w), gj = qj*w + (tj - zj*w);
+    const double v = S.tiles[tile_elem(S.TPC, j >> 5, (i >> 5) - (j >> 5), i & 31, j & 31)];
+    G.tiles[tile_elem(TPCgq, gj >> 5, (gi >> 5) - (gj >> 5), gi & 31, gj & 31)] += v;
+  }
+  for (int p = blockIdx.x*blockDim.x + threadIdx.x; p < nz*w; p += gridDim.x*blockDim.x) {
+    const int z = p/w, q = (g.has_qa ? c - 1 + z : c);
+    G.rhs[q*w + (p - z*w)] += S.rhs[w + p];
+  }
+}
+// x_Q -> the cell systems' trailing rows and the chains' spike vectors (chain order)
+__global__ void gq_scatter_kernel(CellRefs R) {
+  const int c = R.local_cells[blockIdx.y];
+  const BandProb S = R.cs[c], A = R.chains[2*c], Bc = R.chains[2*c + 1], G = R.gq[0];
+  const CellGeom g = R.cells[c];
+  const int w = R.WB*TILE;
+  for (int p = blockIdx.x*blockDim.x + threadIdx.x; p < w; p += gridDim.x*blockDim.x) {
+    if (g.has_qa) { const double x = G.rhs[(c - 1)*w + p]; S.rhs[w + p] = x; A.gf[p] = x; }
+    if (g.has_qb) { const double x = G.rhs[c*w + p]; S.rhs[(1 + g.has_qa)*w + p] = x; Bc.gf[w - 1 - p] = x; }
+  }
+}
+// x_M -> the near-separator rows of both chains (B reversed)
+__global__ void cs_to_chain_kernel(CellRefs R) {
+  const int c = R.local_cells[blockIdx.y];
+  const BandProb S = R.cs[c], A = R.chains[2*c], Bc = R.chains[2*c + 1];
+  const int w = R.WB*TILE;
+  for (int p = blockIdx.x*blockDim.x + threadIdx.x; p < w; p += gridDim.x*blockDim.x) {
+    const double x = S.rhs[p];
+    A.rhs[(size_t)A.Kend*TILE + p] = x; Bc.rhs[(size_t)Bc.Kend*TILE + (w - 1 - p)] = x;
+  }
+}
+__global__ void gather_dp_kernel(CellRefs R, double* __restrict__ dp) {
+  const int c = R.local_cells[blockIdx.y];
+  const BandProb S = R.cs[c], A = R.chains[2*c], Bc = R.chains[2*c + 1];
+  const CellGeom g = R.cells[c];
+  const int w = R.WB*TILE, hi = g.b1 + (g.has_qb ? w : 0);
+  for (int p = g.a0 + blockIdx.x*blockDim.x + threadIdx.x; p < hi; p += gridDim.x*blockDim.x) {
+    double x;
+    if (p < g.m0) x = A.rhs[p - g.a0];
+    else if (p < g.m0 + w) x = S.rhs[p - g.m0];
+    else if (p < g.b1) x = Bc.rhs[g.b1 - 1 - p];
+    else x = R.gq[0].rhs[c*w + (p - g.b1)];
+    dp[p] = x;
+  }
+}
+
+// =====================================================================================================================
+// Host side
+
+static int g_max_blocks = 0;
+static int g_band_ctas_per_chain = 22;
+void band_set_tuning(int band_ctas_per_chain) { if (band_ctas_per_chain > 0) g_band_ctas_per_chain = band_ctas_per_chain; }
 static size_t g_chol_smem = 0;
 
 static void chol_init() {
@@ -1218,131 +1045,249 @@ static void chol_init() {
   int dev = 0, sms = 0, per = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // CTAs per SM: 1 keeps each spine CTA alone on its SM (DYNOBA_CHOL_BPS overrides for experiments)
-  int bps = 1; if (const char* e = getenv("DYNOBA_CHOL_BPS")) bps = atoi(e) > 0 ? atoi(e) : 1;
-  if (const char* e = getenv("DYNOBA_SPINE")) g_spine_ver = atoi(e) == 2 ? 2 : 3;
-  if (const char* e = getenv("DYNOBA_SKEW")) g_skew = std::max(2, atoi(e));
-  if (const char* e = getenv("DYNOBA_WK_WARPS")) g_wk_warps = std::max(1, std::min(SP_WARPS, atoi(e)));
-  if (g_spine_ver == 2) g_wk_warps = CH_WARPS;
-  const size_t need = g_spine_ver == 2 ? (size_t)(1152 + 4*TILE2 + 256 + 64)*sizeof(double)
-                                       : std::max((size_t)(2*4*PANSZ + 2*TILE + 8*TSZ + 4*TILE2 + 64), (size_t)4*(4*TSZ + TILE2 + TILE))*sizeof(double);   // spine | workers with prefetch stages
-  g_chol_smem = std::max(need, (size_t)(220*1024)/bps - 2048);
-  const void* kern = g_spine_ver == 2 ? (const void*)band_cholesky_dataflow_kernel : (const void*)band_cholesky_dataflow_kernel_v3;
-  const int nthr = g_spine_ver == 2 ? CH_WARPS*32 : SP_WARPS*32;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_chol_smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, nthr, g_chol_smem);
+  // one CTA per SM: every spine CTA is alone on its SM
+  const size_t need = std::max((size_t)(2*4*PANSZ + 2*TILE + 8*TSZ + 4*TILE2 + 64), (size_t)4*(4*TSZ + TILE2 + TILE))*sizeof(double);   // spine | workers with prefetch stages
+  g_chol_smem = std::max(need, (size_t)(220*1024) - 2048);
+  cudaFuncSetAttribute(band_cholesky_dataflow_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_chol_smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, band_cholesky_dataflow_kernel_v3, SP_WARPS*32, g_chol_smem);
   g_max_blocks = sms*(per > 0 ? per : 1);
+  cudaFuncSetAttribute(band_backward_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
 }
-static void chol_launch(const CholJob& job, int* fail, cudaStream_t s) {
+// factorisation of np problems (device descriptors dprobs, host mirrors hprobs), flags cleared first
+static int chol_launch(const BandProb* dprobs, const BandProb* hprobs, int np, int WB, int* fail, cudaStream_t s) {
+  if (np <= 0) return 0;
+  chol_init();
+  CholJob job; job.p = dprobs; job.np = np; job.WB = WB; job.skew = 2; job.any_spiked = 0; job.ncols = 0;
   long long ntile = 0;
-  for (int q = 0; q < job.np; q++) ntile += (long long)(job.p[q].NT - job.p[q].Kbeg)*(job.WB + 2);
-  int grid = g_max_blocks;
-  const long long want = (ntile + g_wk_warps - 1)/g_wk_warps + job.np;
-  if (grid > want) grid = (int)want;
-  if (grid < job.np + 1) grid = job.np + 1;
-  CholJob j = job; j.skew = g_skew;
-  // cooperative launch only for its co-residency guarantee (the flag waits need every warp resident)
-  if (g_spine_ver == 2) {
-    void* args[] = { (void*)&j, (void*)&fail };
-    cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel, dim3(grid), dim3(CH_WARPS*32), args, g_chol_smem, s);
-  } else {
-    int wk = g_wk_warps;
-    void* args[] = { (void*)&j, (void*)&wk, (void*)&fail };
-    cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel_v3, dim3(grid), dim3(SP_WARPS*32), args, g_chol_smem, s);
+  for (int q = 0; q < np; q++) {
+    const BandProb& P = hprobs[q];
+    job.any_spiked |= P.spiked; job.ncols = std::max(job.ncols, P.NT);
+    ntile += (long long)P.NT*(P.TPC + 1);
+    const size_t nfl = (size_t)2*P.NT*P.TPC + P.NT + (size_t)WB*WB;
+    cudaMemsetAsync(P.flags, 0, nfl*sizeof(int), s);
   }
+  int grid = g_max_blocks;
+  const long long want = (ntile + 3)/4 + np;
+  if (grid > want) grid = (int)want;
+  if (grid < np + 1 + (job.any_spiked ? 1 : 0)) grid = np + 1 + (job.any_spiked ? 1 : 0);
+  // worker CTAs: without spikes all of them work on band tiles; else pool A gets what keeps the chains at the spine's
+  // pace (~ band_ctas_per_chain CTAs per chain) and the rest streams the spike / FF updates behind them
+  const int workers = grid - np;
+  job.band_ctas = job.any_spiked ? std::max(1, std::min(workers - 1, std::min(g_band_ctas_per_chain*np, workers*2/3))) : workers;
+  // cooperative launch only for its co-residency guarantee (the flag waits need every warp resident)
+  void* args[] = { (void*)&job, (void*)&fail };
+  cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel_v3, dim3(grid), dim3(SP_WARPS*32), args, g_chol_smem, s);
+  return 1;
+}
+static int back_launch(const BandProb* dprobs, int np, int WB, cudaStream_t s) {
+  if (np <= 0) return 0;
+  chol_init();
+  const size_t smem = ((size_t)(WB + 2)*TILE + (size_t)(2*BW_TW + 4*BW_CL + 1)*TILE + 6*TILE*BW_PS)*sizeof(double);
+  BackJob job; job.p = dprobs; job.WB = WB;
+  band_backward_cluster_kernel<<<np*BW_CL, (BW_TW + 1)*32, smem, s>>>(job);
+  return 1;
 }
 
-int launch_band_cholesky(const DevBand& B, int* flags, double* linv, int* fail, cudaStream_t s) {
-  chol_init();
-  const int W1 = B.WB + 1;
-  const int NTA = B.two ? B.NTA : B.NT, NTB = B.two ? B.NTB : 0;
-  const size_t nfl = (size_t)(NTA + NTB)*(2*W1 + 1);
-  cudaMemsetAsync(flags, 0, nfl*sizeof(int), s);
-  int* fA = flags; int* fB = flags + (size_t)NTA*(2*W1 + 1);
-  auto prob = [&](double* tiles, double* rhs, int NT, int kb, int ke, int* f) {
-    CholProb p; p.tiles = tiles; p.rhs = rhs; p.NT = NT; p.Kbeg = kb; p.Kend = ke; p.done = f; p.pre = f + (size_t)NT*W1; p.ydone = f + (size_t)2*NT*W1; return p; };
-  int launches = 0;
-  long long* dtrace = nullptr; long long* dstrace = nullptr; const long long trace_len = (long long)NTA*(2*W1 + 1);
-  if (getenv("DYNOBA_CHOL_TRACE")) {
-    cudaMalloc(&dtrace, trace_len*sizeof(long long)); cudaMemsetAsync(dtrace, 0, trace_len*sizeof(long long), s);
-    cudaMemcpyToSymbolAsync(g_trace, &dtrace, sizeof(dtrace), 0, cudaMemcpyHostToDevice, s);
-    cudaMemcpyToSymbolAsync(g_trace_base, &fA, sizeof(fA), 0, cudaMemcpyHostToDevice, s);
-    cudaMemcpyToSymbolAsync(g_trace_len, &trace_len, sizeof(trace_len), 0, cudaMemcpyHostToDevice, s);
-    cudaMalloc(&dstrace, (size_t)NTA*16*sizeof(long long)); cudaMemsetAsync(dstrace, 0, (size_t)NTA*16*sizeof(long long), s);
-    cudaMemcpyToSymbolAsync(g_strace, &dstrace, sizeof(dstrace), 0, cudaMemcpyHostToDevice, s);
+// ---------------------------------------------------------------------------------------------------------------------
+// Layout.  Cells are cut so that every chain is at least WB tiles long (a boundary separator then only touches the two
+// chains next to it).  Chains without a spike (the first and the last of the system) cost a quarter of the flops per
+// column of a spiked chain; `outer_weight` > 1 makes them longer.
+static size_t align_up(size_t v, size_t a) { return (v + a - 1)/a*a; }
+
+int band_plan_layout(BandPlan& P, int n, int bw, int ncell_request, int rank, int world) {
+  DevBand& B = P.band;
+  B = DevBand{};
+  P.rank = rank; P.world = world; P.WBcs = P.TPCcs = P.WBgq = P.TPCgq = P.NTgq = 0;
+  B.n = n; B.bw = std::max(0, std::min(bw, std::max(n - 1, 0)));
+  B.NT = std::max((n + TILE - 1)/TILE, 1); B.n_pad = B.NT*TILE;
+  B.WB = (B.bw + TILE - 1)/TILE; if (B.NT > 1 && B.WB < 1) B.WB = 1; if (B.WB > B.NT - 1) B.WB = B.NT - 1;
+  const int WB = B.WB, NT = B.NT;
+  // largest feasible number of cells: NT >= (2C - 1) WB + 2C max(WB, 2)
+  const int minlen = std::max(WB, 2);
+  int cmax = WB >= 1 ? (NT + WB)/(2*WB + 2*minlen) : 0;
+  cmax = std::min(cmax, MAX_CELLS);
+  int C;
+  if (ncell_request > 0) C = std::min(ncell_request, cmax);
+  else if (ncell_request < 0) C = 0;
+  else {
+    // default: one cell per GPU; on one GPU a second cell pays once the chains are long (the spiked chains cost 4x the
+    // flops per column, so short systems stay with the two-chain scheme)
+    C = world > 1 ? std::min(world, cmax) : (NT >= 4096 && cmax >= 2 ? 2 : 1);
+    if (NT < std::max(8, 4*WB + 4)) C = 0;
+    C = std::min(C, cmax);
   }
-  auto dump_trace = [&]() {     // after the first factorisation launch: flag-release times of columns in the middle of problem 0
-    if (!dtrace) return;
-    cudaStreamSynchronize(s);
-    std::vector<long long> ht(trace_len); cudaMemcpy(ht.data(), dtrace, trace_len*sizeof(long long), cudaMemcpyDeviceToHost);
-    long long* nul = nullptr; cudaMemcpyToSymbol(g_trace, &nul, sizeof(nul)); cudaFree(dtrace);
-    const int K0 = std::max(4, (B.two ? B.split_lo/TILE : NTA)/2), nd = getenv("DYNOBA_CHOL_TRACE_ALL") ? W1 : std::min(W1, 8);
-    const long long t0 = ht[(size_t)K0*W1];
-    fprintf(stderr, "[trace] ns relative to done(K0,K0), K0 = %d; columns: done dd=0..%d | pre dd=0..2\n", K0, nd - 1);
-    for (int K = K0 - 2; K < K0 + 10; K++) {
-      fprintf(stderr, "[trace] K=%d done:", K);
-      for (int d = 0; d < nd; d++) fprintf(stderr, " %7lld", ht[(size_t)K*W1 + d] ? ht[(size_t)K*W1 + d] - t0 : -1);
-      fprintf(stderr, "  pre:");
-      for (int d = 0; d < std::min(W1, 3); d++) fprintf(stderr, " %7lld", ht[(size_t)NTA*W1 + (size_t)K*W1 + d] ? ht[(size_t)NTA*W1 + (size_t)K*W1 + d] - t0 : -1);
-      fprintf(stderr, "\n");
-    }
-    std::vector<long long> hs((size_t)NTA*16); cudaMemcpy(hs.data(), dstrace, hs.size()*sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaMemcpyToSymbol(g_strace, &nul, sizeof(nul)); cudaFree(dstrace);
-    fprintf(stderr, "[strace] potrf start,end | D: taken, X2 seen, X1 term start, done | X1 trsm start,end | Xn: taken, X2 seen, done | X2 trsm start,end\n");
-    for (int K = K0 - 1; K < K0 + 8; K++) {
-      fprintf(stderr, "[strace] K=%d", K);
-      for (int e = 0; e < 13; e++) { if (e == 2 || e == 6 || e == 8 || e == 11) fprintf(stderr, " |"); fprintf(stderr, " %7lld", hs[(size_t)K*16 + e] ? hs[(size_t)K*16 + e] - t0 : -1); }
-      fprintf(stderr, "\n");
-    }
-  };
-  if (!B.two) {
-    CholJob job; job.np = 1; job.WB = B.WB; job.p[0] = prob(B.tiles, B.rhs, B.NT, 0, B.NT, fA); job.p[1] = job.p[0];
-    chol_launch(job, fail, s); launches++;
-    dump_trace();
-    diag_inverse_kernel<<<(B.NT + 3)/4, 128, 0, s>>>(B.tiles, B.NT, B.WB, linv); launches++;
+  B.ncell = C;
+  P.cells.clear(); P.chains.clear(); P.cs.clear(); P.gq.clear();
+  if (C == 0) {
+    BandProb p{}; p.NT = NT; p.Kend = NT; p.TPC = WB + 1; p.spiked = 0;
+    P.chains.push_back(p);
   } else {
-    const int KmA = B.split_lo/TILE, KmB = NTB - (B.split_hi - B.split_lo)/TILE;
-    CholJob job; job.np = 2; job.WB = B.WB;
-    job.p[0] = prob(B.tiles, B.rhs, NTA, 0, KmA, fA); job.p[1] = prob(B.tiles2, B.rhs2, NTB, 0, KmB, fB);
-    chol_launch(job, fail, s); launches++;                               // both halves, towards the middle
-    dump_trace();
-    merge_middle_kernel<<<64, 256, 0, s>>>(B); launches++;
-    cudaMemsetAsync(fA, 0, (size_t)NTA*(2*W1 + 1)*sizeof(int), s);
-    CholJob mid; mid.np = 1; mid.WB = B.WB; mid.p[0] = prob(B.tiles, B.rhs, NTA, KmA, NTA, fA); mid.p[1] = mid.p[0];
-    chol_launch(mid, fail, s); launches++;                               // the middle separator
-    diag_inverse_kernel<<<(NTA + 3)/4, 128, 0, s>>>(B.tiles, NTA, B.WB, linv); launches++;
-    diag_inverse_kernel<<<(KmB + 3)/4, 128, 0, s>>>(B.tiles2, KmB, B.WB, linv + (size_t)NTA*TILE2); launches++;
+    const long long free_tiles = (long long)NT - (long long)(2*C - 1)*WB;
+    const double outer_weight = P.outer_weight > 0 ? P.outer_weight : ((C >= 2 && world == 1) ? 1.6 : 1.0);
+    std::vector<double> wgt(2*C, 1.0); wgt[0] = wgt[2*C - 1] = outer_weight;
+    double wsum = 0; for (double x : wgt) wsum += x;
+    std::vector<int> len(2*C);
+    long long used = 0;
+    for (int k = 0; k < 2*C; k++) { len[k] = std::max(minlen, (int)(free_tiles*wgt[k]/wsum)); used += len[k]; }
+    for (int k = 0; used < free_tiles; k = (k + 1)%(2*C)) { len[k]++; used++; }
+    for (int k = 0; used > free_tiles; k = (k + 1)%(2*C)) if (len[k] > minlen) { len[k]--; used--; }
+    int t = 0;
+    for (int c = 0; c < C; c++) {
+      CellGeom g{}; g.has_qa = c > 0; g.has_qb = c < C - 1;
+      g.q0 = t*TILE; if (c > 0) t += WB;
+      g.a0 = t*TILE; t += len[2*c];
+      g.m0 = t*TILE; t += WB;
+      t += len[2*c + 1];
+      g.b1 = t*TILE;
+      P.cells.push_back(g);
+      BandProb a{}; a.NT = len[2*c] + WB; a.Kend = len[2*c]; a.spiked = g.has_qa; a.TPC = WB + 1 + (a.spiked ? WB : 0);
+      BandProb b{}; b.NT = len[2*c + 1] + WB; b.Kend = len[2*c + 1]; b.spiked = g.has_qb; b.TPC = WB + 1 + (b.spiked ? WB : 0);
+      P.chains.push_back(a); P.chains.push_back(b);
+    }
+    if (t != NT) return -1;
+    P.WBcs = std::max(1, (C >= 2 ? 3 : 1)*WB - 1); P.TPCcs = P.WBcs + 1;
+    for (int c = 0; c < C; c++) {
+      BandProb s{}; s.NT = WB*(1 + P.cells[c].has_qa + P.cells[c].has_qb); s.Kend = WB; s.TPC = P.TPCcs; s.spiked = 0;
+      P.cs.push_back(s);
+    }
+    P.NTgq = (C - 1)*WB;
+    if (C >= 2) {
+      P.WBgq = std::max(1, std::min(2*WB - 1, P.NTgq - 1)); P.TPCgq = P.WBgq + 1;
+      BandProb gq{}; gq.NT = P.NTgq; gq.Kend = P.NTgq; gq.TPC = P.TPCgq; gq.spiked = 0;
+      P.gq.push_back(gq);
+    } else { P.WBgq = 0; P.TPCgq = 1; }
   }
-  if (getenv("DYNOBA_SPINE_DBG")) {
-    long long hd[16]; cudaStreamSynchronize(s); cudaMemcpyFromSymbol(hd, g_spine_dbg, sizeof(hd));
-    const char* nm2[12] = {"potrf", "store+stage+flag D", "barA", "wait+load Dnext half", "barB (trsm)", "gemm half + stage", "barC + reload", "-", "-", "-", "-", "loop"};
-    const char* nm3[12] = {"A0 potrf", "A0 wait L stored", "A0 wait D input", "A0 X1 rank-8 (+waits)", "A1 potrf", "A1 wait L stored", "A1 wait D input", "A1 X1 rank-8 (+waits)", "A0 potrf: stage + block load", "A0 potrf: 8x8 factor", "A0 potrf: publish + trailing", "-"};
-    const char** nm = g_spine_ver == 2 ? nm2 : nm3;
-    for (int i = 0; i < 12; i++) fprintf(stderr, "[spine] %-22s %10.3f ms\n", nm[i], hd[i]/1.965e6);
+  P.nchain = (int)P.chains.size(); P.ncs = (int)P.cs.size();
+  P.local_cells.clear();
+  for (int c = 0; c < C; c++) if (c*world/C == rank) P.local_cells.push_back(c);
+  // ---- sizes.  doubles: [accumulated: chain tiles | ff | rhs + gf] [cs tiles + rhs] [gq tiles + rhs] [linv] [spike scratch]
+  size_t nd = 0, ni = 0;
+  auto take = [&](size_t cnt) { const size_t o = nd; nd += align_up(cnt, 32); return o; };
+  for (auto& p : P.chains) take((size_t)p.NT*p.TPC*TILE2);
+  for (auto& p : P.chains) if (p.spiked) take((size_t)WB*WB*TILE2);
+  for (auto& p : P.chains) { take((size_t)p.NT*TILE); if (p.spiked) take((size_t)WB*TILE); }
+  P.acc_count = nd;
+  for (auto& p : P.cs) { take((size_t)p.NT*p.TPC*TILE2); take((size_t)p.NT*TILE); }
+  for (auto& p : P.gq) { take((size_t)p.NT*p.TPC*TILE2 + (size_t)p.NT*TILE); }
+  for (auto& p : P.chains) take((size_t)std::max(p.Kend, 1)*TILE2);
+  for (auto& p : P.cs) take((size_t)p.Kend*TILE2);
+  for (auto& p : P.gq) take((size_t)p.Kend*TILE2);
+  int maxk = 1; for (auto& p : P.chains) maxk = std::max(maxk, p.Kend);
+  take((size_t)P.nchain*((maxk + SF_CH - 1)/SF_CH)*std::max(WB, 1)*TILE);
+  P.n_doubles = nd;
+  auto nflags = [&](const BandProb& p, int wb) { return align_up((size_t)2*p.NT*p.TPC + p.NT + (size_t)wb*wb, 32); };
+  for (auto& p : P.chains) ni += nflags(p, WB);
+  for (auto& p : P.cs) ni += nflags(p, P.WBcs);
+  for (auto& p : P.gq) ni += nflags(p, P.WBgq);
+  P.n_ints = ni;
+  P.n_desc_bytes = align_up(sizeof(BandProb)*(size_t)(2*P.nchain + 2*P.ncs + 1) + sizeof(CellGeom)*(size_t)std::max(C, 1) + sizeof(int)*(size_t)std::max(C, 1), 256) + 1024;
+  return 0;
+}
+
+void band_plan_bind(BandPlan& P, double* dbase, int* ibase, void* desc_base, double* dp) {
+  DevBand& B = P.band;
+  const int WB = B.WB, C = B.ncell;
+  size_t nd = 0, ni = 0;
+  auto take = [&](size_t cnt) { double* p = dbase + nd; nd += align_up(cnt, 32); return p; };
+  auto takei = [&](const BandProb& p, int wb) { int* q = ibase + ni; ni += align_up((size_t)2*p.NT*p.TPC + p.NT + (size_t)wb*wb, 32); return q; };
+  P.reduce_ranges.clear();
+  for (auto& p : P.chains) p.tiles = take((size_t)p.NT*p.TPC*TILE2);
+  for (auto& p : P.chains) p.ff = p.spiked ? take((size_t)WB*WB*TILE2) : nullptr;
+  P.rhs_region = dbase + nd;
+  for (auto& p : P.chains) { p.rhs = take((size_t)p.NT*TILE); p.gf = p.spiked ? take((size_t)WB*TILE) : nullptr; }
+  P.rhs_count = (size_t)(dbase + nd - P.rhs_region);
+  B.acc = dbase; B.acc_count = nd;
+  for (auto& p : P.cs) { p.tiles = take((size_t)p.NT*p.TPC*TILE2); p.rhs = take((size_t)p.NT*TILE); p.ff = nullptr; p.gf = nullptr; }
+  P.gq_base = nullptr; P.gq_count = 0;
+  for (auto& p : P.gq) { P.gq_count = (size_t)p.NT*p.TPC*TILE2 + (size_t)p.NT*TILE; P.gq_base = take(P.gq_count); p.tiles = P.gq_base; p.rhs = P.gq_base + (size_t)p.NT*p.TPC*TILE2; p.ff = nullptr; p.gf = nullptr; }
+  for (auto& p : P.chains) p.linv = take((size_t)std::max(p.Kend, 1)*TILE2);
+  for (auto& p : P.cs) p.linv = take((size_t)p.Kend*TILE2);
+  for (auto& p : P.gq) p.linv = take((size_t)p.Kend*TILE2);
+  int maxk = 1; for (auto& p : P.chains) maxk = std::max(maxk, p.Kend);
+  P.spike_scratch = take((size_t)P.nchain*((maxk + SF_CH - 1)/SF_CH)*std::max(WB, 1)*TILE);
+  for (auto& p : P.chains) p.flags = takei(p, WB);
+  for (auto& p : P.cs) p.flags = takei(p, P.WBcs);
+  for (auto& p : P.gq) p.flags = takei(p, P.WBgq);
+  P.flags_base = ibase; P.flags_count = ni;
+  // multi-GPU: the accumulated tiles / ff of a cell are summed at its owner
+  for (int c = 0; c < C; c++) {
+    const int owner = c*P.world/C;
+    const BandProb &a = P.chains[2*c], &b = P.chains[2*c + 1];
+    P.reduce_ranges.push_back({ a.tiles, (size_t)(b.tiles + (size_t)b.NT*b.TPC*TILE2 - a.tiles), owner });
+    if (a.spiked) P.reduce_ranges.push_back({ a.ff, (size_t)WB*WB*TILE2, owner });
+    if (b.spiked) P.reduce_ranges.push_back({ b.ff, (size_t)WB*WB*TILE2, owner });
+  }
+  // ---- descriptors -> device
+  std::vector<BandProb> lc, lcs;
+  for (int c : P.local_cells) { lc.push_back(P.chains[2*c]); lc.push_back(P.chains[2*c + 1]); lcs.push_back(P.cs[c]); }
+  if (C == 0) lc.push_back(P.chains[0]);
+  P.d_local_chains_host = lc; P.d_local_cs_host = lcs; P.n_local_chains = (int)lc.size(); P.n_local_cs = (int)lcs.size();
+  char* d = (char*)desc_base; size_t off = 0;
+  auto put = [&](const void* src, size_t bytes) { void* q = d + off; if (bytes) cudaMemcpy(q, src, bytes, cudaMemcpyHostToDevice); off += align_up(std::max<size_t>(bytes, 1), 16); return q; };
+  P.d_chains = (BandProb*)put(P.chains.data(), sizeof(BandProb)*P.chains.size());
+  P.d_cs = (BandProb*)put(P.cs.data(), sizeof(BandProb)*P.cs.size());
+  P.d_gq = (BandProb*)put(P.gq.data(), sizeof(BandProb)*P.gq.size());
+  P.d_local_chains = (BandProb*)put(lc.data(), sizeof(BandProb)*lc.size());
+  P.d_local_cs = (BandProb*)put(lcs.data(), sizeof(BandProb)*lcs.size());
+  const CellGeom* dcells = (const CellGeom*)put(P.cells.data(), sizeof(CellGeom)*P.cells.size());
+  P.d_local_cell_ids = (int*)put(P.local_cells.data(), sizeof(int)*P.local_cells.size());
+  B.chains = P.d_chains; B.cells = dcells;
+  B.dp = C == 0 ? P.chains[0].rhs : dp;
+}
+
+static CellRefs cell_refs(const BandPlan& P) { return CellRefs{ P.d_chains, P.d_cs, P.d_gq, P.band.cells, P.d_local_cell_ids, P.band.WB }; }
+
+int launch_band_factor(const BandPlan& P, int* fail, cudaStream_t s) {
+  const DevBand& B = P.band; const int WB = B.WB, C = B.ncell;
+  int launches = 0;
+  launches += chol_launch(P.d_local_chains, P.d_local_chains_host.data(), P.n_local_chains, WB, fail, s);
+  if (P.n_local_chains) { int maxk = 1; for (auto& p : P.d_local_chains_host) maxk = std::max(maxk, p.Kend);
+    diag_inverse_kernel<<<dim3((maxk + 3)/4, P.n_local_chains), 128, 0, s>>>(P.d_local_chains); launches++; }
+  if (C == 0) return launches;
+  const int nloc = (int)P.local_cells.size();
+  if (nloc) {
+    bool any_spiked = false; int maxk = 1;
+    for (auto& p : P.d_local_chains_host) { any_spiked |= p.spiked != 0; maxk = std::max(maxk, p.Kend); }
+    if (any_spiked) {
+      int allmaxk = 1; for (auto& p : P.chains) allmaxk = std::max(allmaxk, p.Kend);
+      const int maxchunks = (allmaxk + SF_CH - 1)/SF_CH;
+      spike_forward_partial_kernel<<<dim3((maxk + SF_CH - 1)/SF_CH, P.n_local_chains), 256, 0, s>>>(P.d_local_chains, WB, P.spike_scratch, maxchunks);
+      spike_forward_reduce_kernel<<<dim3((WB*TILE + 255)/256, P.n_local_chains), 256, 0, s>>>(P.d_local_chains, WB, P.spike_scratch, maxchunks);
+      launches += 2;
+    }
+    const int ntcs = WB*(C >= 2 ? 3 : 1);
+    cs_assemble_kernel<<<dim3(ntcs*P.TPCcs, nloc), 256, 0, s>>>(cell_refs(P), P.TPCcs); launches++;
+    launches += chol_launch(P.d_local_cs, P.d_local_cs_host.data(), P.n_local_cs, P.WBcs, fail, s);
+    diag_inverse_kernel<<<dim3((WB + 3)/4, P.n_local_cs), 128, 0, s>>>(P.d_local_cs); launches++;
+  }
+  if (C >= 2) {
+    cudaMemsetAsync(P.gq_base, 0, P.gq_count*sizeof(double), s);
+    for (int c : P.local_cells) { gq_add_cell_kernel<<<148, 256, 0, s>>>(cell_refs(P), c, P.TPCgq); launches++; }
   }
   return launches;
 }
 
-int launch_band_solve(const DevBand& B, const double* linv, cudaStream_t s) {
-  const size_t smem = ((size_t)(B.WB + 2)*TILE + (size_t)(2*BW_TW + 4*BW_CL + 1)*TILE + 6*TILE*BW_PS)*sizeof(double);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(band_backward_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024); attr = true; }
-  const int nthr = (BW_TW + 1)*32;
-  if (!B.two) {
-    BackJob job; job.WB = B.WB; job.p[0] = BackProb{ B.tiles, B.rhs, linv, B.NT, B.NT, 0 }; job.p[1] = job.p[0];
-    band_backward_cluster_kernel<<<BW_CL, nthr, smem, s>>>(job);          // forward sweep: folded into the factorisation
-    return 1;
+int launch_band_top(const BandPlan& P, int* fail, cudaStream_t s) {
+  const DevBand& B = P.band; const int WB = B.WB, C = B.ncell;
+  int launches = 0;
+  if (C == 0) { launches += back_launch(P.d_local_chains, P.n_local_chains, WB, s); return launches; }
+  const int nloc = (int)P.local_cells.size();
+  if (C >= 2) {
+    launches += chol_launch(P.d_gq, P.gq.data(), 1, P.WBgq, fail, s);                  // boundary system (replicated on every rank)
+    diag_inverse_kernel<<<dim3((P.NTgq + 3)/4, 1), 128, 0, s>>>(P.d_gq); launches++;
+    launches += back_launch(P.d_gq, 1, P.WBgq, s);
+    if (nloc) { gq_scatter_kernel<<<dim3(8, nloc), 256, 0, s>>>(cell_refs(P)); launches++; }
   }
-  const int NTA = B.NTA, NTB = B.NTB, KmA = B.split_lo/TILE, KmB = NTB - (B.split_hi - B.split_lo)/TILE;
-  BackJob mid; mid.WB = B.WB; mid.p[0] = BackProb{ B.tiles, B.rhs, linv, NTA, NTA, KmA }; mid.p[1] = mid.p[0];
-  band_backward_cluster_kernel<<<BW_CL, nthr, smem, s>>>(mid);            // x of the middle separator
-  prime_back_kernel<<<8, 256, 0, s>>>(B);
-  BackJob job; job.WB = B.WB;
-  job.p[0] = BackProb{ B.tiles, B.rhs, linv, NTA, KmA, 0 };
-  job.p[1] = BackProb{ B.tiles2, B.rhs2, linv + (size_t)NTA*TILE2, NTB, KmB, 0 };
-  band_backward_cluster_kernel<<<2*BW_CL, nthr, smem, s>>>(job);          // both halves, away from the middle
-  gather_solution_kernel<<<148, 256, 0, s>>>(B);
-  return 4;
+  if (P.world > 1) cudaMemsetAsync(B.dp, 0, (size_t)B.n_pad*sizeof(double), s);        // the owners' segments are summed by the caller
+  if (!nloc) return launches;
+  launches += back_launch(P.d_local_cs, P.n_local_cs, P.WBcs, s);                      // x_M
+  cs_to_chain_kernel<<<dim3(8, nloc), 256, 0, s>>>(cell_refs(P)); launches++;
+  bool any_spiked = false; int maxk = 1;
+  for (auto& p : P.d_local_chains_host) { any_spiked |= p.spiked != 0; maxk = std::max(maxk, p.Kend); }
+  if (any_spiked) { spike_backward_kernel<<<dim3((maxk + 7)/8, P.n_local_chains), 256, (size_t)WB*TILE*sizeof(double), s>>>(P.d_local_chains, WB); launches++; }
+  launches += back_launch(P.d_local_chains, P.n_local_chains, WB, s);
+  gather_dp_kernel<<<dim3(64, nloc), 256, 0, s>>>(cell_refs(P), B.dp); launches++;
+  return launches;
 }
 
 }  // namespace dynoba

@@ -58,12 +58,10 @@ __device__ __forceinline__ bool spd_inverse(const double* V, double* Vi) {
   }
 }
 
-__global__ void band_clear_kernel(DevBand B, double lambda, int add_damping) {
-  const size_t total = B.tile_count*TILE2;
+__global__ void band_clear_kernel(DevBand B) {
   const size_t stride = (size_t)gridDim.x*blockDim.x;
-  for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < total; i += stride) B.tiles[i] = 0.0;
-  const size_t nrhs = B.two ? (size_t)(B.NTA + B.NTB)*TILE : (size_t)B.n_pad;   // rhs2 follows rhs
-  for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < nrhs; i += stride) B.rhs[i] = 0.0;
+  double2* a = reinterpret_cast<double2*>(B.acc);           // (every buffer of the region is padded to 32 doubles)
+  for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < B.acc_count/2; i += stride) a[i] = make_double2(0.0, 0.0);
 }
 __global__ void band_diag_kernel(DevBand B, double lambda, int add_damping) {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -72,7 +70,7 @@ __global__ void band_diag_kernel(DevBand B, double lambda, int add_damping) {
   *band_at(B, i, i) = v;
 }
 int launch_band_clear(const DevBand& B, double lambda, int add_damping, cudaStream_t s) {
-  band_clear_kernel<<<148*8, 256, 0, s>>>(B, lambda, add_damping);
+  band_clear_kernel<<<148*8, 256, 0, s>>>(B);
   band_diag_kernel<<<(B.n_pad + 255)/256, 256, 0, s>>>(B, lambda, add_damping);
   return 2;
 }

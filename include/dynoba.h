@@ -78,6 +78,9 @@ typedef struct {
 /* Sum-all-reduce of n doubles at device pointer `dev` on CUDA stream `stream`, in place.  Supplied by the
  * multi-GPU host (bench.py passes torch.distributed.all_reduce over NCCL).  Return 0 on success. */
 typedef int (*dynoba_allreduce_fn)(void* ctx, double* dev, size_t n, void* stream);
+/* Sum-reduce of n doubles at device pointer `dev` to rank `root` (in place there; the other ranks' buffers are left
+ * unspecified), on CUDA stream `stream`.  bench.py passes torch.distributed.reduce over NCCL.  Return 0 on success. */
+typedef int (*dynoba_reduce_fn)(void* ctx, double* dev, size_t n, int root, void* stream);
 
 /* ---- lifecycle */
 int dynoba_version(void);
@@ -109,6 +112,20 @@ int dynoba_set_pose_order(dynoba_handle h, int64_t n, const int32_t* rank);
 /* Multi-GPU: rank/world of the landmark shard held by this handle and the all-reduce used for the reduced
  * system and the scalar sums.  min_bandwidth forces a common band layout on all ranks (0 = local). */
 int dynoba_set_shard(dynoba_handle h, int rank, int world, dynoba_allreduce_fn fn, void* ctx, int min_bandwidth);
+/* Multi-GPU, optional: with a reduce callback the reduced solve itself is distributed -- the time axis of the banded
+ * reduced system is cut into cells (one per rank by default), every rank factors its own cells and only receives their
+ * tiles (a reduce per cell instead of an all-reduce of the whole band); the small boundary-separator system and the
+ * pose update are all-reduced.  Without it the reduced system is all-reduced and solved on every rank. */
+int dynoba_set_reduce(dynoba_handle h, dynoba_reduce_fn fn, void* ctx);
+/* Number of cells the reduced solve is cut into (nested dissection in time; every cell is eliminated by two concurrent
+ * chains, so 2*ncells chains run at once).  0 = automatic (one per rank; on one GPU by system length), -1 = one plain
+ * band factorisation.  The request is clamped to what the system's length allows.  GTSAM equivalent: the elimination
+ * ordering of LevenbergMarquardtParams (RegularBackendModule.cc:405-419 leaves it at COLAMD). */
+int dynoba_set_partition(dynoba_handle h, int ncells);
+/* Performance parameters of the reduced solve (results do not depend on them): "outer_weight" = relative length of the
+ * two end chains, which carry no spike (default 1.6 on one GPU, 1 otherwise); "band_ctas_per_chain" = worker CTAs that
+ * serve the band tiles of one chain (the others stream the spike updates; process-wide). */
+int dynoba_set_tuning(dynoba_handle h, const char* name, double value);
 /* Builds the device layout (sorting, CSR, band structure) and uploads.  Called implicitly by the
  * compute entry points; exposed so that uploads can be timed separately. */
 int dynoba_finalize(dynoba_handle h);

@@ -212,6 +212,36 @@ def test_two_directional_factorisation_long_trajectory():
     assert abs(st["error_final"] - so["error_final"]) <= 1e-5*so["error_final"]
 
 
+def test_cell_partition_matches_plain_band():
+    """Nested dissection in time of the reduced solve: P = 2, 4, 8, 16 concurrent chains (1, 2, 4, 8 cells, with spike
+    fill-in next to the boundary separators) against the oracle's plain band Cholesky and against the one-chain kernel."""
+    p = synth.make_problem(n_frames=1200, n_objects=3, n_static=6000, n_dynamic=1500, formulation="hybrid", seed=5,
+                           object_span=(200, 300), max_static_age=6, max_dynamic_age=6)
+    o = _oracle(p)
+    lam = 1e-4
+    rc, do = o.schur_solve(lam)
+    assert rc == 0
+    steps = {}
+    for cells in (-1, 1, 2, 4, 8):
+        s = _solver(p); s.set_partition(cells)
+        info = s.info()
+        wb = (info["bandwidth"] + 31)//32
+        assert info["reduced_dim"]//32 >= (4*8 - 1)*max(wb, 2), "graph too short for 8 cells"
+        d = s.solve(lam)
+        assert np.linalg.norm(d - do) <= 1e-6*np.linalg.norm(do), cells
+        steps[cells] = d
+        s.close()
+    for cells in (1, 2, 4, 8):
+        assert np.linalg.norm(steps[cells] - steps[-1]) <= 1e-7*np.linalg.norm(steps[-1]), cells
+    so = o.optimize(max_iterations=5)
+    for cells in (2, 8):
+        s = _solver(p); s.set_partition(cells)
+        st = s.optimize(max_iterations=5)
+        assert st["iterations"] == so["iterations"] and st["inner_iterations"] == so["inner_iterations"], cells
+        assert abs(st["error_final"] - so["error_final"]) <= 1e-5*so["error_final"], cells
+        s.close()
+
+
 def _permuted(p, seed, landmark_runs):
     """The same graph with its factors listed in another order: whole landmark runs shuffled (the order DynOSAM's
     formulations produce up to the order of the landmarks -- the run-based sort of the symbolic phase) or every factor

@@ -120,14 +120,25 @@ def test_bandwidth_rule_matches_oracle():
     assert bench.problem_bandwidth(p) == st["bandwidth"]
 
 
-def test_landmark_sharding_partitions_the_graph():
+@pytest.mark.parametrize("formulation", ["hybrid", "wcme"])
+def test_landmark_sharding_partitions_the_graph(formulation):
+    """Every factor lands on exactly one rank and a factor never refers to a landmark of another rank: the points of a
+    world-centric tracklet chain (joined by ternary factors) stay together."""
     import bench
-    p = synth.make_problem(n_frames=30, n_objects=3, n_static=300, n_dynamic=150, seed=9)
+    p = synth.make_problem(n_frames=30, n_objects=3, n_static=300, n_dynamic=150, seed=9, formulation=formulation)
     shards = [bench.shard_problem(p, r, 4) for r in range(4)]
     assert sum(s.n_point for s in shards) == p.n_point
-    for t in (P.POSE2POINT3, P.HYBRID3):
+    for t in set(b.type for b in p.blocks):
         assert sum(b.n for s in shards for b in s.blocks if b.type == t) == sum(b.n for b in p.blocks if b.type == t)
-    assert sum(b.n for b in shards[1].blocks if b.type in (P.PRIOR6, P.BETWEEN6, P.SMOOTH_HYBRID6)) == 0
+    kept = np.stack([s.meta["kept_points"] for s in shards])
+    assert (kept.sum(0) == 1).all()
+    for s in shards:                       # remapped landmark indices stay inside the shard's own points
+        for b in s.blocks:
+            for k, c in enumerate(P.SLOT_CLASS[b.type]):
+                if c == 1 and b.n:
+                    assert b.idx[:, k].min() >= 0 and b.idx[:, k].max() < s.n_point
+    # the shard of a rank is a slice in time: its landmarks' first frames do not interleave with the next rank's
+    assert np.allclose(sum(s_.n_factors for s_ in shards), p.n_factors)
 
 
 _GLOO_WORKER = r'''
