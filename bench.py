@@ -30,27 +30,53 @@ METRIC = "LM iters/sec on 10k-pose/2M-landmark dynamic BA"
 UNIT = "LM iterations/s"
 
 
-def problem_bandwidth(p: Problem) -> int:
-    """Scalar half-bandwidth of the reduced system in the solver ordering (same rule as libdynoba's finalize)."""
+def _solver_positions(p: Problem) -> np.ndarray:
     order = np.argsort(p.pose_order, kind="stable") if p.pose_order is not None else np.arange(p.n_pose)
     pos = np.empty(p.n_pose, dtype=np.int64); pos[order] = np.arange(p.n_pose)
+    return pos
+
+
+def _point_groups(p: Problem) -> np.ndarray:
+    """Landmark groups as libdynoba's symbolic phase forms them: points joined by a factor with more than one point
+    slot (the points of a WCME / WCPE tracklet chain) are eliminated together.  Returns the group id of every point."""
+    npt = p.n_point
+    edges = []
+    for b in p.blocks:
+        ls = [k for k, c in enumerate(SLOT_CLASS[b.type]) if c == 1]
+        for k in ls[1:]:
+            edges.append(np.stack([b.idx[:, ls[0]], b.idx[:, k]], 1))
+    if not edges or not npt:
+        return np.arange(npt, dtype=np.int64)
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    e = np.concatenate(edges).astype(np.int64)
+    _, group = connected_components(coo_matrix((np.ones(e.shape[0], dtype=np.int8), (e[:, 0], e[:, 1])), shape=(npt, npt)), directed=False)
+    return group.astype(np.int64)
+
+
+def problem_bandwidth(p: Problem) -> int:
+    """Scalar half-bandwidth of the reduced system in the solver ordering (same rule as libdynoba's finalize): the
+    widest spread of pose positions over one landmark group, or over one pose-only factor."""
+    pos = _solver_positions(p)
+    group = _point_groups(p)
+    ng = int(group.max(initial=-1)) + 1
+    gmin = np.full(ng, np.iinfo(np.int64).max); gmax = np.full(ng, -1)
     spread = 0
     for b in p.blocks:
         cls = SLOT_CLASS[b.type]
         pslots = [k for k, c in enumerate(cls) if c == 0]
-        lslots = [k for k, c in enumerate(cls) if c != 0]
+        lslots = [k for k, c in enumerate(cls) if c == 1]
+        if not pslots or not b.n:
+            continue
         pp = pos[b.idx[:, pslots]]
         lo, hi = pp.min(1), pp.max(1)
-        if not lslots:
-            spread = max(spread, int((hi - lo).max(initial=0)))
-            continue
-        lm = b.idx[:, lslots[0]].astype(np.int64)
-        nl = int(lm.max(initial=-1)) + 1
-        gmin = np.full(nl, np.iinfo(np.int64).max); gmax = np.full(nl, -1)
-        np.minimum.at(gmin, lm, lo); np.maximum.at(gmax, lm, hi)
-        ok = gmax >= 0
-        if ok.any():
-            spread = max(spread, int((gmax[ok] - gmin[ok]).max()))
+        spread = max(spread, int((hi - lo).max(initial=0)))        # (also the single-factor spread of flow-variable factors)
+        if lslots:
+            g = group[b.idx[:, lslots[0]]]
+            np.minimum.at(gmin, g, lo); np.maximum.at(gmax, g, hi)
+    ok = gmax >= 0
+    if ok.any():
+        spread = max(spread, int((gmax[ok] - gmin[ok]).max()))
     return 6*spread + 5
 
 
@@ -62,22 +88,8 @@ def shard_problem(p: Problem, rank: int, world: int) -> Problem:
     window wide), which is what the library's per-cell reduce moves.  q.meta["kept_points"] = mask of the kept points."""
     if world == 1:
         return p
-    order = np.argsort(p.pose_order, kind="stable") if p.pose_order is not None else np.arange(p.n_pose)
-    pos = np.empty(p.n_pose, dtype=np.int64); pos[order] = np.arange(p.n_pose)
-    npt = p.n_point
-    # ---- landmark groups: connected components over factors with more than one point slot
-    group = np.arange(npt, dtype=np.int64)
-    edges = []
-    for b in p.blocks:
-        ls = [k for k, c in enumerate(SLOT_CLASS[b.type]) if c == 1]
-        for k in ls[1:]:
-            edges.append(np.stack([b.idx[:, ls[0]], b.idx[:, k]], 1))
-    if edges:
-        from scipy.sparse import coo_matrix
-        from scipy.sparse.csgraph import connected_components
-        e = np.concatenate(edges).astype(np.int64)
-        _, group = connected_components(coo_matrix((np.ones(e.shape[0], dtype=np.int8), (e[:, 0], e[:, 1])), shape=(npt, npt)), directed=False)
-        group = group.astype(np.int64)
+    pos = _solver_positions(p)
+    group = _point_groups(p)
     ngroup = int(group.max(initial=-1)) + 1
     first = np.full(ngroup, np.iinfo(np.int64).max)
     for b in p.blocks:

@@ -453,6 +453,20 @@ static int finalize_impl(dynoba_solver* h) {
     if ((rc = dalloc(h, &desc, h->plan.n_desc_bytes))) return rc;
     if (h->plan.band.ncell > 0) { if ((rc = dalloc(h, &dp, (size_t)h->plan.band.n_pad))) return rc; }
     band_plan_bind(h->plan, dbuf, ibuf, desc, dp);
+    if (h->world > 1) {
+      // every rank must have arrived at the same layout (the collectives exchange raw buffers): agree on n and bw.  The sums of
+      // x and x^2 over the ranks equal world*x and world*x^2 only when all ranks hold the same x -- every rank sees the same sums,
+      // so a disagreement is reported everywhere instead of hanging a collective.
+      const double mine[4] = { (double)h->band.n, (double)h->band.n*(double)h->band.n, (double)h->band.bw, (double)h->band.bw*(double)h->band.bw };
+      double got[4];
+      CK(cudaMemcpyAsync(dbuf, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+      if (h->allreduce(h->ar_ctx, dbuf, 4, (void*)h->stream) != 0) { h->err = "all-reduce callback failed"; return DYNOBA_ERR_COMM; }
+      CK(cudaMemcpyAsync(got, dbuf, sizeof(got), cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+      for (int k = 0; k < 4; k++) if (got[k] != h->world*mine[k]) {
+        h->err = "ranks disagree on the reduced system's size or bandwidth: pass the bandwidth of the unsharded graph as min_bandwidth to dynoba_set_shard";
+        return DYNOBA_ERR_BAD_ARG;
+      }
+    }
   }
   DevBand& B = h->band;
   // ---- variables

@@ -15,7 +15,8 @@ from oracle import oracle as O
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+import datetime
+dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=90))
 
 
 def _tensor(dev, n):
@@ -42,6 +43,7 @@ cases = [("C1 hybrid, replicated solve", synth.make_config("C1"), False, 0),
          ("1200-frame graph, distributed solve, one cell per rank", synth.make_problem(**long_kw), True, 0),
          ("1200-frame graph, distributed solve, two cells per rank", synth.make_problem(**long_kw), True, 2*world)]
 for name, p, distributed, cells in cases:
+    print(f"[rank {rank}] case: {name}", file=sys.stderr, flush=True)
     bw = bench.problem_bandwidth(p)
     sh = bench.shard_problem(p, rank, world)
     s = Solver(sh, device=local); s.set_shard(rank, world, allreduce, bw)

@@ -112,12 +112,16 @@ def test_oracle_lm_reduces_error_and_is_deterministic():
     assert r1["iterations"] == r2["iterations"] and abs(r1["error_final"] - r2["error_final"]) <= 1e-9*r1["error_final"]
 
 
-def test_bandwidth_rule_matches_oracle():
+@pytest.mark.parametrize("formulation,n_static", [("hybrid", 300), ("wcme", 300), ("wcme", 0)])
+def test_bandwidth_rule_matches_oracle(formulation, n_static):
+    """bench.problem_bandwidth (what the multi-GPU ranks pass as the common min_bandwidth) follows the symbolic phase's
+    rule, incl. world-centric tracklet chains, whose points form ONE landmark group."""
     import bench
     from oracle import oracle as O
-    p = synth.make_problem(n_frames=30, n_objects=3, n_static=300, n_dynamic=150, seed=9)
+    p = synth.make_problem(n_frames=30, n_objects=3, n_static=n_static, n_dynamic=150, seed=9, formulation=formulation)
     st = O.OracleProblem(p).optimize(max_iterations=1)
     assert bench.problem_bandwidth(p) == st["bandwidth"]
+    assert max(bench.problem_bandwidth(bench.shard_problem(p, r, 2)) for r in range(2)) <= st["bandwidth"]
 
 
 @pytest.mark.parametrize("formulation", ["hybrid", "wcme"])
