@@ -166,61 +166,100 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_rate(cfg_name, formulation, seed, sample_scale, iters, threads):
-    """LM iterations/s of the CPU oracle (port of the reference's GTSAM-4.2 path) on a bounded sample of the
-    workload, extrapolated linearly in the number of key-frames (every stage of an iteration is linear in it)."""
+def cpu_oracle_rate(cfg_name, formulation, seed, scale, iters, threads):
+    """`iters` LM iterations of the CPU oracle (port of the reference's GTSAM-4.2 path) on the named config at `scale`
+    (1.0 = the stated workload, no extrapolation).  Returns the measured rate and the chi^2 trace ends."""
     from oracle import oracle as O
     os.environ["OMP_NUM_THREADS"] = str(threads)
-    ps = synth.make_config(cfg_name, formulation=formulation, seed=seed, scale=sample_scale)
+    ps = synth.make_config(cfg_name, formulation=formulation, seed=seed, scale=scale)
     o = O.OracleProblem(ps)
     t0 = time.perf_counter()
     st = o.optimize(max_iterations=iters, rel_tol=0.0, abs_tol=0.0)
     dt = time.perf_counter() - t0
-    done = max(st["iterations"], 1)
-    rate_sample = done/dt
-    return dict(rate=rate_sample*sample_scale, rate_sample=rate_sample, seconds=dt, iterations=st["iterations"],
-                inner=st["inner_iterations"], n_factors=ps.n_factors, frames=ps.meta["n_frames"],
+    return dict(rate=max(st["iterations"], 1)/dt, seconds=dt, iterations=st["iterations"], inner=st["inner_iterations"],
+                error_initial=st["error_initial"], error_final=st["error_final"], n_factors=ps.n_factors, frames=ps.meta["n_frames"],
                 stats={k: st[k] for k in ("t_linearize", "t_schur", "t_solve", "t_backsub", "t_error")})
 
 
-def cpu_oracle_best(cfg_name, formulation, seed, sample_scale, iters):
-    """The CPU arm in a clean process, at the thread count that serves it best (the box's OpenMP scaling depends on
-    what the container is really allowed to use): probes {8, 16, 32, all} threads with one iteration, then times
-    `iters` iterations at the fastest setting."""
+def _cpu_run(cfg_name, formulation, seed, scale, iters, threads, timeout):
+    """cpu_oracle_rate in a clean process (own OpenMP runtime, no CUDA context)."""
+    code = ("import json,sys; sys.path.insert(0, %r); import bench; "
+            "print(json.dumps(bench.cpu_oracle_rate(%r, %r, %d, %r, %d, %d)))" % (ROOT, cfg_name, formulation, seed, scale, iters, threads))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads)); env.pop("OMP_PROC_BIND", None)
+    try:
+        pr = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=timeout)
+        return json.loads(pr.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+_THREADS_FILE = os.path.join("/tmp", "dynoba_cpu_threads.json")
+
+
+def cpu_threads(cfg_name, formulation, seed):
+    """Thread count of the CPU legs: the fastest of {8, 16, 32, all} on a 1/50 time slice of the workload (the box's
+    OpenMP scaling depends on what the container is really allowed to use).  Chosen once per box and reused by both CPU
+    legs (`--impl reference` and the cpu_baseline of the product arm) through a file in /tmp."""
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        d = json.load(open(_THREADS_FILE))
+        if d.get("ncpu") == ncpu and d.get("config") == [cfg_name, formulation]:
+            return int(d["threads"]), d["probed"]
+    except Exception:
+        pass
     cands = sorted({t for t in (8, 16, 32, ncpu) if t <= ncpu} or {ncpu})
-    def run(threads, it, timeout):
-        code = ("import json,sys; sys.path.insert(0, %r); import bench; "
-                "print(json.dumps(bench.cpu_oracle_rate(%r, %r, %d, %r, %d, %d)))" % (ROOT, cfg_name, formulation, seed, sample_scale, it, threads))
-        env = dict(os.environ, OMP_NUM_THREADS=str(threads)); env.pop("OMP_PROC_BIND", None)
-        try:
-            pr = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=timeout)
-            return json.loads(pr.stdout.strip().splitlines()[-1])
-        except Exception:
-            return None
     best_t, best_rate = cands[0], -1.0
     for t in cands:
-        r = run(t, 1, 120)
+        r = _cpu_run(cfg_name, formulation, seed, 0.02, 1, t, 120)
         if r and r["rate"] > best_rate:
             best_t, best_rate = t, r["rate"]
-    r = run(best_t, iters, 600)
+    try:
+        json.dump({"ncpu": ncpu, "config": [cfg_name, formulation], "threads": best_t, "probed": cands}, open(_THREADS_FILE, "w"))
+    except Exception:
+        pass
+    return best_t, cands
+
+
+def cpu_oracle_leg(cfg_name, formulation, seed, scale, iters):
+    threads, probed = cpu_threads(cfg_name, formulation, seed)
+    r = _cpu_run(cfg_name, formulation, seed, scale, iters, threads, 1500)
     if r is None:
-        r = dict(rate=best_rate, rate_sample=best_rate/sample_scale, seconds=float("nan"), iterations=0, inner=0, n_factors=0, frames=0, stats={})
-    r["threads"] = best_t; r["probed"] = cands
+        r = dict(rate=float("nan"), seconds=float("nan"), iterations=0, inner=0, error_initial=float("nan"), error_final=float("nan"),
+                 n_factors=0, frames=0, stats={})
+    r["threads"] = threads; r["probed"] = probed
+    r["sample"] = (f"{cfg_name}{'' if scale == 1.0 else f' at {scale:g} scale'} ({r['frames']} key-frames, {r['n_factors']} factors): "
+                   f"{r['iterations']} LM iteration(s), {r['inner']} damped solves, in {r['seconds']:.1f} s on {threads} threads "
+                   f"(fastest of {probed} on a 1/50 slice); no extrapolation")
     return r
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant Jacobian-build kernel, from the ncu --set full
-# capture summarised in profiles/r01_final.md (a counter value cannot be measured inside a timed run).  Only valid for the
-# exact launch that was profiled: C5 at full scale on one GPU; anything else reports null.
-NCU_TRAFFIC = {("C5", "hybrid", 5, 11376204): 577.77e6 + 4309.57e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant Jacobian-build kernel, from an `ncu --set full`
+# capture of this very launch (a counter value cannot be measured inside a timed run); the capture is named next to it.
+# Only valid for the exact launch that was profiled: C5 at full scale on one GPU; anything else reports null.
+NCU_TRAFFIC = {("C5", "hybrid", 5, 11376204): (577.77e6 + 4309.57e6, "profiles/r01_final.md (ncu --set full of the same launch)")}
 
 
 def ncu_traffic(args, world, blk):
     if world != 1 or args.scale != 1.0:
-        return None
+        return None, None
     v = NCU_TRAFFIC.get((args.config, args.formulation, int(blk.type), int(blk.n)))
-    return float(v) if v else None
+    return (float(v[0]), v[1]) if v else (None, None)
+
+
+def quick_config_rate(cfg_name, formulation, seed, device, steps=3):
+    """LM iterations/s of another BASELINE config on one GPU (graph resident, device-timed), for the `configs` object."""
+    from dynosam_b200.binding import Solver, default_params
+    p = synth.make_config(cfg_name, formulation=formulation, seed=seed)
+    s = Solver(p, device=device)
+    prm = dict(relative_error_tol=0.0, absolute_error_tol=0.0)
+    s.optimize(default_params(max_iterations=1, **prm)); s.reset_values()
+    st = s.optimize(default_params(max_iterations=steps, **prm))
+    info = s.info()
+    s.close()
+    return {"workload": f"{cfg_name}: {p.meta['n_frames']} key-frames / {p.meta['n_objects']} objects / {p.n_point} landmarks, {p.n_factors} factors",
+            "value": st["iterations"]/(st["ms_total"]*1e-3), "unit": UNIT, "steps": st["iterations"], "inner_iterations": st["inner_iterations"],
+            "ms_per_step": st["ms_total"]/max(st["iterations"], 1), "chi2": [st["error_initial"], st["error_final"]],
+            "reduced_dim": info["reduced_dim"], "bandwidth": info["bandwidth"]}
 
 
 def main():
@@ -233,9 +272,9 @@ def main():
     ap.add_argument("--formulation", default="hybrid")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--cpu-sample-scale", type=float, default=0.02)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the C2 / C3 / front-end lines of the `configs` object")
     ap.add_argument("--cells", type=int, default=0, help="cells of the reduced solve (0 automatic, -1 plain band)")
     ap.add_argument("--replicated-solve", action="store_true", help="N > 1: all-reduce the reduced system and solve it on every rank")
     ap.add_argument("--tune", default="", help="name=value,... performance parameters (dynoba_set_tuning)")
@@ -246,24 +285,26 @@ def main():
     config = {"workload": f"{args.config}: synthetic {cfg['n_frames']} key-frames / {cfg['n_objects']} objects / "
                           f"{cfg['n_static']} static + {cfg['n_dynamic']} dynamic landmarks, {args.formulation} formulation"
                           + (f", scale {args.scale}" if args.scale != 1.0 else ""),
-              "parallelism": f"landmark-sharded x{world}, replicated reduced solve", "seed": args.seed,
+              "parallelism": (f"landmarks sharded in time x{world}; reduced solve " + ("replicated" if args.replicated_solve else "distributed: one cell of the band per rank, "
+                              "reduce per cell + all-reduce of the boundary system")) if world > 1 else "1 GPU",
+              "seed": args.seed,
               "l2_policy": "working set (Jacobian tiles, GBs) >> 126 MB L2; no explicit flush",
               "noise": "sigma_point 0.2, Huber k 1e-4, LM defaults with rel/abs tol 0 so that exactly K iterations run",
               "timed_region": "LM iterations 1..K from the initial values (after W warm-up iterations and a value reset)"}
-    threads = os.cpu_count() or 1
 
     if args.impl == "reference":
-        # CPU arm: the reference's own toolchain (GTSAM) is absent, so this is the oracle port (cpu_baseline.kind "port")
+        # CPU arm: the reference's own toolchain (GTSAM) is absent, so this is the oracle port (cpu_baseline.kind "port"),
+        # on the stated workload at full size; a step = one LM iteration, at most 3 of them so that the run stays bounded
         if rank != 0:
             return
-        r = cpu_oracle_best(args.config, args.formulation, args.seed, args.cpu_sample_scale*args.scale, max(K, 1))
-        threads = r["threads"]
-        sample = (f"{args.config} at {args.cpu_sample_scale*args.scale:g} scale ({r['frames']} key-frames, {r['n_factors']} factors), "
-                  f"{r['iterations']} LM iterations in {r['seconds']:.1f} s on {threads} threads (best of {r['probed']}); rate scaled linearly in key-frames")
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus, "steps": K,
-                          "warmup": W, "ms_per_step": 1e3/r["rate"], "higher_is_better": True, "scaling": "strong",
+        iters = max(1, min(K, 3))
+        r = cpu_oracle_leg(args.config, args.formulation, args.seed, args.scale, iters)
+        config["timed_region"] = f"LM iterations 1..{iters} from the initial values on the host cores (K capped at 3: one iteration is ~20 s of CPU work)"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["iterations"],
+                          "warmup": 0, "ms_per_step": 1e3/r["rate"], "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                          "inner_iterations": r["inner"], "chi2": [r["error_initial"], r["error_final"]],
+                          "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"], "breakdown_s": r["stats"]},
                           "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -280,20 +321,14 @@ def main():
     bw = problem_bandwidth(full) if world > 1 else 0
     prob = shard_problem(full, rank, world)
 
-    def make_allreduce():
-        def ar(dev, n, stream):
-            class _A:  # noqa
-                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (dev, False), "version": 3, "strides": None}
-            t = torch.as_tensor(_A(), device=f"cuda:{local}")
-            ext = torch.cuda.ExternalStream(stream)
-            with torch.cuda.stream(ext):
-                dist.all_reduce(t)
-        return ar
-
     def _tensor(dev, n):
         class _A:  # noqa
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (dev, False), "version": 3, "strides": None}
         return torch.as_tensor(_A(), device=f"cuda:{local}")
+
+    def allreduce_cb(dev, n, stream):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            dist.all_reduce(_tensor(dev, n))
 
     def reduce_cb(dev, n, root, stream):
         with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
@@ -305,7 +340,7 @@ def main():
         for kv in filter(None, args.tune.split(",")):
             k, v = kv.split("="); s.set_tuning(k, float(v))
         if world > 1:
-            s.set_shard(rank, world, make_allreduce(), bw)
+            s.set_shard(rank, world, allreduce_cb, bw)
             if not args.replicated_solve:
                 s.set_reduce(reduce_cb)
         return s
@@ -314,20 +349,25 @@ def main():
     s = new_solver(prob)
     s.finalize()
     info = s.info()
+    # ---- parity at the stated size (outside the timed region): chi^2 at the initial values and after the first LM
+    # iteration, to be compared with the CPU oracle's first iteration below
+    first = s.optimize(default_params(max_iterations=1, **prm))
+    s.reset_values()
     if W:
         s.optimize(default_params(max_iterations=W, **prm))
         s.reset_values()      # the timed region is LM iterations 1..K from the initial values, like the CPU arm
-    # ---- timed region: exactly K LM iterations, device-timed (CUDA events on the solver's stream), max over ranks
     lin_ms = [s.linearize() for _ in range(3)]                      # whole Jacobian-build pass (after warm-up)
     # the dominant Jacobian-build kernel alone: the factor block with the most algorithmic bytes
     blk_stats = [s.linearize_block(bi) for bi in range(len(prob.blocks))]
     dom = int(np.argmax([b for _, b in blk_stats])) if blk_stats else 0
     dom_ms = [s.linearize_block(dom)[0] for _ in range(7)] if blk_stats else [0.0]
     dom_bytes = blk_stats[dom][1] if blk_stats else 0
+    fp64_peak = s.fp64_rate()
+    # ---- timed region: exactly K LM iterations, device-timed (CUDA events on the solver's stream), max over ranks
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local);
+    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     t0 = time.perf_counter()
@@ -383,7 +423,11 @@ def main():
     pass_ach = info["jacobian_bytes"]/(lin*1e-3)/1e9 if lin > 0 else 0.0
     dms = float(np.median(dom_ms))
     ach = dom_bytes/(dms*1e-3)/1e9 if dms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic(args, world, prob.blocks[dom])
     from dynosam_b200.problem import TYPE_NAMES
+    solves = max(st["inner_iterations"], 1)
+    chol_flops = float(info["reduced_dim"])*float(info["bandwidth"])**2
+    solve_ms = st["ms_factor"]/solves
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done, "warmup": W,
            "ms_per_step": ms_total/max(steps_done, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(st["kernel_launches"]),
@@ -393,19 +437,45 @@ def main():
            "roofline": {"kernel": f"linearize_kernel<{TYPE_NAMES[prob.blocks[dom].type]}> (materialising Jacobian build of the largest factor block, "
                                   f"{prob.blocks[dom].n} factors)",
                         "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                        "frac": ach/peak if peak else None, "traffic": ncu_traffic(args, world, prob.blocks[dom]), "algorithmic_bytes": int(dom_bytes), "ms_per_launch": dms,
+                        "frac": ach/peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                        "algorithmic_bytes": int(dom_bytes), "ms_per_launch": dms,
                         "whole_pass": {"algorithmic_bytes": info["jacobian_bytes"], "ms": lin, "achieved": pass_ach,
                                        "frac": pass_ach/peak if peak else None,
-                                       "note": "all factor blocks of one linearize() incl. the numerically differentiated smoothing factors and the final reduction"}}}
+                                       "note": "all factor blocks of one linearize() incl. the numerically differentiated smoothing factors and the final reduction"}},
+           "reduced_solve": {"kernel": "band_cholesky_dataflow_kernel_v3 + band_backward_cluster_kernel (this rank's share)", "bound": "fp64 latency chain / DMMA",
+                             "flops_per_solve": chol_flops, "note": "n*bw^2 of the plain band Cholesky, whole system; spiked chains do up to 4x that per column",
+                             "ms_per_solve": solve_ms, "achieved_tflops": chol_flops/(solve_ms*1e-3)/1e12 if solve_ms > 0 else None,
+                             "fp64_peak_tflops": fp64_peak, "fp64_peak_source": "dynoba_fp64_rate: register-only DFMA kernel on this GPU (MEASURED_PEAKS.json has no fp64 entry)",
+                             "frac": chol_flops/(solve_ms*1e-3)/1e12/fp64_peak if solve_ms > 0 and fp64_peak > 0 else None}}
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline:
-        r = cpu_oracle_best(args.config, args.formulation, args.seed, args.cpu_sample_scale*args.scale, 4)
-        threads = r["threads"]
-        out["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"{args.config} at {args.cpu_sample_scale*args.scale:g} scale ({r['frames']} key-frames, {r['n_factors']} factors), "
-                                         f"{r['iterations']} LM iterations in {r['seconds']:.1f} s on {threads} threads (best of {r['probed']}); rate scaled linearly in key-frames",
-                               "breakdown_s": r["stats"]}
+        # one LM iteration of the oracle port on the SAME workload at full size: the CPU baseline and, from the same run, the
+        # parity check at the stated size (chi^2 at the initial values and after the first accepted step, 1e-6 relative)
+        r = cpu_oracle_leg(args.config, args.formulation, args.seed, args.scale, 1)
+        out["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"], "breakdown_s": r["stats"]}
+        rel0 = abs(first["error_initial"] - r["error_initial"])/max(abs(r["error_initial"]), 1e-300)
+        rel1 = abs(first["error_final"] - r["error_final"])/max(abs(r["error_final"]), 1e-300)
+        out["parity_check"] = {"workload": config["workload"], "against": "oracle port, same seeded graph, first LM iteration",
+                               "chi2_initial": [first["error_initial"], r["error_initial"], rel0],
+                               "chi2_after_first_iteration": [first["error_final"], r["error_final"], rel1],
+                               "inner_iterations": [first["inner_iterations"], r["inner"]], "tolerance": 1e-6,
+                               "ok": bool(rel0 <= 1e-6 and rel1 <= 1e-6 and first["inner_iterations"] == r["inner"])}
+    if world == 1 and not args.no_extra_configs and args.scale == 1.0:
+        # the other BASELINE configs, short runs (not the headline; the parity of these shapes is covered by tests/)
+        extra = {}
+        for name in ("C2", "C3"):
+            if name != args.config:
+                try:
+                    extra[name] = quick_config_rate(name, args.formulation, args.seed, local)
+                except Exception as e:  # pragma: no cover
+                    extra[name] = {"error": str(e)}
+        try:
+            import bench_frontend
+            extra["C4"] = bench_frontend.run_dynoba(200, 5)
+        except Exception as e:  # pragma: no cover
+            extra["C4"] = {"error": str(e)}
+        out["configs"] = extra
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -82,6 +82,15 @@ def main():
                           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",
                                            "sample": f"{nb} frames: cv2.calcOpticalFlowPyrLK fwd+bwd ({1e3*t_klt:.1f} ms) + numpy dense passes ({1e3*t_dense:.1f} ms)"}}))
         return
+    print(json.dumps(run_dynoba(n, args.warmup)))
+
+
+def run_dynoba(n, warmup):
+    """front-end frames/s through the C ABI (libdynofront) over n frames of the synthetic stream"""
+    frames, static_pts, feats = make_inputs(max(n, warmup) + 1)
+    config = {"workload": f"C4: 1242x375 synthetic stream, {n} frames, 10 objects, {N_STATIC} static KLT points (fwd L3 + bwd L5), "
+                          f"<= {PER_OBJECT} dynamic features/object", "data": "synthetic"}
+    per_frame_bytes = 21*W*H + 2*W*H          # dense passes ~21 B/px (SURVEY 8d) + two gray uploads
     import torch  # noqa: F401  (device selection / presence check only)
     from dynosam_b200.frontend import FeatureTrackerGPU, TrackParams
     t = FeatureTrackerGPU(W, H); prm = TrackParams()
@@ -95,18 +104,18 @@ def main():
         p1, st, _ = t.klt_track(g0, g1, static_pts, 21, 3, 30, 0.03); ms = t.last_ms
         p0, st2, _ = t.klt_track(g1, g0, p1, 21, 5, 30, 0.01)
         return ms + t.last_ms, int(acc.sum()), int(st.sum())
-    for k in range(1, args.warmup + 1):
+    for k in range(1, warmup + 1):
         one(k)
     klt_ms = []; t0 = time.perf_counter()
     for k in range(1, n + 1):
         ms, na, ns = one(k); klt_ms.append(ms)
     dt = time.perf_counter() - t0
     fps = n/dt
-    print(json.dumps({"metric": "frontend fps at 1242x375", "value": fps, "unit": "frames/s", "n_gpus": 1, "frames": n, "ms_per_frame": 1e3*dt/n,
-                      "higher_is_better": True, "dtype": "u8/int16/int32 fixed point + fp32 (OpenCV semantics)", "config": config,
-                      "klt_device_ms_per_frame": float(np.mean(klt_ms)),
-                      "note": "end to end through the C ABI with host images every frame (H2D/D2H inside the timed region); "
-                              f"~{per_frame_bytes/1e6:.1f} MB of image traffic per frame, so a frame is launch/PCIe bound, not HBM bound"}))
+    return {"metric": "frontend fps at 1242x375", "value": fps, "unit": "frames/s", "n_gpus": 1, "frames": n, "ms_per_frame": 1e3*dt/n,
+            "higher_is_better": True, "dtype": "u8/int16/int32 fixed point + fp32 (OpenCV semantics)", "config": config,
+            "klt_device_ms_per_frame": float(np.mean(klt_ms)),
+            "note": "end to end through the C ABI with host images every frame (H2D/D2H inside the timed region); "
+                    f"~{per_frame_bytes/1e6:.1f} MB of image traffic per frame, so a frame is launch/PCIe bound, not HBM bound"}
 
 
 if __name__ == "__main__":

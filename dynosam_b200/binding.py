@@ -24,7 +24,7 @@ REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.
 EXPORTS = [
     "dynoba_version", "dynoba_status_string", "dynoba_last_error", "dynoba_create", "dynoba_destroy",
     "dynoba_lm_default_params", "dynoba_set_variables", "dynoba_set_aux_poses", "dynoba_set_calibration",
-    "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_set_reduce", "dynoba_set_partition", "dynoba_set_tuning", "dynoba_finalize", "dynoba_error",
+    "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_set_reduce", "dynoba_set_partition", "dynoba_set_tuning", "dynoba_fp64_rate", "dynoba_finalize", "dynoba_error",
     "dynoba_optimize", "dynoba_get_variables", "dynoba_get_keys", "dynoba_num_variables", "dynoba_problem_info",
     "dynoba_linearize", "dynoba_linearize_block", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
     "dynoba_get_reduced_system", "dynoba_retract",
@@ -81,6 +81,7 @@ def load():
         L.dynoba_set_reduce.argtypes = [C.c_void_p, REDUCE_FN, C.c_void_p]
         L.dynoba_set_partition.argtypes = [C.c_void_p, C.c_int]
         L.dynoba_set_tuning.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.dynoba_fp64_rate.argtypes = [C.c_void_p, c_dp]
         L.dynoba_finalize.argtypes = [C.c_void_p]
         L.dynoba_error.argtypes = [C.c_void_p, c_dp]
         L.dynoba_optimize.argtypes = [C.c_void_p, C.POINTER(LmParams), C.POINTER(LmStats)]
@@ -197,6 +198,11 @@ class Solver:
 
     def set_tuning(self, name, value):
         self._ck(self.lib.dynoba_set_tuning(self.h, name.encode(), float(value)))
+
+    def fp64_rate(self) -> float:
+        out = C.c_double()
+        self._ck(self.lib.dynoba_fp64_rate(self.h, C.byref(out)))
+        return out.value
 
     def reset_values(self):
         """Re-upload the initial values of the ingested problem (device layout is kept)."""

@@ -801,6 +801,20 @@ static int finalize_impl(dynoba_solver* h) {
 }
 
 // ------------------------------------------------------------------------------------------------ device steps
+// fp64 FMA rate of the device (the roofline denominator of the reduced solve; DMMA m8n8k4 runs at the same rate)
+__global__ void fp64_rate_kernel(double* out, int iters) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = 1.0 + 1e-3*(threadIdx.x + k);
+  const double m = 1.0 - 1e-9, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = fma(a[k], m, c);
+  }
+  double s = 0; for (int k = 0; k < 8; k++) s += a[k];
+  out[(size_t)blockIdx.x*blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void pack_fail_kernel(const int* fail, double* scalars) { scalars[3] = (double)(*fail); for (int i = 0; i < 4; i++) scalars[4 + i] = scalars[i]; }
 
 static int allreduce_dev(dynoba_solver* h, double* p, size_t n) {
@@ -891,6 +905,23 @@ static int read_scalars(dynoba_solver* h, double* out4, bool reduce) {
 }
 
 extern "C" {
+
+int dynoba_fp64_rate(dynoba_handle h, double* tflops) {
+  ARG(h && tflops, "null");
+  cudaSetDevice(h->device);
+  int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int grid = sms*8, block = 256, iters = 1 << 15;
+  double* d; int rc = dalloc(h, &d, (size_t)grid*block, false); if (rc) return rc;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    fp64_rate_kernel<<<grid, block, 0, h->stream>>>(d, iters);
+    CK(cudaEventRecord(h->ev[1], h->stream)); CK(cudaStreamSynchronize(h->stream));
+    float ms; CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); if (rep && ms < best) best = ms;
+  }
+  *tflops = 2.0*8.0*iters*(double)grid*block/(best*1e-3)/1e12;
+  return DYNOBA_OK;
+}
 
 int dynoba_finalize(dynoba_handle h) { if (!h) return DYNOBA_ERR_BAD_ARG; return finalize_impl(h); }
 

@@ -136,6 +136,9 @@ int dynoba_optimize(dynoba_handle h, const dynoba_lm_params* p, dynoba_lm_stats*
 int dynoba_get_variables(dynoba_handle h, int kind, int64_t n, double* out);
 int dynoba_get_keys(dynoba_handle h, int kind, int64_t n, uint64_t* out);
 int dynoba_num_variables(dynoba_handle h, int kind, int64_t* out);
+/* Measured fp64 FMA throughput of the device in TFLOP/s (a few milliseconds of a register-only FMA kernel): the
+ * roofline denominator bench.py prints next to the reduced solve (tcgen05 has no fp64; DMMA runs at the FMA rate). */
+int dynoba_fp64_rate(dynoba_handle h, double* tflops);
 int dynoba_problem_info(dynoba_handle h, int32_t* reduced_dim, int32_t* bandwidth, int64_t* jacobian_bytes);
 
 /* ---- stepwise / parity hooks (what gtsam exposes as graph.linearize(values)) */

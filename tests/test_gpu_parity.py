@@ -212,6 +212,20 @@ def test_two_directional_factorisation_long_trajectory():
     assert abs(st["error_final"] - so["error_final"]) <= 1e-5*so["error_final"]
 
 
+def test_lm_full_c2_matches_oracle():
+    """BASELINE config C2 at full size (2 k key-frames / 500 k static landmarks, 4.2 M factors): chi^2 at the initial
+    values and three LM iterations against the oracle."""
+    p = synth.make_config("C2")
+    assert p.meta["n_frames"] == 2000 and p.n_point == 500_000
+    s = _solver(p); o = _oracle(p)
+    e, eo = s.error(), o.error()
+    assert abs(e - eo) <= REL_CHI2*eo
+    st = s.optimize(max_iterations=3); so = o.optimize(max_iterations=3)
+    assert st["iterations"] == so["iterations"] and st["inner_iterations"] == so["inner_iterations"]
+    assert abs(st["error_final"] - so["error_final"]) <= REL_CHI2*so["error_final"]
+    s.close()
+
+
 def test_cell_partition_matches_plain_band():
     """Nested dissection in time of the reduced solve: P = 2, 4, 8, 16 concurrent chains (1, 2, 4, 8 cells, with spike
     fill-in next to the boundary separators) against the oracle's plain band Cholesky and against the one-chain kernel."""

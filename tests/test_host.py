@@ -194,7 +194,7 @@ def test_bench_reference_arm_contract():
     keys, on a tiny time-slice so that it finishes in seconds; it must not touch the CUDA library."""
     import json, subprocess, sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--cpu-sample-scale", "0.002",
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--scale", "0.002",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
