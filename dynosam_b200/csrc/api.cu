@@ -376,16 +376,17 @@ static int finalize_impl(dynoba_solver* h) {
   for (int64_t i = 0; i < nl; i++) { int x = (int)i; while (uf[x] != x) x = uf[x]; root[i] = x; }      // read-only find
   std::vector<int32_t> gmin(nl, INT32_MAX), gmax(nl, -1), gblk(nl, -1), gcount(nl, 0), gsec(nl, INT32_MAX);
   for (int64_t i = 0; i < nl; i++) gcount[root[i]]++;
-  int spread = 0;
+  int spread = 0, pos_lo = INT32_MAX, pos_hi = -1;     // pos_lo..pos_hi: pose positions this rank's factors touch
   for (size_t bi = 0; bi < h->blocks.size(); bi++) {
     auto& b = h->blocks[bi]; const TypeInfo ti = type_info(b.type);
     b.pose_only = ti.nlmk == 0;
     int lslot = -1; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] != VC_POSE) { lslot = k; break; }
-    int bspread = 0;
-#pragma omp parallel for schedule(static) reduction(max:bspread)
+    int bspread = 0, blo = INT32_MAX, bhi = -1;
+#pragma omp parallel for schedule(static) reduction(max:bspread) reduction(min:blo) reduction(max:bhi)
     for (int64_t i = 0; i < b.n; i++) {
       int lo = INT32_MAX, hi = -1;
       for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE) { const int p = h->pos[b.idx[i*ti.arity + k]]; lo = std::min(lo, p); hi = std::max(hi, p); }
+      blo = std::min(blo, lo); bhi = std::max(bhi, hi);
       if (lslot < 0) { bspread = std::max(bspread, hi - lo); continue; }
       const int g = root[lmk_id(ti.cls[lslot], b.idx[i*ti.arity + lslot])];
       int32_t cur = __atomic_load_n(&gmin[g], __ATOMIC_RELAXED);
@@ -403,7 +404,7 @@ static int finalize_impl(dynoba_solver* h) {
         if (__atomic_compare_exchange_n(&gblk[g], &gb, want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) break;
       }
     }
-    spread = std::max(spread, bspread);
+    spread = std::max(spread, bspread); pos_lo = std::min(pos_lo, blo); pos_hi = std::max(pos_hi, bhi);
   }
   for (int64_t g = 0; g < nl; g++) if (gmax[g] >= 0) spread = std::max(spread, gmax[g] - gmin[g]);
   // group rank: by first pose position, then root id
@@ -465,6 +466,19 @@ static int finalize_impl(dynoba_solver* h) {
       for (int k = 0; k < 4; k++) if (got[k] != h->world*mine[k]) {
         h->err = "ranks disagree on the reduced system's size or bandwidth: pass the bandwidth of the unsharded graph as min_bandwidth to dynoba_set_shard";
         return DYNOBA_ERR_BAD_ARG;
+      }
+      if (h->reduce && h->band.ncell > 0) {
+        // which part of the reduced system does every rank touch?  All-gather [first, last] pose position (a sum over slots
+        // that only their rank fills): the per-cell reduces then only move the part of a cell's tiles that a rank other than
+        // its owner contributes to -- a halo of one co-visibility window when the landmarks are sharded in time.
+        std::vector<double> rng((size_t)2*h->world, 0.0);
+        rng[2*h->rank] = pos_hi >= 0 ? (double)pos_lo : 1.0; rng[2*h->rank + 1] = pos_hi >= 0 ? (double)pos_hi : 0.0;    // (empty: lo > hi)
+        CK(cudaMemcpyAsync(dbuf, rng.data(), rng.size()*8, cudaMemcpyHostToDevice, h->stream));
+        if (h->allreduce(h->ar_ctx, dbuf, rng.size(), (void*)h->stream) != 0) { h->err = "all-reduce callback failed"; return DYNOBA_ERR_COMM; }
+        CK(cudaMemcpyAsync(rng.data(), dbuf, rng.size()*8, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+        std::vector<int> lo(h->world), hi(h->world);
+        for (int r = 0; r < h->world; r++) { lo[r] = 6*(int)rng[2*r]; hi[r] = 6*(int)rng[2*r + 1] + 5; }
+        band_plan_trim(h->plan, lo.data(), hi.data());
       }
     }
   }
@@ -849,7 +863,7 @@ static int do_linearize(dynoba_solver* h) {
 // (parity hook dynoba_get_reduced_system; also the fallback when the host gave no reduce callback or there are no cells).
 static int build_reduced(dynoba_solver* h, double lambda, bool full_sum = false) {
   CK(cudaMemsetAsync(h->fail, 0, 4, h->stream));
-  h->launches += launch_band_clear(h->band, lambda, h->rank == 0, h->stream);
+  h->launches += launch_band_clear(h->band, lambda, h->rank, (h->world > 1 && h->reduce && h->band.ncell > 0 && !full_sum) ? h->world : 1, h->stream);
   for (auto& b : h->blocks) {
     if (b.pose_only) h->launches += launch_pose_factors(b.dev, h->band, h->stream);
     else {

@@ -165,7 +165,7 @@ int launch_sum(const double* partials, int n, double* out, cudaStream_t s);
 int linearize_grid(int n);          // number of partial sums a linearize/error launch of n factors writes
 int numeric_grid(int type, int n);  // CTAs of the column-parallel linearize kernel (0 for analytic factor types)
 
-int launch_band_clear(const DevBand& B, double lambda, int add_damping, cudaStream_t s);
+int launch_band_clear(const DevBand& B, double lambda, int rank, int world, cudaStream_t s);   // world == 1: rank 0 writes the whole diagonal
 int launch_schur_simple(const DevBlock& blk, const unsigned char* grp_win, const DevBand& B, double lambda, int* fail, cudaStream_t s);
 int launch_schur_window(const DevBlock& blk, const DevWindows& Wn, const DevBand& B, double lambda, int* fail, cudaStream_t s);
 int launch_schur_general(const GeneralGroups& G, const DevBand& B, double lambda, int* fail, cudaStream_t s);
@@ -197,6 +197,7 @@ struct BandPlan {
 };
 int band_plan_layout(BandPlan& P, int n, int bw, int ncell_request, int rank, int world);   // 0 = ok
 void band_plan_bind(BandPlan& P, double* dbase, int* ibase, void* desc_base, double* dp);
+void band_plan_trim(BandPlan& P, const int* lo, const int* hi);   // [world] scalar position ranges the ranks' factors touch -> reduce_ranges
 void band_set_tuning(int band_ctas_per_chain);
 int launch_band_factor(const BandPlan& P, int* fail, cudaStream_t s);       // chains, cell separator systems, local part of the boundary system
 int launch_band_top(const BandPlan& P, int* fail, cudaStream_t s);          // boundary system factor + solve, back-substitution, dp of the local cells

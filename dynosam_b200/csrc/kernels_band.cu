@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <climits>
 #include <vector>
 #include <cooperative_groups.h>
 #include "internal.cuh"
@@ -312,47 +313,138 @@ __device__ __forceinline__ void band_worker(const CholJob& job, int wid, int nwo
   }
 }
 
-// Spike worker warp (pool B; only launched when a chain of the job is spiked).  Its tasks never feed the spine, so they
-// live in their own pool: a 30-update spike task in front of a band task in the same in-order queue would stall the
-// chain.  Column-major order; per column K of a spiked chain
-//   slots [0, WB)         Z_r(K) = (Z_r(K) - sum_J Z_r(J) L(K,J)^T) L_KK^-T
-//   slots [WB, WB + NFF)  once per FF_CH columns: FF(r, r2) -= sum_{J in chunk} Z_r(J) Z_r2(J)^T, chunks chained by a counter
-// Operands are tiles of pool A / the spine (never waiting on pool B) or earlier tasks of this order: no deadlock.
-__device__ __forceinline__ void spike_worker(const CholJob& job, int wid, int nworkers, double* sb, double* sinv, double* stage, int lane) {
-  const int WB = job.WB, W1 = WB + 1, NFF = WB*(WB + 1)/2, R = WB + NFF;
+// Spike pool (pool B; only launched when a chain of the job is spiked): the spike tiles Z and the separator block FF.
+// Its tasks never feed the spine, so they live in their own pool -- a 30-update spike task in front of a band task in
+// the same in-order queue would stall the chain -- and it is organised for THROUGHPUT: a whole CTA (8 warps, two per
+// scheduler, so one warp's shared-memory / barrier phases hide behind the other's DMMAs) takes a group task of up to 8
+// output tiles that share their B operand, which is staged ONCE per step for all of them (9 tiles of L2 traffic per 8
+// tile updates instead of 16):
+//   spike group (K, g)       Z_r(K) = (Z_r(K) - sum_J Z_r(J) L(K,J)^T) L_KK^-T  for the rows r = 8g .. 8g+7   (B = L(K,J))
+//   FF group (chunk, r2, g)  FF(r, r2) -= sum_{J in chunk} Z_r(J) Z_r2(J)^T      for 8 rows r >= r2              (B = Z_r2(J))
+// Column-major task order.  Flags are checked per PHASE, not per step: done(L(K,Jhi)) implies every L(K,J), J < Jhi, and
+// done(Z_r(J)) implies the earlier tiles of row r, so the bulk of a task (all steps but the last) runs as soon as the
+// operands of the step before the last exist, and the row chain Z_r(K-1) -> Z_r(K) only carries one update + the TRSM.
+// Operands come from pool A / the spine (which never wait on pool B) or from earlier tasks of this order: no deadlock.
+constexpr int SPK_ROWS = 8;
+__device__ __forceinline__ void spike_cta_worker(const CholJob& job, int cw, int ncw, double* smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int WB = job.WB, W1 = WB + 1;
+  const int G = (WB + SPK_ROWS - 1)/SPK_ROWS;
+  int NGF = 0; for (int r2 = 0; r2 < WB; r2++) NGF += (WB - r2 + SPK_ROWS - 1)/SPK_ROWS;
+  const int R = G + NGF;
+  double* sB = smem;                                  // [2][TSZ] shared B operand (also L_KK for the TRSM)
+  double* sA = smem + 2*TSZ + (size_t)warp*2*TSZ;     // [2][TSZ] this warp's A operand (also its layout-conversion scratch)
+  double* sinv = smem + 2*TSZ + (size_t)SPK_ROWS*2*TSZ;   // [32]
   const long long per_col = (long long)job.np*R;
   const long long ntasks = (long long)job.ncols*per_col;
-  for (long long t = wid; t < ntasks; t += nworkers) {
+  for (long long t = cw; t < ntasks; t += ncw) {
     const int K = (int)(t/per_col); const int u = (int)(t - (long long)K*per_col);
-    const int q = u/R, slot = u - q*R;
+    const int q = u/R; int slot = u - q*R;
     const BandProb P = job.p[q];
     if (!P.spiked || K >= P.NT) continue;
     const int TPC = P.TPC;
-    double acc[TILE];
-    if (slot >= WB) {
+    const int* done = flag_done(P);
+    int r, Bslot0, Bslot1, Jlo, Jhi, r2 = -1, chunk = 0;       // this warp's row; B tile of column J = slot Bslot0 - Bslot1*J
+    const bool ff = slot >= G;
+    if (!ff) {
+      r = slot*SPK_ROWS + warp;
+      Bslot0 = K; Bslot1 = 1; Jlo = max(0, K - WB); Jhi = min(K - 1, P.Kend - 1);
+    } else {
       if (K >= P.Kend || !(((K + 1) % FF_CH) == 0 || K == P.Kend - 1)) continue;
-      const int e = slot - WB;
-      int r = (int)((sqrtf(8.0f*(float)e + 1.0f) - 1.0f)*0.5f);
-      while (r*(r + 1)/2 > e) r--;
-      while ((r + 1)*(r + 2)/2 <= e) r++;
-      const int r2 = e - r*(r + 1)/2, chunk = K/FF_CH;
-      int* cnt = flag_ffcnt(P) + r*WB + r2;
-      double* tp = P.ff + ((size_t)r*WB + r2)*TILE2;
-      wait_flag_ge(cnt, chunk, lane);
+      slot -= G;
+      r2 = 0;
+      for (;;) { const int ng = (WB - r2 + SPK_ROWS - 1)/SPK_ROWS; if (slot < ng) break; slot -= ng; r2++; }
+      r = r2 + slot*SPK_ROWS + warp;
+      chunk = K/FF_CH;
+      Bslot0 = W1 + r2; Bslot1 = 0; Jlo = chunk*FF_CH; Jhi = K;
+    }
+    const bool mine = r < WB;                        // warps without a row still stage B and keep the barriers
+    double* tp = !mine ? nullptr : (ff ? P.ff + ((size_t)r*WB + r2)*TILE2 : P.tiles + ((size_t)K*TPC + W1 + r)*TILE2);
+    double acc[TILE];
+    if (mine) {
+      if (ff) wait_flag_ge(flag_ffcnt(P) + r*WB + r2, chunk, lane);
       cfrag_load(tp, acc, lane);
-      accumulate_updates(P, acc, chunk*FF_CH, K, W1 + r, 0, W1 + r2, 0, r == r2, stage, lane);
-      cfrag_store(tp, acc, lane);
-      set_flag_value(cnt, chunk + 1, lane);
+    }
+    if (Jhi >= Jlo) {
+      // ---- operand flags.  FF: everything exists once the chunk's last column does.  Spike: the flags form monotone
+      // frontiers (done(Z_r(J)) implies the row's earlier tiles, done(L(K,J)) every L(K, J' < J)), so a warp probes a few
+      // columns from the far end once and only blocks, step by step, on what lies beyond the frontier it found
+      int frontA = Jlo - 1, frontB = Jlo - 1;          // last column whose A (own row) / B operand is known to exist (every warp
+                                                       // checks what it loads itself: no barrier between the check and the loads)
+      if (ff) { wait_flag(done + (size_t)K*TPC + W1 + r2, lane); if (mine) wait_flag(done + (size_t)K*TPC + W1 + r, lane); frontA = frontB = Jhi; }
+      else {
+        if (lane == 0) {
+          for (int back = 0; back <= Jhi - Jlo; back = back ? 2*back : 1) {
+            const int J = Jhi - back;
+            if (mine && frontA < Jlo && ld_acquire(done + (size_t)J*TPC + W1 + r) != 0) frontA = J;
+            if (frontB < Jlo && ld_acquire(done + (size_t)J*TPC + (K - J)) != 0) frontB = J;
+            if ((!mine || frontA >= Jlo) && frontB >= Jlo) break;
+          }
+        }
+        frontA = __shfl_sync(0xffffffffu, frontA, 0); frontB = __shfl_sync(0xffffffffu, frontB, 0);
+      }
+      auto need = [&](int J) {                          // block until the operands of step J exist
+        if (mine && J > frontA) { wait_flag(done + (size_t)J*TPC + W1 + r, lane); frontA = J; }
+        if (J > frontB) { wait_flag(done + (size_t)J*TPC + (K - J), lane); frontB = J; }
+      };
+      auto stage_loads = [&](int J, int st) {
+        const double* b = P.tiles + ((size_t)J*TPC + (Bslot0 - Bslot1*J))*TILE2;
+        double* dst = sB + (size_t)st*TSZ;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int ch = threadIdx.x + 256*i, c = ch >> 4, part = ch & 15;
+          const unsigned d = (unsigned)__cvta_generic_to_shared(dst + c*TS + 2*part);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(b + c*TILE + 2*part) : "memory");
+        }
+        if (mine) tile_prefetch(sA + (size_t)st*TSZ, P.tiles + ((size_t)J*TPC + W1 + r)*TILE2, lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      int st = 0;
+      need(Jlo);
+      stage_loads(Jlo, 0);
+      for (int J = Jlo; J <= Jhi; J++) {
+        if (J + 1 <= Jhi) {
+          need(J + 1);
+          stage_loads(J + 1, st ^ 1);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (mine) {
+          double fb[TILE], fa[TILE];
+          sfrag_load(sB + (size_t)st*TSZ, fb, lane);
+          if (ff && r == r2) frag_gemm_sub(acc, fb, fb);
+          else { sfrag_load(sA + (size_t)st*TSZ, fa, lane); frag_gemm_sub(acc, fa, fb); }
+        }
+        __syncthreads();                               // the stage is free for the loads of the step after next
+        st ^= 1;
+      }
+    }
+    if (ff) {
+      if (mine) { cfrag_store(tp, acc, lane); set_flag_value(flag_ffcnt(P) + r*WB + r2, chunk + 1, lane); }
       continue;
     }
-    const size_t o = (size_t)K*TPC + W1 + slot;
-    double* tp = P.tiles + o*TILE2;
-    cfrag_load(tp, acc, lane);
-    accumulate_updates(P, acc, max(0, K - WB), min(K - 1, P.Kend - 1), W1 + slot, 0, K, 1, false, stage, lane);
-    if (K >= P.Kend) {                      // spike tile of a separator column: its Schur complement, final
-      cfrag_store(tp, acc, lane);
-      set_flag(flag_done(P) + o, lane);
-    } else tile_finish_trsm(P, acc, K, tp, flag_done(P) + o, sb, sinv, lane);
+    if (K >= P.Kend) {                                 // spike tile of a separator column: its Schur complement, final
+      if (mine) { cfrag_store(tp, acc, lane); set_flag(flag_done(P) + (size_t)K*TPC + W1 + r, lane); }
+      continue;
+    }
+    // ---- TRSM against L_KK (staged once for the CTA, column-major with stride TILE in the B buffer)
+    if (warp == 0) wait_flag(done + (size_t)K*TPC, lane);
+    __syncthreads();
+    for (int e = threadIdx.x; e < TILE2; e += 256) sB[e] = __ldcg(P.tiles + (size_t)K*TPC*TILE2 + e);
+    __syncthreads();
+    if (threadIdx.x < TILE) sinv[threadIdx.x] = 1.0/sB[threadIdx.x*TILE + threadIdx.x];
+    __syncthreads();
+    if (mine) {
+      __syncwarp();
+      cfrag_store(sA, acc, lane);                      // accumulator fragments -> one row per lane
+      __syncwarp();
+#pragma unroll
+      for (int cc = 0; cc < TILE; cc++) acc[cc] = sA[cc*TILE + lane];
+      tile_trsm(acc, sB, sinv);
+      tile_store(tp, acc, lane);
+      set_flag(flag_done(P) + (size_t)K*TPC + W1 + r, lane);
+    }
+    __syncthreads();                                   // sB / sinv are reused by the next task
   }
 }
 
@@ -560,11 +652,11 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int* __restrict__ fail) {
   extern __shared__ __align__(16) double chol_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= job.np) {
-    if (warp >= 4) return;       // four worker warps per CTA (one per scheduler): [warp][2 stages][2 tiles][TSZ] | [TILE2] | [TILE]
-    double* base = chol_smem + (size_t)warp*(4*TSZ + TILE2 + TILE);
     const int w = (int)blockIdx.x - job.np;
-    if (w < job.band_ctas) band_worker(job, w*4 + warp, job.band_ctas*4, base + 4*TSZ, base + 4*TSZ + TILE2, base, lane);
-    else spike_worker(job, (w - job.band_ctas)*4 + warp, ((int)gridDim.x - job.np - job.band_ctas)*4, base + 4*TSZ, base + 4*TSZ + TILE2, base, lane);
+    if (w >= job.band_ctas) { spike_cta_worker(job, w - job.band_ctas, (int)gridDim.x - job.np - job.band_ctas, chol_smem); return; }
+    if (warp >= 4) return;       // four band worker warps per CTA (one per scheduler): [warp][2 stages][2 tiles][TSZ] | [TILE2] | [TILE]
+    double* base = chol_smem + (size_t)warp*(4*TSZ + TILE2 + TILE);
+    band_worker(job, w*4 + warp, job.band_ctas*4, base + 4*TSZ, base + 4*TSZ + TILE2, base, lane);
     return;
   }
   const BandProb P = job.p[blockIdx.x];
@@ -1046,7 +1138,7 @@ static void chol_init() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // one CTA per SM: every spine CTA is alone on its SM
-  const size_t need = std::max((size_t)(2*4*PANSZ + 2*TILE + 8*TSZ + 4*TILE2 + 64), (size_t)4*(4*TSZ + TILE2 + TILE))*sizeof(double);   // spine | workers with prefetch stages
+  const size_t need = std::max((size_t)(2*4*PANSZ + 2*TILE + 8*TSZ + 4*TILE2 + 64), std::max((size_t)4*(4*TSZ + TILE2 + TILE), (size_t)(2 + 2*SPK_ROWS)*TSZ + TILE))*sizeof(double);   // spine | band workers with prefetch stages | spike CTA
   g_chol_smem = std::max(need, (size_t)(220*1024) - 2048);
   cudaFuncSetAttribute(band_cholesky_dataflow_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_chol_smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, band_cholesky_dataflow_kernel_v3, SP_WARPS*32, g_chol_smem);
@@ -1233,6 +1325,33 @@ void band_plan_bind(BandPlan& P, double* dbase, int* ibase, void* desc_base, dou
   P.d_local_cell_ids = (int*)put(P.local_cells.data(), sizeof(int)*P.local_cells.size());
   B.chains = P.d_chains; B.cells = dcells;
   B.dp = C == 0 ? P.chains[0].rhs : dp;
+}
+
+// Rebuilds the per-cell reduce list from the position ranges [lo[r], hi[r]] (scalar, inclusive) the factors of every
+// rank touch: the tiles of cell c only have to be summed at its owner over the columns a NON-owner contributes to.
+// Entries (i >= j) of a rank lie inside its range, in the column of j (band) or of i (spike tiles of an A chain), so the
+// touched columns of a chain are the tiles of range & chain; the Q x Q block of an A chain is touched when the range meets Qa
+// (the B chain's only receives spike products, which are formed at the owner).
+void band_plan_trim(BandPlan& P, const int* lo, const int* hi) {
+  const DevBand& B = P.band; const int C = B.ncell, WB = B.WB, w = WB*TILE;
+  P.reduce_ranges.clear();
+  for (int c = 0; c < C; c++) {
+    const int owner = c*P.world/C;
+    const CellGeom& g = P.cells[c];
+    const BandProb &a = P.chains[2*c], &b = P.chains[2*c + 1];
+    int a_lo = INT32_MAX, a_hi = -1, b_lo = INT32_MAX, b_hi = -1; bool ffa = false;
+    for (int r = 0; r < P.world; r++) {
+      if (r == owner || lo[r] > hi[r]) continue;
+      const int p0 = std::max(lo[r], g.a0), p1 = std::min(hi[r], g.m0 + w - 1);           // chain A: natural order from a0
+      if (p0 <= p1) { a_lo = std::min(a_lo, (p0 - g.a0)/TILE); a_hi = std::max(a_hi, (p1 - g.a0)/TILE); }
+      const int q0 = std::max(lo[r], g.m0), q1 = std::min(hi[r], g.b1 - 1);                // chain B: reversed from b1 - 1
+      if (q0 <= q1) { b_lo = std::min(b_lo, (g.b1 - 1 - q1)/TILE); b_hi = std::max(b_hi, (g.b1 - 1 - q0)/TILE); }
+      if (g.has_qa && lo[r] < g.a0 && hi[r] >= g.q0) ffa = true;
+    }
+    if (a_hi >= a_lo) P.reduce_ranges.push_back({ a.tiles + (size_t)a_lo*a.TPC*TILE2, (size_t)(a_hi - a_lo + 1)*a.TPC*TILE2, owner });
+    if (b_hi >= b_lo) P.reduce_ranges.push_back({ b.tiles + (size_t)b_lo*b.TPC*TILE2, (size_t)(b_hi - b_lo + 1)*b.TPC*TILE2, owner });
+    if (ffa) P.reduce_ranges.push_back({ a.ff, (size_t)WB*WB*TILE2, owner });
+  }
 }
 
 static CellRefs cell_refs(const BandPlan& P) { return CellRefs{ P.d_chains, P.d_cs, P.d_gq, P.band.cells, P.d_local_cell_ids, P.band.WB }; }

@@ -63,15 +63,18 @@ __global__ void band_clear_kernel(DevBand B) {
   double2* a = reinterpret_cast<double2*>(B.acc);           // (every buffer of the region is padded to 32 doubles)
   for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < B.acc_count/2; i += stride) a[i] = make_double2(0.0, 0.0);
 }
-__global__ void band_diag_kernel(DevBand B, double lambda, int add_damping) {
+// diagonal: damping lambda on the real rows, 1 on the padding rows -- written by ONE rank: rank 0 when the reduced system
+// is all-reduced (world == 1 here), else the owner of the row's cell (owner(c) = c*world/ncell, as in BandPlan)
+__global__ void band_diag_kernel(DevBand B, double lambda, int rank, int world) {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= B.n_pad) return;
-  const double v = i < B.n ? (add_damping ? lambda : 0.0) : 1.0;
-  *band_at(B, i, i) = v;
+  const int owner = world > 1 ? (int)((long long)band_cell(B, i)*world/B.ncell) : 0;
+  if (owner != rank) return;
+  *band_at(B, i, i) = i < B.n ? lambda : 1.0;
 }
-int launch_band_clear(const DevBand& B, double lambda, int add_damping, cudaStream_t s) {
+int launch_band_clear(const DevBand& B, double lambda, int rank, int world, cudaStream_t s) {
   band_clear_kernel<<<148*8, 256, 0, s>>>(B);
-  band_diag_kernel<<<(B.n_pad + 255)/256, 256, 0, s>>>(B, lambda, add_damping);
+  band_diag_kernel<<<(B.n_pad + 255)/256, 256, 0, s>>>(B, lambda, rank, world);
   return 2;
 }
 
