@@ -1128,7 +1128,7 @@ __global__ void gather_dp_kernel(CellRefs R, double* __restrict__ dp) {
 // Host side
 
 static int g_max_blocks = 0;
-static int g_band_ctas_per_chain = 22;
+static int g_band_ctas_per_chain = 0;       // 0: split the worker CTAs by the work of the two pools
 void band_set_tuning(int band_ctas_per_chain) { if (band_ctas_per_chain > 0) g_band_ctas_per_chain = band_ctas_per_chain; }
 static size_t g_chol_smem = 0;
 
@@ -1162,10 +1162,17 @@ static int chol_launch(const BandProb* dprobs, const BandProb* hprobs, int np, i
   const long long want = (ntile + 3)/4 + np;
   if (grid > want) grid = (int)want;
   if (grid < np + 1 + (job.any_spiked ? 1 : 0)) grid = np + 1 + (job.any_spiked ? 1 : 0);
-  // worker CTAs: without spikes all of them work on band tiles; else pool A gets what keeps the chains at the spine's
-  // pace (~ band_ctas_per_chain CTAs per chain) and the rest streams the spike / FF updates behind them
+  // worker CTAs: without spikes all of them work on band tiles; else the two pools share them in proportion to their work
+  // (measured per column: band tiles ~330 us of one CTA, spike + FF updates ~730 us), pool A never below what keeps a chain
+  // at the spine's pace (~22 CTAs per chain)
   const int workers = grid - np;
-  job.band_ctas = job.any_spiked ? std::max(1, std::min(workers - 1, std::min(g_band_ctas_per_chain*np, workers*2/3))) : workers;
+  if (!job.any_spiked) job.band_ctas = workers;
+  else {
+    double wa = 0, wb = 0;
+    for (int q = 0; q < np; q++) { wa += 330.0*hprobs[q].Kend; if (hprobs[q].spiked) wb += 730.0*hprobs[q].Kend; }
+    int a = g_band_ctas_per_chain > 0 ? g_band_ctas_per_chain*np : std::max((int)(workers*wa/(wa + wb)), std::min(22*np, workers/2));
+    job.band_ctas = std::max(1, std::min(workers - 1, a));
+  }
   // cooperative launch only for its co-residency guarantee (the flag waits need every warp resident)
   void* args[] = { (void*)&job, (void*)&fail };
   cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel_v3, dim3(grid), dim3(SP_WARPS*32), args, g_chol_smem, s);
@@ -1202,9 +1209,10 @@ int band_plan_layout(BandPlan& P, int n, int bw, int ncell_request, int rank, in
   if (ncell_request > 0) C = std::min(ncell_request, cmax);
   else if (ncell_request < 0) C = 0;
   else {
-    // default: one cell per GPU; on one GPU a second cell pays once the chains are long (the spiked chains cost 4x the
-    // flops per column, so short systems stay with the two-chain scheme)
-    C = world > 1 ? std::min(world, cmax) : (NT >= 4096 && cmax >= 2 ? 2 : 1);
+    // default: one cell per GPU.  On one GPU the two-chain scheme (one cell, no spike) is the fastest: a second cell halves
+    // the chain but its two spiked chains cost 4x the flops per column, which the worker warps of one GPU do not absorb
+    // (measured on C5: 73 ms per solve with one cell, 86-100 ms with two)
+    C = world > 1 ? std::min(world, cmax) : 1;
     if (NT < std::max(8, 4*WB + 4)) C = 0;
     C = std::min(C, cmax);
   }
