@@ -299,7 +299,8 @@ int dynoba_set_reduce(dynoba_handle h, dynoba_reduce_fn fn, void* ctx) {
 int dynoba_set_tuning(dynoba_handle h, const char* name, double value) {
   ARG(h, "null handle"); ARG(name, "null name");
   if (!std::strcmp(name, "outer_weight")) { h->plan.outer_weight = value; if (h->finalized) free_device(h); }
-  else if (!std::strcmp(name, "band_ctas_per_chain")) band_set_tuning((int)value);
+  else if (!std::strcmp(name, "band_ctas_per_chain")) band_set_tuning(std::max(0, (int)value));
+  else if (!std::strcmp(name, "band_profile")) band_set_tuning(-1);
   else ARG(false, "unknown tuning parameter");
   return DYNOBA_OK;
 }

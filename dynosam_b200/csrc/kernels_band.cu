@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstring>
 #include <climits>
+#include <chrono>
 #include <vector>
 #include <cooperative_groups.h>
 #include "internal.cuh"
@@ -169,8 +170,12 @@ __device__ __forceinline__ bool flags_ready(const int* fa, const int* fb, int la
   return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
 
+// optional stage profile (dynoba_set_tuning "band_profile"): finish times of the spines and of the two worker pools
+__device__ unsigned long long g_prof[40];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 // One launch of the factorisation kernel: np band problems of the same tile bandwidth WB.
-struct CholJob { const BandProb* p; int np, WB, skew, any_spiked, ncols, band_ctas; };   // band_ctas: worker CTAs of pool A
+struct CholJob { const BandProb* p; int np, WB, skew, any_spiked, ncols, band_ctas, profile; };   // band_ctas: worker CTAs of pool A
 __device__ __forceinline__ int* flag_done(const BandProb& P) { return P.flags; }
 __device__ __forceinline__ int* flag_pre(const BandProb& P) { return P.flags + (size_t)P.NT*P.TPC; }
 __device__ __forceinline__ int* flag_ydone(const BandProb& P) { return P.flags + (size_t)2*P.NT*P.TPC; }
@@ -653,10 +658,16 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int* __restrict__ fail) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= job.np) {
     const int w = (int)blockIdx.x - job.np;
-    if (w >= job.band_ctas) { spike_cta_worker(job, w - job.band_ctas, (int)gridDim.x - job.np - job.band_ctas, chol_smem); return; }
+    if (job.profile && threadIdx.x == 0) atomicMin(&g_prof[34], gtimer());
+    if (w >= job.band_ctas) {
+      spike_cta_worker(job, w - job.band_ctas, (int)gridDim.x - job.np - job.band_ctas, chol_smem);
+      if (job.profile && threadIdx.x == 0) atomicMax(&g_prof[33], gtimer());
+      return;
+    }
     if (warp >= 4) return;       // four band worker warps per CTA (one per scheduler): [warp][2 stages][2 tiles][TSZ] | [TILE2] | [TILE]
     double* base = chol_smem + (size_t)warp*(4*TSZ + TILE2 + TILE);
     band_worker(job, w*4 + warp, job.band_ctas*4, base + 4*TSZ, base + 4*TSZ + TILE2, base, lane);
+    if (job.profile && lane == 0) atomicMax(&g_prof[32], gtimer());
     return;
   }
   const BandProb P = job.p[blockIdx.x];
@@ -759,6 +770,7 @@ band_cholesky_dataflow_kernel_v3(CholJob job, int* __restrict__ fail) {
         ev_signal(ev, EV_ST_X1, c + 1, lane);
       }
     }
+    if (job.profile && lane == 0 && blockIdx.x < 32) g_prof[blockIdx.x] = gtimer();
   } else if (warp == 5) {
     // ---------------------------------------------------------------- IO1: inputs of column c+1 -> shared memory
     for (int c = -1; c < Kend; c++) if (c + 1 < NT) {
@@ -1129,7 +1141,13 @@ __global__ void gather_dp_kernel(CellRefs R, double* __restrict__ dp) {
 
 static int g_max_blocks = 0;
 static int g_band_ctas_per_chain = 0;       // 0: split the worker CTAs by the work of the two pools
-void band_set_tuning(int band_ctas_per_chain) { if (band_ctas_per_chain > 0) g_band_ctas_per_chain = band_ctas_per_chain; }
+static int g_band_profile = 0;
+void band_set_tuning(int band_ctas_per_chain) { if (band_ctas_per_chain >= 0) g_band_ctas_per_chain = band_ctas_per_chain; else g_band_profile = -band_ctas_per_chain; }
+// stage timer of the optional profile (dynoba_set_tuning "band_profile"): synchronises the stream, so never on in timed runs
+struct StageTimer { cudaStream_t s; std::chrono::steady_clock::time_point t; bool on;
+  StageTimer(cudaStream_t s_) : s(s_), on(g_band_profile != 0) { if (on) { cudaStreamSynchronize(s); t = std::chrono::steady_clock::now(); } }
+  void lap(const char* what) { if (!on) return; cudaStreamSynchronize(s); auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[band] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count()); t = n; } };
 static size_t g_chol_smem = 0;
 
 static void chol_init() {
@@ -1174,8 +1192,16 @@ static int chol_launch(const BandProb* dprobs, const BandProb* hprobs, int np, i
     job.band_ctas = std::max(1, std::min(workers - 1, a));
   }
   // cooperative launch only for its co-residency guarantee (the flag waits need every warp resident)
+  job.profile = g_band_profile;
+  if (g_band_profile) { unsigned long long init[40]; for (int i = 0; i < 40; i++) init[i] = 0; init[34] = ~0ull; cudaMemcpyToSymbolAsync(g_prof, init, sizeof(init), 0, cudaMemcpyHostToDevice, s); }
   void* args[] = { (void*)&job, (void*)&fail };
   cudaLaunchCooperativeKernel((void*)band_cholesky_dataflow_kernel_v3, dim3(grid), dim3(SP_WARPS*32), args, g_chol_smem, s);
+  if (g_band_profile) {
+    unsigned long long t[40]; cudaStreamSynchronize(s); cudaMemcpyFromSymbol(t, g_prof, sizeof(t));
+    fprintf(stderr, "[band]   launch: %d problems, WB %d, grid %d = %d spines + %d band CTAs + %d spike CTAs\n", np, WB, grid, np, job.band_ctas, grid - np - job.band_ctas);
+    for (int q = 0; q < np && q < 32; q++) fprintf(stderr, "[band]   spine %d (%d columns%s) done at %8.3f ms\n", q, hprobs[q].Kend, hprobs[q].spiked ? ", spiked" : "", (t[q] - t[34])*1e-6);
+    fprintf(stderr, "[band]   band pool done at %8.3f ms, spike pool at %8.3f ms\n", (t[32] - t[34])*1e-6, t[33] ? (t[33] - t[34])*1e-6 : 0.0);
+  }
   return 1;
 }
 static int back_launch(const BandProb* dprobs, int np, int WB, cudaStream_t s) {
@@ -1367,7 +1393,9 @@ static CellRefs cell_refs(const BandPlan& P) { return CellRefs{ P.d_chains, P.d_
 int launch_band_factor(const BandPlan& P, int* fail, cudaStream_t s) {
   const DevBand& B = P.band; const int WB = B.WB, C = B.ncell;
   int launches = 0;
+  StageTimer tm(s);
   launches += chol_launch(P.d_local_chains, P.d_local_chains_host.data(), P.n_local_chains, WB, fail, s);
+  tm.lap("chains");
   if (P.n_local_chains) { int maxk = 1; for (auto& p : P.d_local_chains_host) maxk = std::max(maxk, p.Kend);
     diag_inverse_kernel<<<dim3((maxk + 3)/4, P.n_local_chains), 128, 0, s>>>(P.d_local_chains); launches++; }
   if (C == 0) return launches;
@@ -1383,13 +1411,17 @@ int launch_band_factor(const BandPlan& P, int* fail, cudaStream_t s) {
       launches += 2;
     }
     const int ntcs = WB*(C >= 2 ? 3 : 1);
+    tm.lap("diag inverse + spike forward");
     cs_assemble_kernel<<<dim3(ntcs*P.TPCcs, nloc), 256, 0, s>>>(cell_refs(P), P.TPCcs); launches++;
+    tm.lap("cell systems: assemble");
     launches += chol_launch(P.d_local_cs, P.d_local_cs_host.data(), P.n_local_cs, P.WBcs, fail, s);
     diag_inverse_kernel<<<dim3((WB + 3)/4, P.n_local_cs), 128, 0, s>>>(P.d_local_cs); launches++;
+    tm.lap("cell systems: factor");
   }
   if (C >= 2) {
     cudaMemsetAsync(P.gq_base, 0, P.gq_count*sizeof(double), s);
     for (int c : P.local_cells) { gq_add_cell_kernel<<<148, 256, 0, s>>>(cell_refs(P), c, P.TPCgq); launches++; }
+    tm.lap("boundary system: assemble");
   }
   return launches;
 }
@@ -1399,21 +1431,25 @@ int launch_band_top(const BandPlan& P, int* fail, cudaStream_t s) {
   int launches = 0;
   if (C == 0) { launches += back_launch(P.d_local_chains, P.n_local_chains, WB, s); return launches; }
   const int nloc = (int)P.local_cells.size();
+  StageTimer tm(s);
   if (C >= 2) {
     launches += chol_launch(P.d_gq, P.gq.data(), 1, P.WBgq, fail, s);                  // boundary system (replicated on every rank)
     diag_inverse_kernel<<<dim3((P.NTgq + 3)/4, 1), 128, 0, s>>>(P.d_gq); launches++;
     launches += back_launch(P.d_gq, 1, P.WBgq, s);
     if (nloc) { gq_scatter_kernel<<<dim3(8, nloc), 256, 0, s>>>(cell_refs(P)); launches++; }
+    tm.lap("boundary system: solve");
   }
   if (P.world > 1) cudaMemsetAsync(B.dp, 0, (size_t)B.n_pad*sizeof(double), s);        // the owners' segments are summed by the caller
   if (!nloc) return launches;
   launches += back_launch(P.d_local_cs, P.n_local_cs, P.WBcs, s);                      // x_M
   cs_to_chain_kernel<<<dim3(8, nloc), 256, 0, s>>>(cell_refs(P)); launches++;
+  tm.lap("cell systems: back-substitution");
   bool any_spiked = false; int maxk = 1;
   for (auto& p : P.d_local_chains_host) { any_spiked |= p.spiked != 0; maxk = std::max(maxk, p.Kend); }
   if (any_spiked) { spike_backward_kernel<<<dim3((maxk + 7)/8, P.n_local_chains), 256, (size_t)WB*TILE*sizeof(double), s>>>(P.d_local_chains, WB); launches++; }
   launches += back_launch(P.d_local_chains, P.n_local_chains, WB, s);
   gather_dp_kernel<<<dim3(64, nloc), 256, 0, s>>>(cell_refs(P), B.dp); launches++;
+  tm.lap("chains: back-substitution");
   return launches;
 }
 
