@@ -1,0 +1,3 @@
+// stub: see tests/stubs/gtsam_stub.h
+#pragma once
+#include "../../gtsam_stub.h"

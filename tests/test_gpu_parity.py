@@ -316,3 +316,13 @@ def test_unsupported_topology_reports_status():
     with pytest.raises(DynobaError) as ei:
         s.optimize()
     assert ei.value.status == ERR_UNSUPPORTED
+
+
+def test_plain_c_program_runs_on_the_gpu(tmp_path):
+    """tests/capi/capi_smoke.c through include/dynoba.h: a C consumer of the ABI optimises a small graph on the device."""
+    import os, subprocess, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host import _build_capi_smoke
+    exe = _build_capi_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
