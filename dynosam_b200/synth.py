@@ -12,6 +12,9 @@ which factor type and noise), scaled to the BASELINE.json configs:
   (src/backend/rgbd/HybridEstimator.cc:573-830)
 * WCME: one point per (tracklet, frame), PoseToPoint + LandmarkMotionTernaryFactor chain, motion
   BetweenFactor smoothing (src/backend/rgbd/WorldMotionEstimator.cc:151-351)
+* WCPE: one point per (tracklet, frame), PoseToPoint + LandmarkMotionPoseFactor(m_k-1, m_k, L_k-1, L_k) chain over
+  object POSE variables L_k^j (one per frame the object is seen, no prior), 3-pose LandmarkPoseSmoothingFactor
+  (src/backend/rgbd/WorldPoseEstimator.cc:89-315)
 
 The trajectories follow test/internal/simulator.hpp's ConstantMotionBodyVisitor (constant twist).
 All randomness comes from numpy's PCG64 seeded generator (the reference's simulator is not
@@ -22,8 +25,8 @@ from __future__ import annotations
 import numpy as np
 
 from . import lie
-from .problem import (BETWEEN6, HYBRID3, POSE2POINT3, PRIOR6, SMOOTH_HYBRID6, TERNARY3, FactorBlock, Problem,
-                      camera_pose_key, dynamic_landmark_key, object_motion_key, static_landmark_key)
+from .problem import (BETWEEN6, HYBRID3, MOTIONPOSE3, POSE2POINT3, PRIOR6, SMOOTH_HYBRID6, SMOOTH_POSE6, TERNARY3, FactorBlock, Problem,
+                      camera_pose_key, dynamic_landmark_key, object_motion_key, object_pose_key, static_landmark_key)
 
 KITTI_K = np.array([721.5377, 721.5377, 0.0, 609.5593, 172.854, 0.5372])
 IMG_W, IMG_H = 1242, 375
@@ -57,7 +60,7 @@ def make_problem(n_frames=20, n_objects=1, n_static=700, n_dynamic=300, formulat
                  sigma_point=0.2, sigma_ternary=0.01, huber_k=1e-4, robust=True, meas_noise=None,
                  init_noise_rot=0.01, init_noise_trans=0.05, object_span=None, max_static_age=15,
                  max_dynamic_age=20, with_odometry=True) -> Problem:
-    assert formulation in ("hybrid", "wcme")
+    assert formulation in ("hybrid", "wcme", "wcpe")
     rng = np.random.default_rng(seed)
     N = int(n_frames)
     meas_noise = sigma_point if meas_noise is None else meas_noise
@@ -109,21 +112,23 @@ def make_problem(n_frames=20, n_objects=1, n_static=700, n_dynamic=300, formulat
                            rng.uniform(-0.3, 0.3, J), rng.normal(0, 0.02, J), rng.uniform(0.4, 1.2, J)], 1)
         aux = L_e
         # motion variable layout: object-major, frames s_j .. s_j+D_j-1 (WCME skips the first frame)
-        skip = 0 if formulation == "hybrid" else 1
+        skip = 1 if formulation == "wcme" else 0
         cnt = D - skip
         hstart = N + np.concatenate([[0], np.cumsum(cnt)])         # pose index of the first motion of object j
         oj, ok, _ = _expand(cnt)
         hframe = s[oj] + ok + skip                                 # frame of each motion variable
         if formulation == "hybrid":
             H_gt = lie.se3_exp((hframe - s[oj])[:, None]*xi_obj[oj])   # e_H_k = H^(k-e)
-        else:
+        elif formulation == "wcme":
             H_gt = lie.se3_exp(xi_obj[oj])                             # k-1 -> k motion (constant)
+        else:
+            H_gt = lie.compose(lie.se3_exp((hframe - s[oj])[:, None]*xi_obj[oj]), L_e[oj])   # object pose L_k = e_H_k L_e
         H_init = lie.retract(H_gt, np.concatenate([rng.normal(0, init_noise_rot, (H_gt.shape[0], 3)),
                                                    rng.normal(0, init_noise_trans, (H_gt.shape[0], 3))], 1))
         if formulation == "hybrid":
             H_init[hstart[:-1] - N] = lie.identity(J)               # key-frame motion starts at its prior
         pose_list.append(H_init); order_hint.append(hframe); gt_motion = H_gt
-        pose_keys.append(object_motion_key(oj + 1, hframe))
+        pose_keys.append((object_pose_key if formulation == "wcpe" else object_motion_key)(oj + 1, hframe))
 
         # ---------------- dynamic tracklets
         per = np.full(J, nd//J); per[:nd - per.sum()] += 1
@@ -165,13 +170,23 @@ def make_problem(n_frames=20, n_objects=1, n_static=700, n_dynamic=300, formulat
             blocks.append(FactorBlock(POSE2POINT3, np.stack([fr, pidx], 1), z, np.array([sigma_point]), kh))
             notfirst = off > 0
             cur = np.nonzero(notfirst)[0]
-            blocks.append(FactorBlock(TERNARY3, np.stack([pidx[cur - 1], pidx[cur], hidx[cur]], 1), None,
-                                      np.array([sigma_ternary]), kh))
-            sm_j, sm_o, _ = _expand(np.maximum(cnt - 1, 0))
-            if sm_j.size:
-                i0 = hstart[sm_j] + sm_o
-                blocks.append(FactorBlock(BETWEEN6, np.stack([i0, i0 + 1], 1), lie.identity(i0.shape[0]),
-                                          np.array([0.01, 0.01, 0.01, 0.1, 0.1, 0.1])))
+            if formulation == "wcme":
+                blocks.append(FactorBlock(TERNARY3, np.stack([pidx[cur - 1], pidx[cur], hidx[cur]], 1), None,
+                                          np.array([sigma_ternary]), kh))
+                sm_j, sm_o, _ = _expand(np.maximum(cnt - 1, 0))
+                if sm_j.size:
+                    i0 = hstart[sm_j] + sm_o
+                    blocks.append(FactorBlock(BETWEEN6, np.stack([i0, i0 + 1], 1), lie.identity(i0.shape[0]),
+                                              np.array([0.01, 0.01, 0.01, 0.1, 0.1, 0.1])))
+            else:
+                # LandmarkMotionPoseFactor(m_k-1, m_k, L_k-1, L_k) (WorldPoseEstimator.cc:170-178) + 3-pose smoothing (:259-306)
+                blocks.append(FactorBlock(MOTIONPOSE3, np.stack([pidx[cur - 1], pidx[cur], hidx[cur] - 1, hidx[cur]], 1), None,
+                                          np.array([sigma_ternary]), kh))
+                tri_j, tri_o, _ = _expand(np.maximum(cnt - 2, 0))
+                if tri_j.size:
+                    i0 = hstart[tri_j] + tri_o
+                    blocks.append(FactorBlock(SMOOTH_POSE6, np.stack([i0, i0 + 1, i0 + 2], 1), None,
+                                              np.array([0.01, 0.01, 0.01, 0.1, 0.1, 0.1])))
 
     # ---------------- camera chain
     blocks.append(FactorBlock(PRIOR6, np.array([[0]]), X_gt[:1], np.full(6, 1e-6)))

@@ -50,7 +50,7 @@ def test_linearize_every_factor_type():
     _check_linearization(_all_types_problem())
 
 
-@pytest.mark.parametrize("formulation", ["hybrid", "wcme"])
+@pytest.mark.parametrize("formulation", ["hybrid", "wcme", "wcpe"])
 def test_linearize_c1(formulation):
     _check_linearization(synth.make_config("C1", formulation=formulation))
 
@@ -149,6 +149,24 @@ def test_lm_wcme_c1_matches_oracle():
     assert abs(st["error_final"] - so["error_final"]) <= REL_CHI2*so["error_final"]
     pose, point, _ = s.values()
     assert np.abs(pose - o.pose).max() < 1e-6 and np.abs(point - o.point).max() < 1e-5
+
+
+def test_lm_wcpe_c1_matches_oracle():
+    """World-centric POSE formulation end to end (WorldPoseEstimator.cc:89-315): object pose variables L_k, one point
+    per (tracklet, frame) chained by the four-key LandmarkMotionPoseFactor (numerical Jacobians, as the reference), and
+    the three-pose LandmarkPoseSmoothingFactor.  Numerical differentiation leaves ~1e-6 of rounding in the Jacobians, so
+    the trajectories are compared a little looser than the analytic formulations."""
+    p = synth.make_config("C1", formulation="wcpe")
+    assert any(b.type == MOTIONPOSE3 for b in p.blocks) and any(b.type == SMOOTH_POSE6 for b in p.blocks)
+    s = _solver(p); o = _oracle(p)
+    assert abs(s.error() - o.error()) <= REL_CHI2*o.error()
+    lam = 1e-4
+    d = s.solve(lam)
+    rc, do = o.schur_solve(lam)
+    assert rc == 0 and np.linalg.norm(d - do) <= 1e-5*np.linalg.norm(do)
+    st = s.optimize(max_iterations=10); so = o.optimize(max_iterations=10)
+    assert st["iterations"] == so["iterations"] and st["inner_iterations"] == so["inner_iterations"]
+    assert abs(st["error_final"] - so["error_final"]) <= 1e-5*so["error_final"]
 
 
 def test_damped_solve_every_factor_type():
