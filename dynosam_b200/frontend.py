@@ -11,7 +11,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdynofront.so")
 EXPORTS = ["dynofront_create", "dynofront_destroy", "dynofront_last_error", "dynofront_set_frame", "dynofront_track_dynamic",
-           "dynofront_sample_candidates", "dynofront_propagate_mask", "dynofront_klt_track", "dynofront_get_pyramid_level"]
+           "dynofront_sample_candidates", "dynofront_propagate_mask", "dynofront_klt_track", "dynofront_klt_track_fb",
+           "dynofront_klt_last_min_eig", "dynofront_track_static_flow", "dynofront_get_pyramid_level"]
 
 
 class TrackParamsC(C.Structure):
@@ -27,6 +28,13 @@ class TrackParams:
 
     def c(self):
         return TrackParamsC(self.max_dynamic_feature_age, self.min_distance, self.shrink_row, self.shrink_col)
+
+
+class KltFbParamsC(C.Structure):
+    _fields_ = [("win", C.c_int32), ("max_level", C.c_int32), ("max_count", C.c_int32), ("epsilon", C.c_double),
+                ("win_back", C.c_int32), ("max_level_back", C.c_int32), ("max_count_back", C.c_int32), ("epsilon_back", C.c_double),
+                ("use_initial_flow", C.c_int32), ("min_eig_threshold", C.c_double), ("max_fb_distance", C.c_double),
+                ("check_static", C.c_int32), ("max_feature_track_age", C.c_int32), ("track", TrackParamsC)]
 
 
 _LIB = None
@@ -48,6 +56,11 @@ def load():
         L.dynofront_propagate_mask.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p]*4 + [C.POINTER(TrackParamsC), C.c_int32, C.c_void_p]
         L.dynofront_klt_track.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double, C.POINTER(C.c_float)]
+        L.dynofront_klt_track_fb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.POINTER(KltFbParamsC), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        L.dynofront_klt_last_min_eig.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.dynofront_track_static_flow.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                                  C.POINTER(C.c_int64)] + [C.c_void_p]*8 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.dynofront_get_pyramid_level.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
@@ -129,6 +142,42 @@ class FeatureTrackerGPU:
                                               1 if initial is not None else 0, float(min_eig), C.byref(ms)))
         self.last_ms = ms.value
         return nxt, st, err
+
+    def klt_track_fb(self, prev_gray, cur_gray, prev_pts, prm: TrackParams | None = None, prev_age=None, max_feature_track_age=25,
+                     win=21, max_level=3, max_count=30, eps=0.03, initial=None, min_eig=1e-4, max_fb_distance=0.5):
+        """KltFeatureTracker::trackPoints in one call: forward LK, backward LK (21x21, 5 levels, OpenCV default criteria), the
+        round-trip test and -- when prev_age is given -- the label / border / age checks.  Returns (next, status, back, keep)."""
+        pg = np.ascontiguousarray(prev_gray, dtype=np.uint8); cg = np.ascontiguousarray(cur_gray, dtype=np.uint8)
+        p0 = np.ascontiguousarray(prev_pts, dtype=np.float32).reshape(-1, 2); n = p0.shape[0]
+        nxt = np.ascontiguousarray(initial, dtype=np.float32).reshape(-1, 2).copy() if initial is not None else np.zeros((n, 2), np.float32)
+        st = np.zeros(n, np.uint8); back = np.zeros((n, 2), np.float32); keep = np.zeros(n, np.uint8); ms = C.c_float()
+        check = prev_age is not None
+        age = np.ascontiguousarray(prev_age, dtype=np.int32) if check else None
+        pc = KltFbParamsC(win, max_level, max_count, float(eps), 21, 5, 30, 0.01, 1 if initial is not None else 0, float(min_eig), float(max_fb_distance),
+                          1 if check else 0, int(max_feature_track_age), (prm or TrackParams()).c())
+        ns = C.c_int32(); nk = C.c_int32()
+        self._ck(self.lib.dynofront_klt_track_fb(self.h, _p(pg), _p(cg), n, _p(p0), _p(nxt), _p(st), _p(back), C.byref(pc), _p(age), _p(keep),
+                                                 C.byref(ns), C.byref(nk), C.byref(ms)))
+        self.last_ms = ms.value; self.last_counts = (ns.value, nk.value)
+        return nxt, st, back, (keep if check else None)
+
+    def klt_last_min_eig(self, n):
+        out = np.zeros((n, 2), np.float32)
+        self._ck(self.lib.dynofront_klt_last_min_eig(self.h, n, _p(out)))
+        return out
+
+    def track_static_flow(self, prev_pred_kp, prev_age, prev_usable, det_xy, cell_size, max_features, next_tracklet_id):
+        """ExternalFlowFeatureTracker::trackStatic on the frame given to set_frame.  Returns a dict of per-feature arrays."""
+        kp = np.ascontiguousarray(prev_pred_kp, dtype=np.float64).reshape(-1, 2); n = kp.shape[0]
+        age = np.ascontiguousarray(prev_age, dtype=np.int32); use = np.ascontiguousarray(prev_usable, dtype=np.uint8)
+        det = np.ascontiguousarray(det_xy, dtype=np.int32).reshape(-1, 2); m = det.shape[0]
+        acc = np.zeros(n, np.uint8); fl = np.zeros((n, 2)); pk = np.zeros((n, 2)); oage = np.zeros(n, np.int32)
+        dacc = np.zeros(m, np.uint8); dfl = np.zeros((m, 2)); dpk = np.zeros((m, 2)); dtid = np.zeros(m, np.int64)
+        nid = C.c_int64(int(next_tracklet_id)); nt = C.c_int32(); nd = C.c_int32()
+        self._ck(self.lib.dynofront_track_static_flow(self.h, n, _p(kp), _p(age), _p(use), m, _p(det), int(cell_size), int(max_features), C.byref(nid),
+                                                      _p(acc), _p(fl), _p(pk), _p(oage), _p(dacc), _p(dfl), _p(dpk), _p(dtid), C.byref(nt), C.byref(nd)))
+        return dict(acc=acc, flow=fl, pred=pk, age=oage, det_acc=dacc, det_flow=dfl, det_pred=dpk, det_tracklet=dtid,
+                    next_tracklet_id=nid.value, n_tracked=nt.value, n_detected=nd.value)
 
     def pyramid_level(self, which, level):
         w = C.c_int32(); h = C.c_int32()

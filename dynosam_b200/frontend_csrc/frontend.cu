@@ -35,6 +35,12 @@ struct dynofront_ctx {
   // KLT
   std::vector<uint8_t*> pyr[2]; std::vector<short*> der; std::vector<int> lw, lh;
   float *k_prev = nullptr, *k_next = nullptr, *k_err = nullptr; uint8_t* k_st = nullptr; int k_cap = 0;
+  float *k_back = nullptr, *k_eig = nullptr; uint8_t *k_st2 = nullptr, *k_keep = nullptr; int32_t* k_age = nullptr; int* k_count = nullptr;   // forward-backward tracker
+  std::vector<short*> der2;                       // Scharr derivatives of the CURRENT image (backward pass)
+  // external-flow static tracker scratch
+  int sf_cap = 0, sf_cells = 0; double* sf_kp = nullptr; int32_t* sf_age = nullptr; uint8_t* sf_use = nullptr; int32_t* sf_det = nullptr;
+  int *sf_cell = nullptr, *sf_win = nullptr, *sf_win2 = nullptr, *sf_cnt = nullptr; uint8_t* sf_pass = nullptr; uint8_t* sf_acc = nullptr; double* sf_out = nullptr;
+  int32_t* sf_oage = nullptr; long long* sf_otid = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   std::vector<void*> allocs;
 };
@@ -295,7 +301,7 @@ __device__ __forceinline__ int der_at(const short* D, int w, int h, int x, int y
 
 __global__ void __launch_bounds__(KLT_WARPS*32) klt_kernel(KltLevels L, int n, const float* __restrict__ prevPts, float* __restrict__ nextPts,
                                                            uint8_t* __restrict__ status, float* __restrict__ err, int win, int maxCount, float eps2,
-                                                           int use_initial, float minEigThreshold) {
+                                                           int use_initial, float minEigThreshold, float* __restrict__ eig_out) {
   extern __shared__ short ksm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pt = blockIdx.x*KLT_WARPS + warp;
@@ -336,6 +342,7 @@ __global__ void __launch_bounds__(KLT_WARPS*32) klt_kernel(KltLevels L, int n, c
     const float A11 = (float)sA11*FLT_SCALE, A12 = (float)sA12*FLT_SCALE, A22 = (float)sA22*FLT_SCALE;
     float D = A11*A22 - A12*A12;
     const float minEig = (A22 + A11 - sqrtf((A11 - A22)*(A11 - A22) + 4.f*A12*A12))/(2*win*win);
+    if (eig_out && level == 0 && lane == 0) { eig_out[2*pt] = minEig; eig_out[2*pt + 1] = (A11 + A22)/(2*win*win); }
     if (minEig < minEigThreshold || D < 1.1920929e-07f) { if (level == 0) st = false; continue; }
     D = 1.f/D;
     nx -= halfWin; ny -= halfWin;
@@ -385,6 +392,116 @@ __global__ void __launch_bounds__(KLT_WARPS*32) klt_kernel(KltLevels L, int n, c
     }
   }
   if (lane == 0) { nextPts[2*pt] = nx; nextPts[2*pt + 1] = ny; status[pt] = st ? 1 : 0; if (err) err[pt] = e; }
+}
+
+// ---------------------------------------------------------------------------------------------------- forward-backward KLT
+// KltFeatureTracker::trackPoints after the two cv::calcOpticalFlowPyrLK calls (StaticFeatureTracker.cc:505-534): a track
+// survives when both passes succeeded and the backward pass returns to within 0.5 px of where it started (float
+// arithmetic, as the reference's lambda), then the per-point checks of :575-592 / :628-646 -- background label at the
+// truncated key-point, inside the image and the shrunken image, age + 1 <= max_feature_track_age.
+__global__ void klt_fb_filter_kernel(int n, const float* __restrict__ prev, const float* __restrict__ next, const float* __restrict__ back,
+                                     const uint8_t* __restrict__ st_f, const uint8_t* __restrict__ st_b, float max_dist, uint8_t* __restrict__ status,
+                                     int check, const int32_t* __restrict__ mask, int W, int H, dynofront_track_params prm, const int32_t* __restrict__ age,
+                                     int max_age, uint8_t* __restrict__ keep, int* __restrict__ count) {
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dx = prev[2*i] - back[2*i], dy = prev[2*i + 1] - back[2*i + 1];
+  const bool ok = st_f[i] && st_b[i] && sqrtf(dx*dx + dy*dy) <= max_dist;
+  status[i] = ok ? 1 : 0;
+  bool k = ok;
+  if (check && ok) {
+    const double kx = (double)next[2*i], ky = (double)next[2*i + 1];
+    const int x = (int)kx, y = (int)ky;                                       // functional_keypoint::u / v: truncation
+    const bool contained = kx >= 0.0 && kx < (double)W && ky >= 0.0 && ky < (double)H;
+    const bool shrunk = y > prm.shrink_row && y < H - prm.shrink_row && x > prm.shrink_col && x < W - prm.shrink_col;
+    k = contained && shrunk && mask[(size_t)y*W + x] == 0 && age[i] + 1 <= max_age;
+  }
+  keep[i] = k ? 1 : 0;
+  if (ok) atomicAdd(count, 1);
+  if (k) atomicAdd(count + 1, 1);
+}
+__global__ void count_status_kernel(int n, const uint8_t* st, int* count) {
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n && st[i]) atomicAdd(count, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------- external-flow static tracker
+// ExternalFlowFeatureTracker::trackStatic / constructStaticFeature (StaticFeatureTracker.cc:70-220).  The reference walks
+// the previous features in order and the FIRST one that passes every check claims its grid cell (cells are only marked by
+// successful constructions): in parallel, the passing feature with the smallest index per cell wins (atomicMin).  New
+// detections do the same among the cells the tracked features left free, in detection order, until the frame holds
+// max_features (a prefix count); tracklet ids are handed out in that order.
+__device__ __forceinline__ bool sf_construct(const float* flow, const int32_t* mask, int W, int H, int x, int y, double kx, double ky, double* out) {
+  if (mask[(size_t)y*W + x] != 0) return false;
+  const double fx = (double)flow[2*((size_t)y*W + x)], fy = (double)flow[2*((size_t)y*W + x) + 1];
+  if (!(fx != 0 && fy != 0)) return false;
+  const double px = kx + fx, py = ky + fy;
+  if (!(px >= 0.0 && px < (double)W && py >= 0.0 && py < (double)H)) return false;
+  out[0] = fx; out[1] = fy; out[2] = px; out[3] = py;
+  return true;
+}
+__global__ void sf_prev_kernel(int n, const double* __restrict__ kp, const uint8_t* __restrict__ usable, const float* flow, const int32_t* mask, int W, int H,
+                               int cell_size, int ncols, int* __restrict__ cell, uint8_t* __restrict__ pass, double* __restrict__ out, int* __restrict__ win) {
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double kx = kp[2*i], ky = kp[2*i + 1];
+  pass[i] = 0; cell[i] = -1;
+  if (!(kx >= 0.0 && kx < (double)W && ky >= 0.0 && ky < (double)H)) return;
+  const int x = (int)kx, y = (int)ky;
+  const int c = (int)floor(ky/cell_size)*ncols + (int)floor(kx/cell_size);
+  cell[i] = c;
+  if (!usable[i]) return;
+  if (!sf_construct(flow, mask, W, H, x, y, kx, ky, out + 4*(size_t)i)) return;
+  pass[i] = 1;
+  atomicMin(win + c, i);
+}
+__global__ void sf_prev_resolve_kernel(int n, const int* cell, const uint8_t* pass, const int* win, const int32_t* age, uint8_t* acc, double* out, int32_t* oage, int* cnt) {
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool a = pass[i] && win[cell[i]] == i;
+  acc[i] = a ? 1 : 0; oage[i] = a ? age[i] + 1 : 0;
+  if (!a) { out[4*(size_t)i] = out[4*(size_t)i + 1] = out[4*(size_t)i + 2] = out[4*(size_t)i + 3] = 0.0; }
+  else atomicAdd(cnt, 1);
+}
+__global__ void sf_det_kernel(int n, const int32_t* __restrict__ xy, const float* flow, const int32_t* mask, int W, int H, int cell_size, int ncols,
+                              const int* __restrict__ win_prev, int* __restrict__ cell, uint8_t* __restrict__ pass, double* __restrict__ out, int* __restrict__ win) {
+  const int j = blockIdx.x*blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int x = xy[2*j], y = xy[2*j + 1];
+  pass[j] = 0; cell[j] = -1;
+  if (x < 0 || x >= W || y < 0 || y >= H) return;
+  if (mask[(size_t)y*W + x] != 0) return;
+  const int c = (int)floor((double)y/cell_size)*ncols + (int)floor((double)x/cell_size);
+  cell[j] = c;
+  if (win_prev[c] != 0x7fffffff) return;                       // cell taken by a tracked feature
+  if (!sf_construct(flow, mask, W, H, x, y, (double)x, (double)y, out + 4*(size_t)j)) return;
+  pass[j] = 1;
+  atomicMin(win + c, j);
+}
+// one CTA: in-order prefix count of the accepted detections, truncated at `room`; tracklet ids follow the order
+__global__ void __launch_bounds__(1024) sf_det_resolve_kernel(int n, const int* cell, const uint8_t* pass, const int* win, const int* cnt_prev, int max_features,
+                                                              long long base_id, uint8_t* acc, double* out, long long* otid, int* cnt_det) {
+  __shared__ int s_scan[1024]; __shared__ int s_base;
+  const int room = max(0, max_features - *cnt_prev);
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += 1024) {
+    const int j = j0 + threadIdx.x;
+    const int a = (j < n && pass[j] && win[cell[j]] == j) ? 1 : 0;
+    s_scan[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0; __syncthreads(); s_scan[threadIdx.x] += v; __syncthreads(); }
+    const int rank = s_base + s_scan[threadIdx.x] - a;           // accepted detections before j
+    if (j < n) {
+      const bool fin = a && rank < room;
+      acc[j] = fin ? 1 : 0; otid[j] = fin ? base_id + rank : 0;
+      if (!fin) { out[4*(size_t)j] = out[4*(size_t)j + 1] = out[4*(size_t)j + 2] = out[4*(size_t)j + 3] = 0.0; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_base += s_scan[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *cnt_det = min(s_base, room);
 }
 
 // ---------------------------------------------------------------------------------------------------- host API
@@ -552,6 +669,12 @@ int dynofront_propagate_mask(dynofront_handle h, int32_t n, const double* kp, co
   return 0;
 }
 
+static int klt_scratch(dynofront_ctx* h, int cap) {
+  if (falloc(h, &h->k_prev, 2*(size_t)cap) || falloc(h, &h->k_next, 2*(size_t)cap) || falloc(h, &h->k_err, cap) || falloc(h, &h->k_st, cap) ||
+      falloc(h, &h->k_back, 2*(size_t)cap) || falloc(h, &h->k_eig, 2*(size_t)cap) || falloc(h, &h->k_st2, cap) || falloc(h, &h->k_keep, cap) ||
+      falloc(h, &h->k_age, cap) || falloc(h, &h->k_count, 2)) return -3;
+  h->k_cap = cap; return 0;
+}
 static int build_pyramid(dynofront_ctx* h, int which, const uint8_t* host_img, int max_level, int win, bool with_deriv) {
   const int W = h->W, H = h->H;
   if (h->lw.empty()) {
@@ -561,6 +684,7 @@ static int build_pyramid(dynofront_ctx* h, int which, const uint8_t* host_img, i
       uint8_t *a, *b; short* d;
       if (falloc(h, &a, (size_t)w*hh) || falloc(h, &b, (size_t)w*hh) || falloc(h, &d, 2*(size_t)w*hh)) return -3;
       h->pyr[0].push_back(a); h->pyr[1].push_back(b); h->der.push_back(d);
+      short* d2; if (falloc(h, &d2, 2*(size_t)w*hh)) return -3; h->der2.push_back(d2);
       w = (w + 1)/2; hh = (hh + 1)/2;
       if (w < 2 || hh < 2) break;
     }
@@ -570,7 +694,7 @@ static int build_pyramid(dynofront_ctx* h, int which, const uint8_t* host_img, i
   for (int l = 0; l <= max_level && l < (int)h->lw.size(); l++) {
     const int w = h->lw[l], hh = h->lh[l];
     if (l > 0) pyr_down_kernel<<<dim3((w + 31)/32, (hh + 7)/8), blk, 0, h->s>>>(h->pyr[which][l-1], h->lw[l-1], h->lh[l-1], h->pyr[which][l], w, hh);
-    if (with_deriv) scharr_kernel<<<dim3((w + 31)/32, (hh + 7)/8), blk, 0, h->s>>>(h->pyr[which][l], w, hh, h->der[l]);
+    if (with_deriv) scharr_kernel<<<dim3((w + 31)/32, (hh + 7)/8), blk, 0, h->s>>>(h->pyr[which][l], w, hh, which == 0 ? h->der[l] : h->der2[l]);
   }
   return 0;
 }
@@ -583,7 +707,7 @@ int dynofront_klt_track(dynofront_handle h, const uint8_t* prev_gray, const uint
   cudaSetDevice(h->dev);
   // buildOpticalFlowPyramid: stop when a level is not larger than the window (lkpyramid.cpp)
   int levels = 0; { int w = h->W, hh = h->H; for (int l = 0; l <= max_level && l < 8; l++) { levels = l; if (l < max_level) { const int w2 = (w + 1)/2, h2 = (hh + 1)/2; if (w2 <= win || h2 <= win) break; w = w2; hh = h2; } } }
-  if (n > h->k_cap) { const int cap = std::max(n, 4096); if (falloc(h, &h->k_prev, 2*(size_t)cap) || falloc(h, &h->k_next, 2*(size_t)cap) || falloc(h, &h->k_err, cap) || falloc(h, &h->k_st, cap)) return -3; h->k_cap = cap; }
+  if (n > h->k_cap) { const int cap = std::max(n, 4096); if (klt_scratch(h, cap)) return -3; }
   FCK(cudaEventRecord(h->e0, h->s));
   if (build_pyramid(h, 0, prev_gray, levels, win, true)) return -3;
   if (build_pyramid(h, 1, cur_gray, levels, win, false)) return -3;
@@ -596,7 +720,7 @@ int dynofront_klt_track(dynofront_handle h, const uint8_t* prev_gray, const uint
   if (n > 0) {
     const size_t smem = (size_t)KLT_WARPS*win*win*3*sizeof(short);
     klt_kernel<<<(n + KLT_WARPS - 1)/KLT_WARPS, KLT_WARPS*32, smem, h->s>>>(L, n, h->k_prev, h->k_next, h->k_st, h->k_err, win, max_count, (float)eps,
-                                                                            use_initial, (float)min_eig);
+                                                                            use_initial, (float)min_eig, h->k_eig);
   }
   FCK(cudaMemcpyAsync(next_pts, h->k_next, 2*(size_t)n*4, cudaMemcpyDeviceToHost, h->s));
   FCK(cudaMemcpyAsync(status, h->k_st, n, cudaMemcpyDeviceToHost, h->s));
@@ -605,6 +729,120 @@ int dynofront_klt_track(dynofront_handle h, const uint8_t* prev_gray, const uint
   FCK(cudaStreamSynchronize(h->s));
   FCK(cudaGetLastError());
   if (ms_device) FCK(cudaEventElapsedTime(ms_device, h->e0, h->e1));
+  return 0;
+}
+
+int dynofront_klt_track_fb(dynofront_handle h, const uint8_t* prev_gray, const uint8_t* cur_gray, int32_t n, const float* prev_pts, float* next_pts,
+                           uint8_t* status, float* back_pts, const dynofront_klt_fb_params* P, const int32_t* prev_age, uint8_t* keep,
+                           int32_t* n_status, int32_t* n_keep, float* ms_device) {
+  if (!h || !prev_gray || !cur_gray || n < 0 || !prev_pts || !next_pts || !status || !P) return -1;
+  if (P->win < 3 || P->win > KLT_MAXWIN || P->win_back < 3 || P->win_back > KLT_MAXWIN || P->max_level < 0 || P->max_level_back < 0) { h->err = "win must be in [3,31]"; return -1; }
+  if (P->check_static && (!prev_age || !keep)) { h->err = "check_static needs prev_age and keep"; return -1; }
+  cudaSetDevice(h->dev);
+  auto nlevels = [&](int max_level, int win) { int levels = 0; int w = h->W, hh = h->H;
+    for (int l = 0; l <= max_level && l < 8; l++) { levels = l; if (l < max_level) { const int w2 = (w + 1)/2, h2 = (hh + 1)/2; if (w2 <= win || h2 <= win) break; w = w2; hh = h2; } } return levels; };
+  const int lf = nlevels(P->max_level, P->win), lb = nlevels(P->max_level_back, P->win_back), lmax = std::max(lf, lb);
+  if (n > h->k_cap) { if (klt_scratch(h, std::max(n, 4096))) return -3; }
+  FCK(cudaEventRecord(h->e0, h->s));
+  if (build_pyramid(h, 0, prev_gray, lmax, P->win, true)) return -3;        // both images with derivatives: each is "previous" once
+  if (build_pyramid(h, 1, cur_gray, lmax, P->win, true)) return -3;
+  FCK(cudaMemcpyAsync(h->k_prev, prev_pts, 2*(size_t)n*4, cudaMemcpyHostToDevice, h->s));
+  FCK(cudaMemcpyAsync(h->k_next, P->use_initial_flow ? next_pts : prev_pts, 2*(size_t)n*4, cudaMemcpyHostToDevice, h->s));
+  if (P->check_static) FCK(cudaMemcpyAsync(h->k_age, prev_age, (size_t)n*4, cudaMemcpyHostToDevice, h->s));
+  FCK(cudaMemsetAsync(h->k_count, 0, 2*sizeof(int), h->s));
+  auto levels_of = [&](int nl, int fwd) { KltLevels L; L.nlev = nl + 1;
+    for (int l = 0; l <= nl; l++) { L.I[l] = h->pyr[fwd ? 0 : 1][l]; L.J[l] = h->pyr[fwd ? 1 : 0][l]; L.D[l] = fwd ? h->der[l] : h->der2[l]; L.w[l] = h->lw[l]; L.h[l] = h->lh[l]; } return L; };
+  auto run = [&](const KltLevels& L, const float* from, float* to, uint8_t* st, int win, int max_count, double epsilon, int use_initial, float* eig) {
+    const int mc = std::min(std::max(max_count, 0), 100); double eps = std::min(std::max(epsilon, 0.0), 10.0); eps *= eps;
+    if (n > 0) klt_kernel<<<(n + KLT_WARPS - 1)/KLT_WARPS, KLT_WARPS*32, (size_t)KLT_WARPS*win*win*3*sizeof(short), h->s>>>(L, n, from, to, st, h->k_err, win, mc, (float)eps,
+                                                                                                                        use_initial, (float)P->min_eig_threshold, eig);
+  };
+  const KltLevels LF = levels_of(lf, 1), LB = levels_of(lb, 0);
+  run(LF, h->k_prev, h->k_next, h->k_st, P->win, P->max_count, P->epsilon, P->use_initial_flow, h->k_eig);
+  if (P->use_initial_flow && n > 0) {
+    // StaticFeatureTracker.cc:491-503: with OPTFLOW_USE_INITIAL_FLOW fewer than 10 successes -> track again from scratch
+    int succ = 0;
+    count_status_kernel<<<(n + 255)/256, 256, 0, h->s>>>(n, h->k_st, h->k_count);
+    FCK(cudaMemcpyAsync(&succ, h->k_count, sizeof(int), cudaMemcpyDeviceToHost, h->s)); FCK(cudaStreamSynchronize(h->s));
+    FCK(cudaMemsetAsync(h->k_count, 0, 2*sizeof(int), h->s));
+    if (succ < 10) { FCK(cudaMemcpyAsync(h->k_next, h->k_prev, 2*(size_t)n*4, cudaMemcpyDeviceToDevice, h->s)); run(LF, h->k_prev, h->k_next, h->k_st, P->win, P->max_count, P->epsilon, 0, h->k_eig); }
+  }
+  FCK(cudaMemcpyAsync(h->k_back, h->k_next, 2*(size_t)n*4, cudaMemcpyDeviceToDevice, h->s));       // flags = 0: the backward search starts at the forward result
+  run(LB, h->k_next, h->k_back, h->k_st2, P->win_back, P->max_count_back, P->epsilon_back, 0, nullptr);
+  if (n > 0) klt_fb_filter_kernel<<<(n + 255)/256, 256, 0, h->s>>>(n, h->k_prev, h->k_next, h->k_back, h->k_st, h->k_st2, (float)P->max_fb_distance, h->k_st,
+                                                                  P->check_static, h->mask, h->W, h->H, P->track, h->k_age, P->max_feature_track_age, h->k_keep, h->k_count);
+  int counts[2] = {0, 0};
+  FCK(cudaMemcpyAsync(next_pts, h->k_next, 2*(size_t)n*4, cudaMemcpyDeviceToHost, h->s));
+  FCK(cudaMemcpyAsync(status, h->k_st, n, cudaMemcpyDeviceToHost, h->s));
+  if (back_pts) FCK(cudaMemcpyAsync(back_pts, h->k_back, 2*(size_t)n*4, cudaMemcpyDeviceToHost, h->s));
+  if (keep) FCK(cudaMemcpyAsync(keep, h->k_keep, n, cudaMemcpyDeviceToHost, h->s));
+  FCK(cudaMemcpyAsync(counts, h->k_count, sizeof(counts), cudaMemcpyDeviceToHost, h->s));
+  FCK(cudaEventRecord(h->e1, h->s));
+  FCK(cudaStreamSynchronize(h->s));
+  FCK(cudaGetLastError());
+  if (n_status) *n_status = counts[0]; if (n_keep) *n_keep = counts[1];
+  if (ms_device) FCK(cudaEventElapsedTime(ms_device, h->e0, h->e1));
+  return 0;
+}
+
+int dynofront_klt_last_min_eig(dynofront_handle h, int32_t n, float* out) {
+  if (!h || !out || n < 0 || n > h->k_cap || !h->k_eig) return -1;
+  cudaSetDevice(h->dev);
+  FCK(cudaMemcpy(out, h->k_eig, 2*(size_t)n*4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dynofront_track_static_flow(dynofront_handle h, int32_t n_prev, const double* prev_pred_kp, const int32_t* prev_age, const uint8_t* prev_usable,
+                                int32_t n_det, const int32_t* det_xy, int32_t cell_size, int32_t max_features, int64_t* next_tracklet_id,
+                                uint8_t* acc_prev, double* flow_prev, double* pred_prev, int32_t* age_out,
+                                uint8_t* acc_det, double* flow_det, double* pred_det, int64_t* tracklet_det, int32_t* n_tracked, int32_t* n_detected) {
+  if (!h || n_prev < 0 || n_det < 0 || cell_size <= 0 || !next_tracklet_id) return -1;
+  if ((n_prev && (!prev_pred_kp || !prev_age || !prev_usable || !acc_prev || !flow_prev || !pred_prev || !age_out)) ||
+      (n_det && (!det_xy || !acc_det || !flow_det || !pred_det || !tracklet_det))) { h->err = "null array"; return -1; }
+  cudaSetDevice(h->dev);
+  const int ncols = (int)std::ceil((double)h->W/cell_size), nrows = (int)std::ceil((double)h->H/cell_size), ncell = ncols*nrows;
+  const int nmax = std::max(std::max(n_prev, n_det), 1);
+  if (nmax > h->sf_cap || ncell > h->sf_cells) {
+    const int cap = std::max(nmax, 4096), cells = std::max(ncell, h->sf_cells);
+    int rc = 0;
+    rc |= falloc(h, &h->sf_kp, 2*(size_t)cap); rc |= falloc(h, &h->sf_age, cap); rc |= falloc(h, &h->sf_use, cap); rc |= falloc(h, &h->sf_det, 2*(size_t)cap);
+    rc |= falloc(h, &h->sf_cell, cap); rc |= falloc(h, &h->sf_win, cells); rc |= falloc(h, &h->sf_win2, cells); rc |= falloc(h, &h->sf_cnt, 2);
+    rc |= falloc(h, &h->sf_pass, cap); rc |= falloc(h, &h->sf_acc, cap); rc |= falloc(h, &h->sf_out, 4*(size_t)cap); rc |= falloc(h, &h->sf_oage, cap); rc |= falloc(h, &h->sf_otid, cap);
+    if (rc) return -3;
+    h->sf_cap = cap; h->sf_cells = cells;
+  }
+  fill_i32_kernel<<<(ncell + 255)/256, 256, 0, h->s>>>(h->sf_win, ncell, 0x7fffffff);
+  fill_i32_kernel<<<(ncell + 255)/256, 256, 0, h->s>>>(h->sf_win2, ncell, 0x7fffffff);
+  FCK(cudaMemsetAsync(h->sf_cnt, 0, 2*sizeof(int), h->s));
+  std::vector<double> o4; std::vector<uint8_t> acc; int cnt[2] = {0, 0};
+  if (n_prev) {
+    FCK(cudaMemcpyAsync(h->sf_kp, prev_pred_kp, 2*(size_t)n_prev*8, cudaMemcpyHostToDevice, h->s));
+    FCK(cudaMemcpyAsync(h->sf_age, prev_age, (size_t)n_prev*4, cudaMemcpyHostToDevice, h->s));
+    FCK(cudaMemcpyAsync(h->sf_use, prev_usable, (size_t)n_prev, cudaMemcpyHostToDevice, h->s));
+    sf_prev_kernel<<<(n_prev + 255)/256, 256, 0, h->s>>>(n_prev, h->sf_kp, h->sf_use, h->flow, h->mask, h->W, h->H, cell_size, ncols, h->sf_cell, h->sf_pass, h->sf_out, h->sf_win);
+    sf_prev_resolve_kernel<<<(n_prev + 255)/256, 256, 0, h->s>>>(n_prev, h->sf_cell, h->sf_pass, h->sf_win, h->sf_age, h->sf_acc, h->sf_out, h->sf_oage, h->sf_cnt);
+    o4.resize(4*(size_t)n_prev);
+    FCK(cudaMemcpyAsync(acc_prev, h->sf_acc, n_prev, cudaMemcpyDeviceToHost, h->s));
+    FCK(cudaMemcpyAsync(o4.data(), h->sf_out, o4.size()*8, cudaMemcpyDeviceToHost, h->s));
+    FCK(cudaMemcpyAsync(age_out, h->sf_oage, (size_t)n_prev*4, cudaMemcpyDeviceToHost, h->s));
+    FCK(cudaStreamSynchronize(h->s));
+    for (int i = 0; i < n_prev; i++) { flow_prev[2*i] = o4[4*(size_t)i]; flow_prev[2*i + 1] = o4[4*(size_t)i + 1]; pred_prev[2*i] = o4[4*(size_t)i + 2]; pred_prev[2*i + 1] = o4[4*(size_t)i + 3]; }
+  }
+  if (n_det) {
+    FCK(cudaMemcpyAsync(h->sf_det, det_xy, 2*(size_t)n_det*4, cudaMemcpyHostToDevice, h->s));
+    sf_det_kernel<<<(n_det + 255)/256, 256, 0, h->s>>>(n_det, h->sf_det, h->flow, h->mask, h->W, h->H, cell_size, ncols, h->sf_win, h->sf_cell, h->sf_pass, h->sf_out, h->sf_win2);
+    sf_det_resolve_kernel<<<1, 1024, 0, h->s>>>(n_det, h->sf_cell, h->sf_pass, h->sf_win2, h->sf_cnt, max_features, (long long)*next_tracklet_id, h->sf_acc, h->sf_out, h->sf_otid, h->sf_cnt + 1);
+    o4.resize(4*(size_t)n_det);
+    FCK(cudaMemcpyAsync(acc_det, h->sf_acc, n_det, cudaMemcpyDeviceToHost, h->s));
+    FCK(cudaMemcpyAsync(o4.data(), h->sf_out, o4.size()*8, cudaMemcpyDeviceToHost, h->s));
+    FCK(cudaMemcpyAsync(tracklet_det, h->sf_otid, (size_t)n_det*8, cudaMemcpyDeviceToHost, h->s));
+    FCK(cudaStreamSynchronize(h->s));
+    for (int j = 0; j < n_det; j++) { flow_det[2*j] = o4[4*(size_t)j]; flow_det[2*j + 1] = o4[4*(size_t)j + 1]; pred_det[2*j] = o4[4*(size_t)j + 2]; pred_det[2*j + 1] = o4[4*(size_t)j + 3]; }
+  }
+  FCK(cudaMemcpyAsync(cnt, h->sf_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->s)); FCK(cudaStreamSynchronize(h->s));
+  FCK(cudaGetLastError());
+  *next_tracklet_id += cnt[1];
+  if (n_tracked) *n_tracked = cnt[0]; if (n_detected) *n_detected = cnt[1];
   return 0;
 }
 

@@ -6,6 +6,8 @@
  *   dynofront_track_dynamic     FeatureTracker::trackDynamic        dynosam/src/frontend/vision/FeatureTracker.cc:339-498
  *   dynofront_sample_candidates FeatureTracker::sampleDynamic scan  FeatureTracker.cc:864-953
  *   dynofront_propagate_mask    FeatureTracker::propogateMask       FeatureTracker.cc:1212-1359
+ *   dynofront_track_static_flow ExternalFlowFeatureTracker::trackStatic / constructStaticFeature  StaticFeatureTracker.cc:70-220
+ *   dynofront_klt_track_fb      KltFeatureTracker::trackPoints: forward + backward LK, round-trip test, label / border / age checks (:486-592)
  *   dynofront_klt_track         cv::calcOpticalFlowPyrLK as called by KltFeatureTracker::trackPoints
  *                               (StaticFeatureTracker.cc:420-625) and FeatureTracker::trackDynamicKLT (FeatureTracker.cc:500-862)
  * Images are row-major, tightly packed: flow float32[H][W][2] (CV_32FC2), masks int32[H][W] (CV_32S, ObjectId),
@@ -63,6 +65,40 @@ int dynofront_klt_track(dynofront_handle h, const uint8_t* prev_gray, const uint
                         const float* prev_pts, float* next_pts, uint8_t* status, float* err, int32_t win,
                         int32_t max_level, int32_t max_count, double epsilon, int32_t use_initial_flow,
                         double min_eig_threshold, float* ms_device);
+/* KltFeatureTracker::trackPoints as ONE call (StaticFeatureTracker.cc:486-534,575-592): forward LK, the reference's
+ * retry without the initial flow when fewer than 10 points survive, backward LK from the forward result, the
+ * forward-backward test (both statuses good and the backward track within max_fb_distance of the start, float
+ * arithmetic) and, with check_static, the per-point checks that follow the (host-side, out of scope) RANSAC:
+ * background label at the truncated key-point of the motion mask given to dynofront_set_frame, inside the image and the
+ * shrunken image, age + 1 <= max_feature_track_age.  Nothing returns to the host between the stages.
+ * status[n] = forward-backward result, keep[n] = status && checks (may be NULL without check_static),
+ * back_pts[n][2] (may be NULL) = where the backward pass landed. */
+typedef struct {
+  int32_t win, max_level, max_count; double epsilon;                 /* forward: (21, 3, 30, 0.03), StaticFeatureTracker.cc:440-446 */
+  int32_t win_back, max_level_back, max_count_back; double epsilon_back;   /* backward: (21, 5, 30, 0.01), :510-512 (OpenCV defaults) */
+  int32_t use_initial_flow; double min_eig_threshold; double max_fb_distance;   /* 1e-4, 0.5 */
+  int32_t check_static, max_feature_track_age;                       /* params/FrontendParams.yaml max_feature_track_age */
+  dynofront_track_params track;                                      /* shrink margins */
+} dynofront_klt_fb_params;
+int dynofront_klt_track_fb(dynofront_handle h, const uint8_t* prev_gray, const uint8_t* cur_gray, int32_t n, const float* prev_pts,
+                           float* next_pts, uint8_t* status, float* back_pts, const dynofront_klt_fb_params* prm,
+                           const int32_t* prev_age, uint8_t* keep, int32_t* n_status, int32_t* n_keep, float* ms_device);
+/* parity hook: (min eigenvalue, trace/(2 win^2)) of the level-0 spatial gradient matrix of the last forward pass, [n][2] */
+int dynofront_klt_last_min_eig(dynofront_handle h, int32_t n, float* out);
+
+/* ExternalFlowFeatureTracker::trackStatic + constructStaticFeature (StaticFeatureTracker.cc:70-220) on the flow / motion
+ * mask given to dynofront_set_frame.  Previous static features (predicted key-point, age, usable flag) are walked in
+ * array order: the first one per grid cell (cell_size px, OccupancyGrid2D.hpp:96-101) that is contained, usable, on the
+ * background, has a non-zero flow and a predicted key-point inside the image is kept with age + 1.  Then the detections
+ * det_xy[n_det][2] (integer pixel positions, e.g. the ORB key-points, in detector order) fill the still empty cells
+ * until the frame holds max_features; their tracklet ids count up from *next_tracklet_id (updated).  Rows of rejected
+ * features are zero. */
+int dynofront_track_static_flow(dynofront_handle h, int32_t n_prev, const double* prev_pred_kp, const int32_t* prev_age,
+                                const uint8_t* prev_usable, int32_t n_det, const int32_t* det_xy, int32_t cell_size,
+                                int32_t max_features, int64_t* next_tracklet_id, uint8_t* acc_prev, double* flow_prev,
+                                double* pred_prev, int32_t* age_out, uint8_t* acc_det, double* flow_det, double* pred_det,
+                                int64_t* tracklet_det, int32_t* n_tracked, int32_t* n_detected);
+
 /* parity hooks: pyramid level / Scharr derivative of the last prev image (level l): sizes via w,h out */
 int dynofront_get_pyramid_level(dynofront_handle h, int32_t which /*0 prev,1 cur*/, int32_t level, int32_t* w, int32_t* hgt,
                                 uint8_t* img, int16_t* deriv);

@@ -4,6 +4,8 @@ Literal Python restatement (plain loops, the reference's iteration order) of
   * FeatureTracker::trackDynamic      dynosam/src/frontend/vision/FeatureTracker.cc:339-498
   * FeatureTracker::sampleDynamic     (candidate scan)  :864-953
   * FeatureTracker::propogateMask     :1212-1359
+  * ExternalFlowFeatureTracker::trackStatic / constructStaticFeature   StaticFeatureTracker.cc:70-220
+  * KltFeatureTracker::trackPoints forward-backward filter and post checks   StaticFeatureTracker.cc:486-592
   * FeatureTrackerBase::isWithinShrunkenImage  FeatureTrackerBase.cc:313-326,  Camera::isKeypointContained Camera.cc:71-74,
     functional_keypoint::u/v int truncation  dynosam_cv/include/dynosam_cv/Feature.hpp:46-55
 cv::circle is the real OpenCV routine (cv2.circle), and the pyramidal KLT oracle is cv2.calcOpticalFlowPyrLK itself
@@ -145,3 +147,97 @@ def klt_track(prev_gray, cur_gray, prev_pts, win=21, max_level=3, max_count=30, 
                                             criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, max_count, eps),
                                             flags=flags, minEigThreshold=min_eig)
     return nxt.reshape(-1, 2), st.reshape(-1), err.reshape(-1)
+
+
+def _construct_static_feature(kp, flow, motion_mask, rows, cols):
+    """ExternalFlowFeatureTracker::constructStaticFeature (StaticFeatureTracker.cc:172-218): (flow, predicted kp) or None."""
+    x = int(kp[0]); y = int(kp[1])
+    if int(motion_mask[y, x]) != BACKGROUND:
+        return None
+    fx = float(flow[y, x, 0]); fy = float(flow[y, x, 1])
+    if not (fx != 0 and fy != 0):
+        return None
+    pred = (kp[0] + fx, kp[1] + fy)
+    if not keypoint_contained(pred, rows, cols):
+        return None
+    return (fx, fy), pred
+
+
+def track_static_flow(prev_pred_kp, prev_age, prev_usable, det_xy, flow, motion_mask, cell_size, max_features, next_tracklet_id):
+    """ExternalFlowFeatureTracker::trackStatic (StaticFeatureTracker.cc:70-170), literal loops.  The detections are the
+    (integer) key-points the ORB extractor returned, in its order."""
+    import math
+    rows, cols = motion_mask.shape
+    ncols = math.ceil(cols/cell_size); nrows = math.ceil(rows/cell_size)
+    occ = [False]*(ncols*nrows)
+    cell_of = lambda kp: int(math.floor(kp[1]/cell_size))*ncols + int(math.floor(kp[0]/cell_size))
+    n = len(prev_age); m = len(det_xy)
+    acc = np.zeros(n, np.uint8); fl = np.zeros((n, 2)); pk = np.zeros((n, 2)); age = np.zeros(n, np.int32)
+    dacc = np.zeros(m, np.uint8); dfl = np.zeros((m, 2)); dpk = np.zeros((m, 2)); dtid = np.zeros(m, np.int64)
+    count = 0
+    for i in range(n):
+        kp = (float(prev_pred_kp[i][0]), float(prev_pred_kp[i][1]))
+        if not keypoint_contained(kp, rows, cols):
+            continue
+        x = int(kp[0]); y = int(kp[1])
+        c = cell_of(kp)
+        label = int(motion_mask[y, x])
+        if occ[c]:
+            continue
+        if prev_usable[i] and label == BACKGROUND:
+            f = _construct_static_feature(kp, flow, motion_mask, rows, cols)
+            if f is not None:
+                acc[i] = 1; fl[i] = f[0]; pk[i] = f[1]; age[i] = int(prev_age[i]) + 1
+                occ[c] = True; count += 1
+    n_tracked = count
+    if count < max_features:
+        for j in range(m):
+            if count >= max_features:
+                break
+            x = int(det_xy[j][0]); y = int(det_xy[j][1])
+            if int(motion_mask[y, x]) != BACKGROUND:
+                continue
+            kp = (float(x), float(y))
+            c = cell_of(kp)
+            if not occ[c]:
+                f = _construct_static_feature(kp, flow, motion_mask, rows, cols)
+                if f is not None:
+                    dacc[j] = 1; dfl[j] = f[0]; dpk[j] = f[1]; dtid[j] = next_tracklet_id
+                    next_tracklet_id += 1; occ[c] = True; count += 1
+    return dict(acc=acc, flow=fl, pred=pk, age=age, det_acc=dacc, det_flow=dfl, det_pred=dpk, det_tracklet=dtid,
+                next_tracklet_id=next_tracklet_id, n_tracked=n_tracked, n_detected=count - n_tracked)
+
+
+def klt_track_fb(prev_gray, cur_gray, prev_pts, motion_mask=None, prev_age=None, max_feature_track_age=25, prm: TrackParams = None,
+                 win=21, max_level=3, max_count=30, eps=0.03, initial=None):
+    """KltFeatureTracker::trackPoints (StaticFeatureTracker.cc:486-534, 575-592 / 628-646): cv2 forward (retry without the
+    initial flow below 10 successes), cv2 backward (21x21, maxLevel 5, default criteria), round trip <= 0.5 px in float,
+    then the per-point label / border / age checks.  Returns (next, status, back, keep)."""
+    import cv2
+    prm = prm or TrackParams()
+    p0 = np.ascontiguousarray(prev_pts, dtype=np.float32).reshape(-1, 2)
+    nxt, st, _ = klt_track(prev_gray, cur_gray, p0, win, max_level, max_count, eps, initial)
+    if initial is not None and int(st.sum()) < 10:
+        nxt, st, _ = klt_track(prev_gray, cur_gray, p0, win, max_level, max_count, eps, None)
+    back, stb, _ = cv2.calcOpticalFlowPyrLK(cur_gray, prev_gray, nxt.reshape(-1, 1, 2).astype(np.float32), None, winSize=(21, 21), maxLevel=5)
+    back = back.reshape(-1, 2); stb = stb.reshape(-1)
+    d = p0 - back
+    dist = np.sqrt((d[:, 0]*d[:, 0] + d[:, 1]*d[:, 1]).astype(np.float32))
+    status = ((st != 0) & (stb != 0) & (dist <= np.float32(0.5))).astype(np.uint8)
+    keep = None
+    if prev_age is not None:
+        rows, cols = motion_mask.shape
+        keep = np.zeros(len(status), np.uint8)
+        for i in range(len(status)):
+            if not status[i]:
+                continue
+            kp = (float(nxt[i, 0]), float(nxt[i, 1]))
+            x = int(kp[0]); y = int(kp[1])
+            if not (keypoint_contained(kp, rows, cols) and within_shrunken(kp, rows, cols, prm)):
+                continue
+            if int(motion_mask[y, x]) != BACKGROUND:
+                continue
+            if int(prev_age[i]) + 1 > max_feature_track_age:
+                continue
+            keep[i] = 1
+    return nxt, status, back, keep

@@ -183,9 +183,98 @@ def test_klt_matches_opencv(max_level, initial):
     nxt, stt, err = t.klt_track(g0, g1, pts, win=21, max_level=max_level, max_count=30, eps=0.03, initial=init)
     rn, rs, re = FO.klt_track(g0, g1, pts, 21, max_level, 30, 0.03, init)
     agree = stt == rs
-    # status flags: bit-exact except where cv2's float accumulation puts minEig within rounding of the threshold
+    # status flags: bit-exact except where cv2's float accumulation (its 21x21 sums run in fp32 SIMD lanes, ours are exact
+    # integers) lands on the other side of a threshold.  The one tolerated deviation, proven per point: a mismatching point
+    # has its level-0 min eigenvalue within fp32 accumulation error of minEigThreshold (the error of a 441-term fp32 sum
+    # relative to the matrix trace), or both sides agree that it is tracked but the final position left the image by a
+    # sub-pixel amount (positions differ by < 1e-2 px).
     assert agree.mean() >= 0.998, agree.mean()
+    eig = t.klt_last_min_eig(n)
+    for i in np.flatnonzero(~agree):
+        near_threshold = abs(float(eig[i, 0]) - 1e-4) <= 441*2.0**-24*max(float(eig[i, 1]), 1e-4)
+        x, y = (rn[i] if rs[i] else nxt[i])
+        at_border = min(x, y, W - 1 - x, H - 1 - y) < 22 + 1e-2
+        assert near_threshold or at_border, (i, eig[i], stt[i], rs[i], nxt[i], rn[i])
     both = (stt == 1) & (rs == 1)
     d = np.abs(nxt[both] - rn[both]).max(axis=1)
     assert np.percentile(d, 99) < 1e-2 and np.median(d) < 1e-3, (np.percentile(d, 99), np.median(d))
     assert np.abs(err[both] - re[both]).max() < 0.5
+
+
+def _static_inputs(rng, st_k, n_prev=1500, n_det=2500):
+    _, mask, flow = st_k
+    kp = np.stack([rng.uniform(-3, W + 3, n_prev), rng.uniform(-3, H + 3, n_prev)], 1)      # some outside the image
+    kp[:200] = kp[200:400] + rng.uniform(-1.5, 1.5, (200, 2))                               # several features per grid cell
+    age = rng.integers(0, 30, n_prev).astype(np.int32)
+    usable = (rng.uniform(0, 1, n_prev) > 0.1).astype(np.uint8)
+    det = np.stack([rng.integers(0, W, n_det), rng.integers(0, H, n_det)], 1).astype(np.int32)
+    return kp, age, usable, det, mask, flow
+
+
+def test_static_flow_oracle_first_come_per_cell():
+    """Oracle self-check: of two usable background features in one grid cell the first in iteration order wins; a feature
+    that fails a check does not occupy its cell; detections only fill free cells and stop at max_features."""
+    from oracle import frontend_oracle as FO
+    mask = np.zeros((60, 90), np.int32); mask[:, 60:] = 2
+    flow = np.zeros((60, 90, 2), np.float32); flow[..., 0] = 1.25; flow[..., 1] = -0.5
+    flow[10, 10] = (0.0, 1.0)                                        # zero x-flow at (10, 10): constructStaticFeature fails
+    kp = np.array([[10.4, 10.2], [12.0, 11.0], [13.0, 12.0], [70.0, 5.0], [31.0, 31.0]])
+    r = FO.track_static_flow(kp, [3, 4, 5, 6, 7], [1, 1, 1, 1, 0], [(12, 12), (40, 40), (41, 41), (50, 10), (20, 50)], flow, mask, 15, 4, 100)
+    assert list(r["acc"]) == [0, 1, 0, 0, 0]           # 0: zero flow (cell stays free), 1 takes cell 0, 2 same cell, 3 on object, 4 unusable
+    assert list(r["age"]) == [0, 5, 0, 0, 0]
+    assert list(r["det_acc"]) == [0, 1, 0, 1, 1] and list(r["det_tracklet"]) == [0, 100, 0, 101, 102]   # (12,12) occupied, (41,41) same cell as (40,40)
+    assert r["next_tracklet_id"] == 103 and r["n_tracked"] == 1 and r["n_detected"] == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_features", [400, 3000])
+def test_track_static_flow_bit_exact(max_features):
+    """ExternalFlowFeatureTracker::trackStatic on the device: accept flags, ages, flows, predicted key-points and the new
+    tracklet ids equal the literal loops, with and without the max_features cut."""
+    from dynosam_b200.frontend import FeatureTrackerGPU
+    from oracle import frontend_oracle as FO
+    rng = np.random.default_rng(21)
+    stream = SyntheticStream(n_objects=10, seed=42)
+    kp, age, usable, det, mask, flow = _static_inputs(rng, stream.frame(7))
+    flow = flow.copy(); flow[::7, ::5, 0] = 0.0                      # exact zeros in the flow field
+    t = FeatureTrackerGPU(W, H); t.set_frame(flow, mask, None)
+    g = t.track_static_flow(kp, age, usable, det, 15, max_features, 5000)
+    o = FO.track_static_flow(kp, age, usable, det, flow, mask, 15, max_features, 5000)
+    for k in ("acc", "age", "det_acc", "det_tracklet"):
+        assert np.array_equal(g[k], o[k]), k
+    for k in ("flow", "pred", "det_flow", "det_pred"):
+        assert np.array_equal(g[k], o[k]), k                          # doubles formed from the same floats: bit-exact
+    assert (g["next_tracklet_id"], g["n_tracked"], g["n_detected"]) == (o["next_tracklet_id"], o["n_tracked"], o["n_detected"])
+    assert g["n_tracked"] > 100 and g["n_detected"] > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("initial", [False, True])
+def test_klt_forward_backward_on_device(initial):
+    """KltFeatureTracker::trackPoints as one device call: the forward-backward status and the label / border / age checks
+    agree with cv2 + the literal checks wherever the two LK passes themselves agree (see test_klt_matches_opencv for the
+    one tolerated deviation of the LK status)."""
+    from dynosam_b200.frontend import FeatureTrackerGPU, TrackParams
+    from oracle import frontend_oracle as FO
+    rng = np.random.default_rng(4)
+    stream = SyntheticStream(n_objects=10, seed=42)
+    g0, _, _ = stream.frame(20); g1, m1, f1 = stream.frame(21)
+    n = 800
+    pts = np.stack([rng.uniform(5, W - 5, n), rng.uniform(5, H - 5, n)], 1).astype(np.float32)
+    age = rng.integers(0, 30, n).astype(np.int32)
+    init = (pts + rng.normal(0, 0.7, pts.shape)).astype(np.float32) if initial else None
+    prm = TrackParams(shrink_row=20, shrink_col=20)
+    t = FeatureTrackerGPU(W, H); t.set_frame(f1, m1, None)
+    nxt, stt, back, keep = t.klt_track_fb(g0, g1, pts, prm, age, 25, initial=init)
+    fprm = FO.TrackParams(shrink_row=20, shrink_col=20)
+    rn, rs, rb, rk = FO.klt_track_fb(g0, g1, pts, m1, age, 25, fprm, initial=init)
+    agree = stt == rs
+    assert agree.mean() >= 0.99, agree.mean()
+    both = (stt == 1) & (rs == 1)
+    assert np.percentile(np.abs(nxt[both] - rn[both]).max(axis=1), 99) < 1e-2
+    # the per-point checks are integer logic on the truncated key-point: identical wherever the key-points truncate alike
+    same_px = both & (nxt.astype(np.float64).astype(np.int64) == rn.astype(np.float64).astype(np.int64)).all(axis=1)
+    assert same_px.sum() > 0.8*both.sum()
+    assert np.array_equal(keep[same_px], rk[same_px])
+    assert 0 < keep.sum() < stt.sum()                                # the checks removed something and kept something
+    assert t.last_counts == (int(stt.sum()), int(keep.sum()))
