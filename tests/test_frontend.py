@@ -227,7 +227,7 @@ def test_static_flow_oracle_first_come_per_cell():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("max_features", [400, 3000])
+@pytest.mark.parametrize("max_features", [400, 900, 3000])
 def test_track_static_flow_bit_exact(max_features):
     """ExternalFlowFeatureTracker::trackStatic on the device: accept flags, ages, flows, predicted key-points and the new
     tracklet ids equal the literal loops, with and without the max_features cut."""
@@ -245,7 +245,7 @@ def test_track_static_flow_bit_exact(max_features):
     for k in ("flow", "pred", "det_flow", "det_pred"):
         assert np.array_equal(g[k], o[k]), k                          # doubles formed from the same floats: bit-exact
     assert (g["next_tracklet_id"], g["n_tracked"], g["n_detected"]) == (o["next_tracklet_id"], o["n_tracked"], o["n_detected"])
-    assert g["n_tracked"] > 100 and g["n_detected"] > 100
+    assert g["n_tracked"] > 100 and (g["n_detected"] == 0 if max_features == 400 else g["n_detected"] > 100)   # 767 tracked: the 400 cut admits no detection
 
 
 @pytest.mark.gpu
