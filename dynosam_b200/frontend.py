@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdynofront.so")
 EXPORTS = ["dynofront_create", "dynofront_destroy", "dynofront_last_error", "dynofront_set_frame", "dynofront_track_dynamic",
            "dynofront_sample_candidates", "dynofront_propagate_mask", "dynofront_klt_track", "dynofront_klt_track_fb",
-           "dynofront_klt_last_min_eig", "dynofront_track_static_flow", "dynofront_get_pyramid_level"]
+           "dynofront_klt_last_min_eig", "dynofront_track_static_flow", "dynofront_next_frame", "dynofront_pin_host", "dynofront_unpin_host",
+           "dynofront_get_motion_mask", "dynofront_get_pyramid_level"]
 
 
 class TrackParamsC(C.Structure):
@@ -61,6 +62,10 @@ def load():
         L.dynofront_klt_last_min_eig.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.dynofront_track_static_flow.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                                   C.POINTER(C.c_int64)] + [C.c_void_p]*8 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.dynofront_next_frame.argtypes = [C.c_void_p] + [C.c_void_p]*4
+        L.dynofront_pin_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.dynofront_unpin_host.argtypes = [C.c_void_p, C.c_void_p]
+        L.dynofront_get_motion_mask.argtypes = [C.c_void_p, C.c_void_p]
         L.dynofront_get_pyramid_level.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
@@ -102,6 +107,30 @@ class FeatureTrackerGPU:
         flow = np.ascontiguousarray(flow, dtype=np.float32); motion_mask = np.ascontiguousarray(motion_mask, dtype=np.int32)
         det = None if detection_mask is None else np.ascontiguousarray(detection_mask, dtype=np.uint8)
         self._ck(self.lib.dynofront_set_frame(self.h, _p(flow), _p(motion_mask), _p(det)))
+
+    # ---- streaming mode (resident frames)
+    def pin(self, arr):
+        """register a C-contiguous numpy array as pinned host memory (asynchronous uploads); keep it alive until unpin"""
+        self._ck(self.lib.dynofront_pin_host(self.h, _p(arr), arr.nbytes))
+
+    def unpin(self, arr):
+        self._ck(self.lib.dynofront_unpin_host(self.h, _p(arr)))
+
+    def next_frame(self, gray, flow, motion_mask, detection_mask=None):
+        """arrays must already be C-contiguous uint8 / float32 / int32 (no conversion copies on the streaming path)"""
+        assert gray.dtype == np.uint8 and flow.dtype == np.float32 and motion_mask.dtype == np.int32
+        assert gray.flags.c_contiguous and flow.flags.c_contiguous and motion_mask.flags.c_contiguous
+        self._ck(self.lib.dynofront_next_frame(self.h, _p(gray), _p(flow), _p(motion_mask), _p(detection_mask)))
+
+    def propagate_mask_resident(self, prev_pred_kp, prev_label, prm: TrackParams, min_votes=150):
+        kp = np.ascontiguousarray(prev_pred_kp, dtype=np.float64).reshape(-1, 2); lab = np.ascontiguousarray(prev_label, dtype=np.int32)
+        pc = prm.c()
+        self._ck(self.lib.dynofront_propagate_mask(self.h, kp.shape[0], _p(kp), _p(lab), None, None, C.byref(pc), int(min_votes), None))
+
+    def motion_mask(self):
+        out = np.zeros((self.H, self.W), np.int32)
+        self._ck(self.lib.dynofront_get_motion_mask(self.h, _p(out)))
+        return out
 
     def track_dynamic(self, prev_pred_kp, prev_label, prev_age, prev_tracklet, prm: TrackParams, next_tracklet_id: int, want_masks=True):
         kp = np.ascontiguousarray(prev_pred_kp, dtype=np.float64).reshape(-1, 2); n = kp.shape[0]
@@ -147,7 +176,8 @@ class FeatureTrackerGPU:
                      win=21, max_level=3, max_count=30, eps=0.03, initial=None, min_eig=1e-4, max_fb_distance=0.5):
         """KltFeatureTracker::trackPoints in one call: forward LK, backward LK (21x21, 5 levels, OpenCV default criteria), the
         round-trip test and -- when prev_age is given -- the label / border / age checks.  Returns (next, status, back, keep)."""
-        pg = np.ascontiguousarray(prev_gray, dtype=np.uint8); cg = np.ascontiguousarray(cur_gray, dtype=np.uint8)
+        pg = None if prev_gray is None else np.ascontiguousarray(prev_gray, dtype=np.uint8)     # None, None: the resident frame pair
+        cg = None if cur_gray is None else np.ascontiguousarray(cur_gray, dtype=np.uint8)
         p0 = np.ascontiguousarray(prev_pts, dtype=np.float32).reshape(-1, 2); n = p0.shape[0]
         nxt = np.ascontiguousarray(initial, dtype=np.float32).reshape(-1, 2).copy() if initial is not None else np.zeros((n, 2), np.float32)
         st = np.zeros(n, np.uint8); back = np.zeros((n, 2), np.float32); keep = np.zeros(n, np.uint8); ms = C.c_float()

@@ -21,7 +21,7 @@
 #define FCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -3; } } while (0)
 
 struct dynofront_ctx {
-  int dev = 0, W = 0, H = 0; cudaStream_t s = nullptr; std::string err;
+  int dev = 0, W = 0, H = 0; cudaStream_t s = nullptr; std::string err; bool have_prev = false, have_cur = false, have_pyr = false, have_pyr_cur = false;
   float* flow = nullptr; int32_t* mask = nullptr; uint8_t* det = nullptr; bool has_det = false;
   uint8_t* det_work = nullptr; uint8_t* trk = nullptr; int* trk_idx = nullptr; bool det_work_valid = false;
   // feature scratch (capacity cap)
@@ -549,6 +549,25 @@ int dynofront_set_frame(dynofront_handle h, const float* flow, const int32_t* mo
   FCK(cudaStreamSynchronize(h->s));
   return 0;
 }
+static int build_pyramid(dynofront_ctx* h, int which, const uint8_t* host_img, int max_level, int win, bool with_deriv);
+// Streaming: the frame that was current becomes the previous one WITHOUT moving data (the device buffers swap roles:
+// flow / motion mask for propogateMask, gray pyramid + Scharr derivatives for the KLT), then only the new frame's images
+// cross PCIe (asynchronously when the host buffers are pinned, dynofront_pin_host) and only its pyramid is built.
+int dynofront_next_frame(dynofront_handle h, const uint8_t* gray, const float* flow, const int32_t* motion_mask, const uint8_t* detection_mask) {
+  if (!h || !gray || !flow || !motion_mask) return -1;
+  cudaSetDevice(h->dev);
+  const size_t npx = (size_t)h->W*h->H;
+  std::swap(h->flow, h->pflow); std::swap(h->mask, h->pmask);
+  FCK(cudaMemcpyAsync(h->flow, flow, 2*npx*sizeof(float), cudaMemcpyHostToDevice, h->s));
+  FCK(cudaMemcpyAsync(h->mask, motion_mask, npx*sizeof(int32_t), cudaMemcpyHostToDevice, h->s));
+  if (detection_mask) { FCK(cudaMemcpyAsync(h->det, detection_mask, npx, cudaMemcpyHostToDevice, h->s)); h->has_det = true; } else h->has_det = false;
+  h->det_work_valid = false;
+  h->have_prev = h->have_cur; h->have_cur = true;
+  if (!h->lw.empty()) { std::swap(h->pyr[0], h->pyr[1]); std::swap(h->der, h->der2); }
+  h->have_pyr = h->have_pyr_cur; h->have_pyr_cur = true;
+  if (build_pyramid(h, 1, gray, 5, 21, true)) return -3;       // (levels that are too small for a window are simply never read)
+  return 0;                                                     // no synchronisation: the next call's work is ordered behind on the stream
+}
 static int ensure_features(dynofront_ctx* h, int n) {
   if (n <= h->cap) return 0;
   const int cap = std::max(n, 4096);
@@ -648,27 +667,51 @@ int dynofront_sample_candidates(dynofront_handle h, int32_t nobj, const int32_t*
 
 int dynofront_propagate_mask(dynofront_handle h, int32_t n, const double* kp, const int32_t* lab, const int32_t* prev_mask, const float* prev_flow,
                              const dynofront_track_params* prm, int32_t min_votes, int32_t* current_mask) {
-  if (!h || !prm || n < 0 || !prev_mask || !prev_flow || !current_mask) return -1;
+  if (!h || !prm || n < 0) return -1;
+  const bool resident = !prev_mask && !prev_flow && !current_mask;       // previous / current frame already on the device (dynofront_next_frame)
+  if (!resident && (!prev_mask || !prev_flow || !current_mask)) { h->err = "pass all three images, or none for the resident frames"; return -1; }
+  if (resident && !h->have_prev) { h->err = "no previous frame on the device"; return -2; }
   cudaSetDevice(h->dev);
   if (ensure_features(h, n)) return -3;
   const size_t npx = (size_t)h->W*h->H;
   FCK(cudaMemcpyAsync(h->f_kp, kp, 2*(size_t)n*8, cudaMemcpyHostToDevice, h->s));
   FCK(cudaMemcpyAsync(h->f_lab, lab, (size_t)n*4, cudaMemcpyHostToDevice, h->s));
-  FCK(cudaMemcpyAsync(h->pmask, prev_mask, npx*4, cudaMemcpyHostToDevice, h->s));
-  FCK(cudaMemcpyAsync(h->pflow, prev_flow, 2*npx*4, cudaMemcpyHostToDevice, h->s));
-  FCK(cudaMemcpyAsync(h->cmask, current_mask, npx*4, cudaMemcpyHostToDevice, h->s));
+  const int32_t* pmask = h->pmask; const float* pflow = h->pflow; int32_t* cmask = resident ? h->mask : h->cmask;
+  if (!resident) {
+    FCK(cudaMemcpyAsync(h->pmask, prev_mask, npx*4, cudaMemcpyHostToDevice, h->s));
+    FCK(cudaMemcpyAsync(h->pflow, prev_flow, 2*npx*4, cudaMemcpyHostToDevice, h->s));
+    FCK(cudaMemcpyAsync(h->cmask, current_mask, npx*4, cudaMemcpyHostToDevice, h->s));
+    h->have_prev = false;               // the resident previous frame was overwritten
+  }
   std::vector<int32_t> labels(lab, lab + n);
   std::sort(labels.begin(), labels.end()); labels.erase(std::unique(labels.begin(), labels.end()), labels.end());
   for (int32_t l : labels) {      // objects in ascending label order, sequentially (FeatureTracker.cc:1262)
-    pm_vote_kernel<<<1, 256, 0, h->s>>>(n, h->f_kp, h->f_lab, l, h->cmask, h->W, h->H, min_votes, h->pflag);
-    pm_warp_kernel<<<(unsigned)((npx + 255)/256), 256, 0, h->s>>>(npx, h->W, h->H, h->pmask, h->pflow, l, *prm, h->pflag, h->cmask);
+    pm_vote_kernel<<<1, 256, 0, h->s>>>(n, h->f_kp, h->f_lab, l, cmask, h->W, h->H, min_votes, h->pflag);
+    pm_warp_kernel<<<(unsigned)((npx + 255)/256), 256, 0, h->s>>>(npx, h->W, h->H, pmask, pflow, l, *prm, h->pflag, cmask);
   }
-  FCK(cudaMemcpyAsync(current_mask, h->cmask, npx*4, cudaMemcpyDeviceToHost, h->s));
+  if (!resident) FCK(cudaMemcpyAsync(current_mask, h->cmask, npx*4, cudaMemcpyDeviceToHost, h->s));
   FCK(cudaStreamSynchronize(h->s));
   FCK(cudaGetLastError());
   return 0;
 }
-
+int dynofront_get_motion_mask(dynofront_handle h, int32_t* out) {
+  if (!h || !out) return -1;
+  cudaSetDevice(h->dev);
+  FCK(cudaMemcpyAsync(out, h->mask, (size_t)h->W*h->H*4, cudaMemcpyDeviceToHost, h->s)); FCK(cudaStreamSynchronize(h->s));
+  return 0;
+}
+int dynofront_pin_host(dynofront_handle h, void* ptr, size_t bytes) {
+  if (!h || !ptr) return -1;
+  cudaSetDevice(h->dev);
+  FCK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int dynofront_unpin_host(dynofront_handle h, void* ptr) {
+  if (!h || !ptr) return -1;
+  cudaSetDevice(h->dev);
+  FCK(cudaHostUnregister(ptr));
+  return 0;
+}
 static int klt_scratch(dynofront_ctx* h, int cap) {
   if (falloc(h, &h->k_prev, 2*(size_t)cap) || falloc(h, &h->k_next, 2*(size_t)cap) || falloc(h, &h->k_err, cap) || falloc(h, &h->k_st, cap) ||
       falloc(h, &h->k_back, 2*(size_t)cap) || falloc(h, &h->k_eig, 2*(size_t)cap) || falloc(h, &h->k_st2, cap) || falloc(h, &h->k_keep, cap) ||
@@ -711,6 +754,7 @@ int dynofront_klt_track(dynofront_handle h, const uint8_t* prev_gray, const uint
   FCK(cudaEventRecord(h->e0, h->s));
   if (build_pyramid(h, 0, prev_gray, levels, win, true)) return -3;
   if (build_pyramid(h, 1, cur_gray, levels, win, false)) return -3;
+  h->have_pyr = h->have_pyr_cur = false;      // (the resident pyramids of the streaming mode were overwritten)
   FCK(cudaMemcpyAsync(h->k_prev, prev_pts, 2*(size_t)n*4, cudaMemcpyHostToDevice, h->s));
   FCK(cudaMemcpyAsync(h->k_next, use_initial ? next_pts : prev_pts, 2*(size_t)n*4, cudaMemcpyHostToDevice, h->s));
   KltLevels L; L.nlev = levels + 1;
@@ -735,7 +779,10 @@ int dynofront_klt_track(dynofront_handle h, const uint8_t* prev_gray, const uint
 int dynofront_klt_track_fb(dynofront_handle h, const uint8_t* prev_gray, const uint8_t* cur_gray, int32_t n, const float* prev_pts, float* next_pts,
                            uint8_t* status, float* back_pts, const dynofront_klt_fb_params* P, const int32_t* prev_age, uint8_t* keep,
                            int32_t* n_status, int32_t* n_keep, float* ms_device) {
-  if (!h || !prev_gray || !cur_gray || n < 0 || !prev_pts || !next_pts || !status || !P) return -1;
+  if (!h || n < 0 || !prev_pts || !next_pts || !status || !P) return -1;
+  const bool resident = !prev_gray && !cur_gray;           // both pyramids already on the device (dynofront_next_frame, twice)
+  if (!resident && (!prev_gray || !cur_gray)) { h->err = "pass both images, or none for the resident frames"; return -1; }
+  if (resident && !(h->have_pyr && h->have_pyr_cur)) { h->err = "two frames are needed on the device"; return -2; }
   if (P->win < 3 || P->win > KLT_MAXWIN || P->win_back < 3 || P->win_back > KLT_MAXWIN || P->max_level < 0 || P->max_level_back < 0) { h->err = "win must be in [3,31]"; return -1; }
   if (P->check_static && (!prev_age || !keep)) { h->err = "check_static needs prev_age and keep"; return -1; }
   cudaSetDevice(h->dev);
@@ -744,8 +791,11 @@ int dynofront_klt_track_fb(dynofront_handle h, const uint8_t* prev_gray, const u
   const int lf = nlevels(P->max_level, P->win), lb = nlevels(P->max_level_back, P->win_back), lmax = std::max(lf, lb);
   if (n > h->k_cap) { if (klt_scratch(h, std::max(n, 4096))) return -3; }
   FCK(cudaEventRecord(h->e0, h->s));
-  if (build_pyramid(h, 0, prev_gray, lmax, P->win, true)) return -3;        // both images with derivatives: each is "previous" once
-  if (build_pyramid(h, 1, cur_gray, lmax, P->win, true)) return -3;
+  if (!resident) {
+    if (build_pyramid(h, 0, prev_gray, lmax, P->win, true)) return -3;      // both images with derivatives: each is "previous" once
+    if (build_pyramid(h, 1, cur_gray, lmax, P->win, true)) return -3;
+    h->have_pyr = h->have_pyr_cur = true;
+  }
   FCK(cudaMemcpyAsync(h->k_prev, prev_pts, 2*(size_t)n*4, cudaMemcpyHostToDevice, h->s));
   FCK(cudaMemcpyAsync(h->k_next, P->use_initial_flow ? next_pts : prev_pts, 2*(size_t)n*4, cudaMemcpyHostToDevice, h->s));
   if (P->check_static) FCK(cudaMemcpyAsync(h->k_age, prev_age, (size_t)n*4, cudaMemcpyHostToDevice, h->s));

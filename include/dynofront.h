@@ -37,6 +37,17 @@ const char* dynofront_last_error(dynofront_handle h);
 /* Upload the current frame's dense inputs (any pointer may be NULL to keep the previous upload). */
 int dynofront_set_frame(dynofront_handle h, const float* flow, const int32_t* motion_mask, const uint8_t* detection_mask);
 
+/* Streaming mode: makes the frame that was current the previous one without moving it (device buffers swap roles) and
+ * uploads ONLY the new frame: gray (its pyramid and Scharr derivatives are built at once), flow, motion mask, optional
+ * detection mask.  Returns without synchronising; copies are asynchronous when the host buffers were registered with
+ * dynofront_pin_host (they must then stay untouched until the next dynofront call returns).  After two frames
+ * dynofront_propagate_mask and dynofront_klt_track_fb accept NULL images and work on the resident pair
+ * (reference: the frame loop of FeatureTracker::track, FeatureTracker.cc:73-192, which re-uploads both images per call). */
+int dynofront_next_frame(dynofront_handle h, const uint8_t* gray, const float* flow, const int32_t* motion_mask, const uint8_t* detection_mask);
+int dynofront_pin_host(dynofront_handle h, void* ptr, size_t bytes);     /* cudaHostRegister / Unregister of a caller buffer */
+int dynofront_unpin_host(dynofront_handle h, void* ptr);
+int dynofront_get_motion_mask(dynofront_handle h, int32_t* out);          /* the current frame's motion mask as it is on the device */
+
 /* trackDynamic: n previous dynamic features (predicted key-point at this frame, object label, age, tracklet id),
  * iterated in array order.  Outputs are per input feature (rows of rejected features are zero); new tracklet ids
  * are handed out in iteration order starting at *next_tracklet_id, which is updated.  detection_mask_out /
@@ -54,7 +65,8 @@ int dynofront_track_dynamic(dynofront_handle h, int32_t n, const double* prev_pr
 int dynofront_sample_candidates(dynofront_handle h, int32_t n_objects, const int32_t* objects, const dynofront_track_params* prm,
                                 int32_t* counts, int32_t* offsets, int32_t* zero_flow, int32_t* indices, int64_t capacity);
 
-/* propogateMask: previous-frame features (predicted key-point, label), previous mask / flow, current mask (in/out). */
+/* propogateMask: previous-frame features (predicted key-point, label), previous mask / flow, current mask (in/out).
+ * All three images NULL: streaming mode, the resident previous frame votes into the resident current motion mask in place. */
 int dynofront_propagate_mask(dynofront_handle h, int32_t n, const double* prev_pred_kp, const int32_t* prev_label,
                              const int32_t* prev_mask, const float* prev_flow, const dynofront_track_params* prm,
                              int32_t min_votes, int32_t* current_mask);
@@ -71,6 +83,7 @@ int dynofront_klt_track(dynofront_handle h, const uint8_t* prev_gray, const uint
  * arithmetic) and, with check_static, the per-point checks that follow the (host-side, out of scope) RANSAC:
  * background label at the truncated key-point of the motion mask given to dynofront_set_frame, inside the image and the
  * shrunken image, age + 1 <= max_feature_track_age.  Nothing returns to the host between the stages.
+ * prev_gray == cur_gray == NULL: streaming mode, the two resident pyramids are used (nothing is uploaded or rebuilt).
  * status[n] = forward-backward result, keep[n] = status && checks (may be NULL without check_static),
  * back_pts[n][2] (may be NULL) = where the backward pass landed. */
 typedef struct {

@@ -278,3 +278,40 @@ def test_klt_forward_backward_on_device(initial):
     assert np.array_equal(keep[same_px], rk[same_px])
     assert 0 < keep.sum() < stt.sum()                                # the checks removed something and kept something
     assert t.last_counts == (int(stt.sum()), int(keep.sum()))
+
+
+@pytest.mark.gpu
+def test_streaming_mode_equals_call_by_call():
+    """dynofront_next_frame keeps the previous frame on the device (buffers swap roles, only the new frame is uploaded):
+    mask propagation, dynamic tracking and the forward-backward KLT on the resident pair give exactly what the
+    call-by-call entry points give on re-uploaded images, over several consecutive frames."""
+    from dynosam_b200.frontend import FeatureTrackerGPU, TrackParams
+    rng = np.random.default_rng(3)
+    stream = SyntheticStream(n_objects=6, seed=5)
+    frames = [stream.frame(k) for k in range(4)]
+    frames = [(np.ascontiguousarray(g, np.uint8), np.ascontiguousarray(m, np.int32), np.ascontiguousarray(f, np.float32)) for g, m, f in frames]
+    prm = TrackParams()
+    pts = np.stack([rng.uniform(25, W - 25, 300), rng.uniform(25, H - 25, 300)], 1).astype(np.float32)
+    age = rng.integers(0, 30, 300).astype(np.int32)
+    a = FeatureTrackerGPU(W, H); b = FeatureTrackerGPU(W, H)
+    for arr in frames[1]:
+        a.pin(arr)                                            # pinned and pageable host buffers both work
+    a.next_frame(frames[0][0], frames[0][2], frames[0][1])
+    for k in range(1, 4):
+        g0, m0, f0 = frames[k-1]; g1, m1, f1 = frames[k]
+        kp, lab = _features_from_mask(rng, m0, f0, per_object=120)
+        fage = rng.integers(0, 22, len(lab)).astype(np.int32); tid = np.arange(len(lab), dtype=np.int64)
+        a.next_frame(g1, f1, m1)
+        a.propagate_mask_resident(kp, lab, prm, min_votes=20)
+        ra = a.track_dynamic(kp, lab, fage, tid, prm, 9000)
+        ka = a.klt_track_fb(None, None, pts, prm, age, 25)
+        cur = b.propagate_mask(kp, lab, m0, f0, m1, prm, min_votes=20)
+        b.set_frame(f1, cur, None)
+        rb = b.track_dynamic(kp, lab, fage, tid, prm, 9000)
+        kb = b.klt_track_fb(g0, g1, pts, prm, age, 25)
+        assert np.array_equal(a.motion_mask(), cur), k
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y), k
+        for x, y in zip(ka, kb):
+            assert np.array_equal(x, y), k
+    a.unpin(frames[1][0]); a.unpin(frames[1][1]); a.unpin(frames[1][2])
