@@ -34,7 +34,9 @@ class SyntheticStream:
         W_, H_ = self.W, self.H
         off = self.cam_v*k
         i0 = int(np.floor(off)); f = off - i0
-        gray = (1 - f)*self.bg[:, i0:i0 + W_] + f*self.bg[:, i0 + 1:i0 + 1 + W_]
+        wb = self.bg.shape[1]                               # the background strip wraps around: streams of any length
+        c0 = (i0 + np.arange(W_)) % wb; c1 = (i0 + 1 + np.arange(W_)) % wb
+        gray = (1 - f)*self.bg[:, c0] + f*self.bg[:, c1]
         mask = np.zeros((H_, W_), np.int32)
         flow = np.zeros((H_, W_, 2), np.float32); flow[..., 0] = -self.cam_v; flow[..., 1] = 1e-3   # no exact zeros in the background
         for o in self.obj:
