@@ -41,7 +41,7 @@ def make_inputs(n_frames, seed=42):
             sel = rng.choice(len(ys), size=min(PER_OBJECT, len(ys)), replace=False)
             kps.append(np.stack([xs[sel] + 0.5 + f0[ys[sel], xs[sel], 0], ys[sel] + 0.5 + f0[ys[sel], xs[sel], 1]], 1))
             labs.append(np.full(len(sel), lab, np.int32))
-        kp = np.concatenate(kps); lab = np.concatenate(labs)
+        kp = np.concatenate(kps) if kps else np.zeros((0, 2)); lab = np.concatenate(labs) if labs else np.zeros(0, np.int32)
         ok = (kp[:, 0] > 1) & (kp[:, 0] < W - 1) & (kp[:, 1] > 1) & (kp[:, 1] < H - 1)
         feats.append((kp[ok], lab[ok], rng.integers(0, 21, ok.sum()).astype(np.int32), np.arange(ok.sum(), dtype=np.int64)))
     return frames, static_pts, feats

@@ -41,6 +41,7 @@ class SyntheticStream:
         flow = np.zeros((H_, W_, 2), np.float32); flow[..., 0] = -self.cam_v; flow[..., 1] = 1e-3   # no exact zeros in the background
         for o in self.obj:
             x = o["x"] + o["vx"]*k; y = o["y"] + o["vy"]*k
+            x = (x + o["w"]) % (W_ + o["w"]) - o["w"]; y = (y + o["h"]) % (H_ + o["h"]) - o["h"]   # objects re-enter on the other side
             xi, yi = int(round(x)), int(round(y))
             x0, y0 = max(xi, 0), max(yi, 0); x1, y1 = min(xi + o["w"], W_), min(yi + o["h"], H_)
             if x1 <= x0 or y1 <= y0:
