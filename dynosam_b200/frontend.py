@@ -148,7 +148,7 @@ class FeatureTrackerGPU:
     def sample_candidates(self, objects, prm: TrackParams, capacity=None):
         objs = np.ascontiguousarray(objects, dtype=np.int32); n = objs.shape[0]
         cap = int(capacity if capacity is not None else self.W*self.H)
-        counts = np.zeros(n, np.int32); offs = np.zeros(n, np.int32); zero = np.zeros(n, np.int32); idx = np.zeros(cap, np.int32)
+        counts = np.zeros(n, np.int32); offs = np.zeros(n, np.int32); zero = np.zeros(n, np.int32); idx = np.empty(cap, np.int32)
         pc = prm.c()
         self._ck(self.lib.dynofront_sample_candidates(self.h, n, _p(objs), C.byref(pc), _p(counts), _p(offs), _p(zero), _p(idx), cap))
         return {int(o): idx[offs[i]:offs[i] + counts[i]].copy() for i, o in enumerate(objs)}, {int(o): int(zero[i]) for i, o in enumerate(objs)}
