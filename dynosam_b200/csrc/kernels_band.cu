@@ -1235,10 +1235,10 @@ int band_plan_layout(BandPlan& P, int n, int bw, int ncell_request, int rank, in
   if (ncell_request > 0) C = std::min(ncell_request, cmax);
   else if (ncell_request < 0) C = 0;
   else {
-    // default: one cell per GPU.  On one GPU the two-chain scheme (one cell, no spike) is the fastest: a second cell halves
-    // the chain but its two spiked chains cost 4x the flops per column, which the worker warps of one GPU do not absorb
-    // (measured on C5: 73 ms per solve with one cell, 86-100 ms with two)
-    C = world > 1 ? std::min(world, cmax) : 1;
+    // default: one cell per GPU.  On one GPU a second cell pays for long systems when its two spiked chains (4x the flops
+    // per column) are kept SHORT: the plain end chains then set the time, the worker warps absorb the spike work behind
+    // them (C5: 73.4 ms per solve with one cell, 66.8 with two cells and end chains 4.5x as long; equal lengths: 86)
+    C = world > 1 ? std::min(world, cmax) : (NT >= 4096 && cmax >= 2 ? 2 : 1);
     if (NT < std::max(8, 4*WB + 4)) C = 0;
     C = std::min(C, cmax);
   }
@@ -1249,7 +1249,7 @@ int band_plan_layout(BandPlan& P, int n, int bw, int ncell_request, int rank, in
     P.chains.push_back(p);
   } else {
     const long long free_tiles = (long long)NT - (long long)(2*C - 1)*WB;
-    const double outer_weight = P.outer_weight > 0 ? P.outer_weight : ((C >= 2 && world == 1) ? 1.6 : 1.0);
+    const double outer_weight = P.outer_weight > 0 ? P.outer_weight : ((C >= 2 && world == 1) ? 4.5 : 1.0);
     std::vector<double> wgt(2*C, 1.0); wgt[0] = wgt[2*C - 1] = outer_weight;
     double wsum = 0; for (double x : wgt) wsum += x;
     std::vector<int> len(2*C);

@@ -123,7 +123,7 @@ int dynoba_set_reduce(dynoba_handle h, dynoba_reduce_fn fn, void* ctx);
  * ordering of LevenbergMarquardtParams (RegularBackendModule.cc:405-419 leaves it at COLAMD). */
 int dynoba_set_partition(dynoba_handle h, int ncells);
 /* Performance parameters of the reduced solve (results do not depend on them): "outer_weight" = relative length of the
- * two end chains, which carry no spike (default 1.6 on one GPU, 1 otherwise); "band_ctas_per_chain" = worker CTAs that
+ * two end chains, which carry no spike (default 4.5 on one GPU, 1 otherwise); "band_ctas_per_chain" = worker CTAs that
  * serve the band tiles of one chain (the others stream the spike updates; process-wide). */
 int dynoba_set_tuning(dynoba_handle h, const char* name, double value);
 /* Builds the device layout (sorting, CSR, band structure) and uploads.  Called implicitly by the
