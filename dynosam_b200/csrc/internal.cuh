@@ -96,22 +96,71 @@ __host__ __device__ __forceinline__ int band_cell(const DevBand& B, int p) {    
   while (c + 1 < B.ncell && p >= dld(B.cells[c + 1].q0)) c++;
   return c;
 }
+// Geometry and storage of one cell, loaded once (a handful of descriptor reads) and then used for many entries: the
+// kernels that scatter 6x6 blocks resolve the cell of the block's first column and address the 36 entries with integer
+// arithmetic only.
+struct BandCellRef {
+  int q0, a0, m0, b1;          // j in [q0, b1) belongs to this cell
+  double *ta, *tb, *ffa;       // tiles of chain A / B, Q x Q block of chain A
+  int tpca, tpcb;
+};
+__host__ __device__ __forceinline__ BandCellRef band_cell_ref(const DevBand& B, int j) {
+  BandCellRef R;
+  if (B.ncell == 0) { R.q0 = 0; R.a0 = 0; R.m0 = B.n_pad; R.b1 = B.n_pad; R.ta = dld(B.chains[0].tiles); R.tb = nullptr; R.ffa = nullptr; R.tpca = B.WB + 1; R.tpcb = 0; return R; }
+  const int c = band_cell(B, j);
+  R.q0 = dld(B.cells[c].q0); R.a0 = dld(B.cells[c].a0); R.m0 = dld(B.cells[c].m0); R.b1 = dld(B.cells[c].b1);
+  R.ta = dld(B.chains[2*c].tiles); R.tb = dld(B.chains[2*c + 1].tiles); R.ffa = dld(B.chains[2*c].ff);
+  R.tpca = dld(B.chains[2*c].TPC); R.tpcb = dld(B.chains[2*c + 1].TPC);
+  return R;
+}
+// address of entry (i >= j) whose column j lies in the cell of R
+__host__ __device__ __forceinline__ double* band_at_in(const DevBand& B, const BandCellRef& R, int i, int j) {
+  const int w = B.WB*TILE;
+  if (B.ncell == 0 || (j >= R.a0 && i < R.m0 + w)) { const int li = i - R.a0, lj = j - R.a0; return R.ta + tile_elem(R.tpca, lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31); }
+  if (j < R.a0) {
+    const int sj = j - R.q0;
+    if (i < R.a0) { const int si = i - R.q0; return R.ffa + ((size_t)(si >> 5)*B.WB + (sj >> 5))*TILE2 + (size_t)(sj & 31)*TILE + (si & 31); }
+    const int li = i - R.a0;
+    return R.ta + tile_elem(R.tpca, li >> 5, B.WB + 1 + (sj >> 5), sj & 31, li & 31);
+  }
+  if (i < R.b1) { const int li = R.b1 - 1 - j, lj = R.b1 - 1 - i; return R.tb + tile_elem(R.tpcb, lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31); }
+  const int s = R.b1 + w - 1 - i, lc = R.b1 - 1 - j;
+  return R.tb + tile_elem(R.tpcb, lc >> 5, B.WB + 1 + (s >> 5), s & 31, lc & 31);
+}
 // address of entry (i >= j) / of rhs element p of the reduced system
 __host__ __device__ __forceinline__ double* band_at(const DevBand& B, int i, int j) {
-  if (B.ncell == 0) { const int I = i >> 5, J = j >> 5; return dld(B.chains[0].tiles) + tile_elem(B.WB + 1, J, I - J, i & 31, j & 31); }
-  const int c = band_cell(B, j), w = B.WB*TILE;
-  const int q0 = dld(B.cells[c].q0), a0 = dld(B.cells[c].a0), m0 = dld(B.cells[c].m0), b1 = dld(B.cells[c].b1);
-  if (j < a0) {
-    const int sj = j - q0;
-    if (i < a0) { const int si = i - q0; return dld(B.chains[2*c].ff) + ((size_t)(si >> 5)*B.WB + (sj >> 5))*TILE2 + (size_t)(sj & 31)*TILE + (si & 31); }
-    const int li = i - a0;
-    return dld(B.chains[2*c].tiles) + tile_elem(dld(B.chains[2*c].TPC), li >> 5, B.WB + 1 + (sj >> 5), sj & 31, li & 31);
-  }
-  if (i < m0 + w) { const int li = i - a0, lj = j - a0; return dld(B.chains[2*c].tiles) + tile_elem(dld(B.chains[2*c].TPC), lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31); }
-  if (i < b1) { const int li = b1 - 1 - j, lj = b1 - 1 - i; return dld(B.chains[2*c + 1].tiles) + tile_elem(dld(B.chains[2*c + 1].TPC), lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31); }
-  const int s = b1 + w - 1 - i, lc = b1 - 1 - j;
-  return dld(B.chains[2*c + 1].tiles) + tile_elem(dld(B.chains[2*c + 1].TPC), lc >> 5, B.WB + 1 + (s >> 5), s & 31, lc & 31);
+  const BandCellRef R = band_cell_ref(B, j);
+  return band_at_in(B, R, i, j);
 }
+// same, reusing R when column j still lies in its cell (the common case for the entries of one 6x6 block)
+__host__ __device__ __forceinline__ double* band_at_cached(const DevBand& B, BandCellRef& R, int i, int j) {
+  if (B.ncell != 0 && (j < R.q0 || j >= R.b1)) R = band_cell_ref(B, j);
+  return band_at_in(B, R, i, j);
+}
+// 6x6 block scatter: rows i0..i0+5, columns j0..j0+5 (i0 >= j0).  Almost every block lies inside ONE band chain (A or B
+// of one cell): its entries are then addressed from a per-block base with a few integer operations each.  Blocks that
+// touch a separator or straddle a zone boundary take the general, out-of-line path per entry (keeps the unrolled
+// 36-entry flush loops of the callers small).
+struct BandBlockRef { double* base; int tpc, oi, oj, rev, fast; };
+#if defined(__CUDACC__)
+static __device__ __noinline__ double* band_at_slow(DevBand B, int i, int j) { return band_at(B, i, j); }   // (by value: a reference would
+                                                                 // force the caller's kernel parameter into local memory)
+__device__ __forceinline__ BandBlockRef band_block_ref(const DevBand& B, int i0, int j0) {
+  BandBlockRef K; K.fast = 1; K.rev = 0;
+  if (B.ncell == 0) { K.base = dld(B.chains[0].tiles); K.tpc = B.WB + 1; K.oi = 0; K.oj = 0; return K; }
+  const BandCellRef R = band_cell_ref(B, j0);
+  const int w = B.WB*TILE;
+  if (j0 >= R.a0 && i0 + 5 < R.m0 + w) { K.base = R.ta; K.tpc = R.tpca; K.oi = R.a0; K.oj = R.a0; return K; }                  // chain A
+  if (j0 >= R.m0 && j0 + 5 < R.b1 && i0 >= R.m0 + w && i0 + 5 < R.b1) { K.base = R.tb; K.tpc = R.tpcb; K.oi = R.b1 - 1; K.rev = 1; return K; }   // chain B
+  K.fast = 0; K.base = nullptr; K.tpc = 0; K.oi = K.oj = 0;
+  return K;
+}
+__device__ __forceinline__ double* band_block_at(const DevBand& B, const BandBlockRef& K, int i, int j) {
+  if (!K.fast) return band_at_slow(B, i, j);
+  const int li = K.rev ? K.oi - j : i - K.oi, lj = K.rev ? K.oi - i : j - K.oj;
+  return K.base + tile_elem(K.tpc, lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31);
+}
+#endif
 __host__ __device__ __forceinline__ double* rhs_at(const DevBand& B, int p) {
   if (B.ncell == 0) return dld(B.chains[0].rhs) + p;
   const int c = band_cell(B, p), w = B.WB*TILE;

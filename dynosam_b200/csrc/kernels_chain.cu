@@ -170,16 +170,17 @@ schur_general_kernel(const DevBlock* __restrict__ blocks, const int* __restrict_
           double s = 0; for (int q = 0; q < 3; q++) s += P[3*r + q]*vj.J(q, vj.pcol[s2] + c);
           PA[6*r + c] = s;
         }
+        const BandBlockRef cref = band_block_ref(B, (a > b ? a : b)*6, (a < b ? a : b)*6);   // the block's storage, resolved once
         for (int c = 0; c < 6; c++) {
           double ai[3]; for (int r = 0; r < 3; r++) ai[r] = vi.J(r, vi.pcol[s1] + c);
           for (int c2 = 0; c2 < 6; c2++) {
             if (same && c2 > c) continue;
             const double m = ai[0]*PA[c2] + ai[1]*PA[6 + c2] + ai[2]*PA[12 + c2];
             const int row = a*6 + c, col = b*6 + c2;
-            if (a > b || same) atomicAdd(band_at(B, row, col), m);
-            else if (a < b) atomicAdd(band_at(B, col, row), m);
+            if (a > b || same) atomicAdd(band_block_at(B, cref, row, col), m);
+            else if (a < b) atomicAdd(band_block_at(B, cref, col, row), m);
             else { const int hi = row > col ? row : col, lo = row > col ? col : row;
-                   atomicAdd(band_at(B, hi, lo), c == c2 ? 2.0*m : m); }
+                   atomicAdd(band_block_at(B, cref, hi, lo), c == c2 ? 2.0*m : m); }
           }
         }
       }

@@ -223,6 +223,7 @@ schur_simple_kernel(DevBlock blk, const unsigned char* __restrict__ grp_win, Dev
             PA[r*6 + c] = s;
           }
         const bool same = (i == j && s1 == s2);
+        const BandBlockRef cref = band_block_ref(B, (a > b ? a : b)*6, (a < b ? a : b)*6);   // the block's storage, resolved once
 #pragma unroll
         for (int c = 0; c < 6; c++) {
 #pragma unroll
@@ -232,11 +233,11 @@ schur_simple_kernel(DevBlock blk, const unsigned char* __restrict__ grp_win, Dev
 #pragma unroll
             for (int r = 0; r < D; r++) m += Ai[r*6 + c]*PA[r*6 + c2];
             const int row = a*6 + c, col = b*6 + c2;
-            if (a > b || same) atomicAdd(band_at(B, row, col), m);
-            else if (a < b) atomicAdd(band_at(B, col, row), m);
+            if (a > b || same) atomicAdd(band_block_at(B, cref, row, col), m);
+            else if (a < b) atomicAdd(band_block_at(B, cref, col, row), m);
             else {  // two different factor slots on the same variable: contributes M + M^T
               const int hi = row > col ? row : col, lo = row > col ? col : row;
-              atomicAdd(band_at(B, hi, lo), c == c2 ? 2.0*m : m);
+              atomicAdd(band_block_at(B, cref, hi, lo), c == c2 ? 2.0*m : m);
             }
           }
         }
@@ -285,6 +286,7 @@ __global__ void pose_factors_kernel(DevBlock blk, DevBand B, int arity) {
     }
     for (int k2 = 0; k2 <= k1; k2++) {
       const int b = blk.idx[(size_t)k2*blk.stride + f];
+        const BandBlockRef cref = band_block_ref(B, (a > b ? a : b)*6, (a < b ? a : b)*6);   // the block's storage, resolved once
       for (int c = 0; c < 6; c++)
         for (int c2 = 0; c2 < 6; c2++) {
           if (k1 == k2 && c2 > c) continue;
@@ -293,10 +295,10 @@ __global__ void pose_factors_kernel(DevBlock blk, DevBand B, int arity) {
           for (int r = 0; r < 6; r++)
             m += blk.J[(size_t)(r*JC + 6*k1 + c)*blk.stride + f]*blk.J[(size_t)(r*JC + 6*k2 + c2)*blk.stride + f];
           const int row = a*6 + c, col = b*6 + c2;
-          if (a > b || k1 == k2) atomicAdd(band_at(B, row, col), m);
-          else if (a < b) atomicAdd(band_at(B, col, row), m);
+          if (a > b || k1 == k2) atomicAdd(band_block_at(B, cref, row, col), m);
+          else if (a < b) atomicAdd(band_block_at(B, cref, col, row), m);
           else { const int hi = row > col ? row : col, lo = row > col ? col : row;
-                 atomicAdd(band_at(B, hi, lo), c == c2 ? 2.0*m : m); }
+                 atomicAdd(band_block_at(B, cref, hi, lo), c == c2 ? 2.0*m : m); }
         }
     }
   }

@@ -19,6 +19,14 @@
 
 namespace dynoba {
 
+// acc[e] with a run-time index (rare slow path of the flush): a select chain keeps the accumulators in registers
+__device__ __forceinline__ double acc_at(const double (&acc)[36], int e) {
+  double v = 0.0;
+#pragma unroll
+  for (int k = 0; k < 36; k++) if (k == e) v = acc[k];
+  return v;
+}
+
 constexpr int STG_WARPS = 4;          // K4a: landmarks per CTA
 constexpr int ACC_THREADS = WIN_ACC_WARPS*32;
 constexpr int WSLOT = WIN_SLOT_DOUBLES;   // 42 doubles = 21 x 16 B: odd stride => conflict-free LDS.128 across slots
@@ -283,13 +291,28 @@ schur_accum_kernel(DevWindows Wn, DevBand B) {
   }
   if (active && touched) {
     const int pa = cvars[a], pb = cvars[b];   // cvars ascending => pa >= pb
+    const BandBlockRef cref = band_block_ref(B, pa*6, pb*6);   // the block's storage, resolved once for its 36 entries
+    if (cref.fast) {
+      // inside one band chain: tile coordinates of the block's corner, then 36 additions with compile-time offsets (a block
+      // spans at most two tile rows and two tile columns)
+      const int li0 = cref.rev ? cref.oi - (pb*6 + 5) : pa*6 - cref.oi, lj0 = cref.rev ? cref.oi - (pa*6 + 5) : pb*6 - cref.oj;
 #pragma unroll
-    for (int r = 0; r < 6; r++)
+      for (int r = 0; r < 6; r++)
 #pragma unroll
-      for (int c = 0; c < 6; c++) {
+        for (int c = 0; c < 6; c++) {
+          if (a == b && c > r) continue;
+          // natural: (li, lj) = (li0 + r, lj0 + c); reversed chain: row and column swap and run backwards
+          const int li = cref.rev ? li0 + (5 - c) : li0 + r, lj = cref.rev ? lj0 + (5 - r) : lj0 + c;
+          atomicAdd(cref.base + tile_elem(cref.tpc, lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31), acc[r*6 + c]);
+        }
+    } else {
+#pragma unroll 1
+      for (int e = 0; e < 36; e++) {
+        const int r = e/6, c = e - 6*r;
         if (a == b && c > r) continue;
-        atomicAdd(band_at(B, pa*6 + r, pb*6 + c), acc[r*6 + c]);
+        atomicAdd(band_at_slow(B, pa*6 + r, pb*6 + c), acc_at(acc, e));
       }
+    }
     if (a == b) {
 #pragma unroll
       for (int c = 0; c < 6; c++) atomicAdd(rhs_at(B, pa*6 + c), gs[a*6 + c]);
