@@ -143,6 +143,12 @@ __host__ __device__ __forceinline__ double* band_at_cached(const DevBand& B, Ban
 // 36-entry flush loops of the callers small).
 struct BandBlockRef { double* base; int tpc, oi, oj, rev, fast; };
 #if defined(__CUDACC__)
+// fire-and-forget fp64 addition into the reduced system: RED on the GLOBAL window.  A plain atomicAdd through a pointer the
+// compiler cannot prove global (loaded from a descriptor) becomes a generic, value-returning ATOM with an address-space
+// query per call -- measured +6 ms per damped solve on C5
+__device__ __forceinline__ void red_add(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
 static __device__ __noinline__ double* band_at_slow(DevBand B, int i, int j) { return band_at(B, i, j); }   // (by value: a reference would
                                                                  // force the caller's kernel parameter into local memory)
 __device__ __forceinline__ BandBlockRef band_block_ref(const DevBand& B, int i0, int j0) {

@@ -146,7 +146,7 @@ schur_general_kernel(const DevBlock* __restrict__ blocks, const int* __restrict_
     }
     for (int s = 0; s < v.np; s++) {
       const int pos = v.pose(s);
-      for (int c = 0; c < 6; c++) { double a = 0; for (int r = 0; r < 3; r++) a += v.J(r, v.pcol[s] + c)*rb[r]; atomicAdd(rhs_at(B, pos*6 + c), a); }
+      for (int c = 0; c < 6; c++) { double a = 0; for (int r = 0; r < 3; r++) a += v.J(r, v.pcol[s] + c)*rb[r]; red_add(rhs_at(B, pos*6 + c), a); }
     }
   }
   // factor pairs
@@ -177,10 +177,10 @@ schur_general_kernel(const DevBlock* __restrict__ blocks, const int* __restrict_
             if (same && c2 > c) continue;
             const double m = ai[0]*PA[c2] + ai[1]*PA[6 + c2] + ai[2]*PA[12 + c2];
             const int row = a*6 + c, col = b*6 + c2;
-            if (a > b || same) atomicAdd(band_block_at(B, cref, row, col), m);
-            else if (a < b) atomicAdd(band_block_at(B, cref, col, row), m);
+            if (a > b || same) red_add(band_block_at(B, cref, row, col), m);
+            else if (a < b) red_add(band_block_at(B, cref, col, row), m);
             else { const int hi = row > col ? row : col, lo = row > col ? col : row;
-                   atomicAdd(band_block_at(B, cref, hi, lo), c == c2 ? 2.0*m : m); }
+                   red_add(band_block_at(B, cref, hi, lo), c == c2 ? 2.0*m : m); }
           }
         }
       }

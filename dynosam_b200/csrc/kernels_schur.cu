@@ -166,7 +166,7 @@ schur_simple_kernel(DevBlock blk, const unsigned char* __restrict__ grp_win, Dev
         double a = 0;
 #pragma unroll
         for (int r = 0; r < D; r++) a += el(r*JC + PCOL0 + 6*sl + c, i)*rb[r];
-        atomicAdd(rhs_at(B, pos*6 + c), a);
+        red_add(rhs_at(B, pos*6 + c), a);
       }
     }
   }
@@ -233,11 +233,11 @@ schur_simple_kernel(DevBlock blk, const unsigned char* __restrict__ grp_win, Dev
 #pragma unroll
             for (int r = 0; r < D; r++) m += Ai[r*6 + c]*PA[r*6 + c2];
             const int row = a*6 + c, col = b*6 + c2;
-            if (a > b || same) atomicAdd(band_block_at(B, cref, row, col), m);
-            else if (a < b) atomicAdd(band_block_at(B, cref, col, row), m);
+            if (a > b || same) red_add(band_block_at(B, cref, row, col), m);
+            else if (a < b) red_add(band_block_at(B, cref, col, row), m);
             else {  // two different factor slots on the same variable: contributes M + M^T
               const int hi = row > col ? row : col, lo = row > col ? col : row;
-              atomicAdd(band_block_at(B, cref, hi, lo), c == c2 ? 2.0*m : m);
+              red_add(band_block_at(B, cref, hi, lo), c == c2 ? 2.0*m : m);
             }
           }
         }
@@ -282,7 +282,7 @@ __global__ void pose_factors_kernel(DevBlock blk, DevBand B, int arity) {
       double g = 0;
 #pragma unroll
       for (int r = 0; r < 6; r++) g += blk.J[(size_t)(r*JC + 6*k1 + c)*blk.stride + f]*bb[r];
-      atomicAdd(rhs_at(B, a*6 + c), g);
+      red_add(rhs_at(B, a*6 + c), g);
     }
     for (int k2 = 0; k2 <= k1; k2++) {
       const int b = blk.idx[(size_t)k2*blk.stride + f];
@@ -295,10 +295,10 @@ __global__ void pose_factors_kernel(DevBlock blk, DevBand B, int arity) {
           for (int r = 0; r < 6; r++)
             m += blk.J[(size_t)(r*JC + 6*k1 + c)*blk.stride + f]*blk.J[(size_t)(r*JC + 6*k2 + c2)*blk.stride + f];
           const int row = a*6 + c, col = b*6 + c2;
-          if (a > b || k1 == k2) atomicAdd(band_block_at(B, cref, row, col), m);
-          else if (a < b) atomicAdd(band_block_at(B, cref, col, row), m);
+          if (a > b || k1 == k2) red_add(band_block_at(B, cref, row, col), m);
+          else if (a < b) red_add(band_block_at(B, cref, col, row), m);
           else { const int hi = row > col ? row : col, lo = row > col ? col : row;
-                 atomicAdd(band_block_at(B, cref, hi, lo), c == c2 ? 2.0*m : m); }
+                 red_add(band_block_at(B, cref, hi, lo), c == c2 ? 2.0*m : m); }
         }
     }
   }

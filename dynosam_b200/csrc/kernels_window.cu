@@ -303,19 +303,19 @@ schur_accum_kernel(DevWindows Wn, DevBand B) {
           if (a == b && c > r) continue;
           // natural: (li, lj) = (li0 + r, lj0 + c); reversed chain: row and column swap and run backwards
           const int li = cref.rev ? li0 + (5 - c) : li0 + r, lj = cref.rev ? lj0 + (5 - r) : lj0 + c;
-          atomicAdd(cref.base + tile_elem(cref.tpc, lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31), acc[r*6 + c]);
+          red_add(cref.base + tile_elem(cref.tpc, lj >> 5, (li >> 5) - (lj >> 5), li & 31, lj & 31), acc[r*6 + c]);
         }
     } else {
 #pragma unroll 1
       for (int e = 0; e < 36; e++) {
         const int r = e/6, c = e - 6*r;
         if (a == b && c > r) continue;
-        atomicAdd(band_at_slow(B, pa*6 + r, pb*6 + c), acc_at(acc, e));
+        red_add(band_at_slow(B, pa*6 + r, pb*6 + c), acc_at(acc, e));
       }
     }
     if (a == b) {
 #pragma unroll
-      for (int c = 0; c < 6; c++) atomicAdd(rhs_at(B, pa*6 + c), gs[a*6 + c]);
+      for (int c = 0; c < 6; c++) red_add(rhs_at(B, pa*6 + c), gs[a*6 + c]);
     }
   }
 }
