@@ -254,3 +254,56 @@ def test_plain_c_program_links_the_abi(tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
     else:
         assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)
+
+
+_GLOO_CELL_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tools"))
+import numpy as np, torch, torch.distributed as dist
+from dynosam_b200 import synth
+import bench, cell_proto
+from oracle import oracle as O
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+# a trajectory long enough for two cells: static + one object, short tracks -> narrow band
+p = synth.make_problem(n_frames=90, n_objects=1, n_static=500, n_dynamic=80, seed=4, max_static_age=3, max_dynamic_age=3, object_span=(30, 40))
+lam = 1e-3
+full = O.OracleProblem(p)
+S_full, g_full, pos = full.reduced_dense(lam)
+shard = bench.shard_problem(p, rank, world)               # time shard: this rank's landmarks and pose-only factors
+S, g, pos_r = O.OracleProblem(shard).reduced_dense(lam)
+assert np.array_equal(pos, pos_r)
+if rank != 0:
+    S -= lam*np.eye(S.shape[0])                           # damping is added once
+# (reduced_dense returns the system in SOLVER order -- the band); padding to whole model tiles
+T = cell_proto.T
+n = S.shape[0]; npad = (n + T - 1)//T*T
+def ordered(M, v):
+    Mo = np.eye(npad); Mo[:n, :n] = M
+    vo = np.zeros(npad); vo[:n] = v
+    if rank != 0: Mo[n:, n:] = 0.0                        # padding diagonal also only once
+    return Mo, vo
+So, go = ordered(S, g)
+bw = bench.problem_bandwidth(p); WB = (bw + T - 1)//T
+x = cell_proto.cell_solve(So, go, WB, 2, rank, world, dist)
+ref = np.linalg.solve(S_full, g_full)
+err = np.abs(x[:n] - ref).max()/np.abs(ref).max()
+assert err < 1e-8, err
+dist.destroy_process_group()
+print("rank", rank, "cells ok", err)
+'''
+
+
+def test_distributed_cell_solve_gloo(tmp_path):
+    """world_size-2 gloo run of the DISTRIBUTED reduced solve's exchange pattern on the executable specification
+    (tools/cell_proto.py): per-rank partial reduced systems of the time-sharded graph (oracle arithmetic), a reduce per cell
+    to its owner, all-reduce of the boundary-separator system and of the solution; the result equals the dense solve of
+    the unsharded system."""
+    script = tmp_path / "worker_cells.py"
+    script.write_text(_GLOO_CELL_WORKER.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29573", str(script)],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("cells ok") == 2

@@ -100,8 +100,15 @@ class Chain:
         return x[:Kend]
 
 
-def cell_solve(S, g, WB, C):
+def cell_solve(S, g, WB, C, rank=0, world=1, comm=None):
+    """Solve S x = g by the cell scheme.  With world > 1 (comm = a torch.distributed-like object with reduce(tensor, dst)
+    and all_reduce(tensor) on float64 tensors), S and g are THIS RANK'S PARTIAL sums of the reduced system: every rank
+    places its contribution into the full layout, the buffers of cell c are summed at its owner c*world//C (a reduce per
+    cell), owners factor their cells, the boundary system and the solution are all-reduced -- the exchange pattern of
+    libdynoba's distributed reduced solve (api.cu: build_reduced / solve_step)."""
     n = S.shape[0]; NT = n//T; L = Layout(NT, WB, C); w = WB*T
+    owner = lambda c: c*world//C
+    mine = [c for c in range(C) if owner(c) == rank]
     chains = []
     for cell in L.cells:
         A = Chain(cell['m0'] - cell['a0'] + WB, cell['m0'] - cell['a0'], WB, cell['has_qa'])
@@ -147,8 +154,19 @@ def cell_solve(S, g, WB, C):
     for p in range(n):
         arr, ix = rhs_locate(p); arr[ix] += g[p]
 
-    # ---- stage 1: all chains (one launch on the device)
-    for A, Bc in chains:
+    # ---- multi-GPU exchange 1: a reduce per cell to its owner (tiles, Q x Q block of the A chain), rhs all-reduced
+    if world > 1:
+        import torch
+        for c in range(C):
+            A, Bc = chains[c]
+            for arr in (A.tiles, Bc.tiles, A.FF):
+                t = torch.from_numpy(arr.reshape(-1)); comm.reduce(t, dst=owner(c))
+            for arr in (A.rhs, Bc.rhs, A.gF, Bc.gF):
+                t = torch.from_numpy(arr.reshape(-1)); comm.all_reduce(t)
+
+    # ---- stage 1: all chains of this rank's cells (one launch on the device)
+    for c in mine:
+        A, Bc = chains[c]
         A.factor(); Bc.factor()
 
     # ---- stage 2: cell separator systems [M | Qa | Qb], M eliminated
@@ -173,8 +191,9 @@ def cell_solve(S, g, WB, C):
                 D[r*T:(r + 1)*T, r2*T:(r2 + 1)*T] = ch.FF[r, r2]
         return np.tril(D)
     sym = lambda Lo: Lo + np.tril(Lo, -1).T
-    cellsys = []
-    for c, cell in enumerate(L.cells):
+    cellsys = {}
+    for c in mine:
+        cell = L.cells[c]
         A, Bc = chains[c]
         MM = sym(dense_lower(A, A.Kend)) + flip(sym(dense_lower(Bc, Bc.Kend)))
         gM = A.rhs[A.Kend:].ravel() + Bc.rhs[Bc.Kend:].ravel()[::-1]
@@ -187,25 +206,30 @@ def cell_solve(S, g, WB, C):
         Sba = -Wb @ Wa.T
         ga = A.gF.ravel() - Wa @ yM
         gb = Bc.gF.ravel()[::-1] - Wb @ yM
-        cellsys.append(dict(LM=LM, yM=yM, Wa=Wa, Wb=Wb, Saa=Saa, Sbb=Sbb, Sba=Sba, ga=ga, gb=gb))
+        cellsys[c] = dict(LM=LM, yM=yM, Wa=Wa, Wb=Wb, Saa=Saa, Sbb=Sbb, Sba=Sba, ga=ga, gb=gb)
 
-    # ---- stage 3: global boundary-separator system (block tridiagonal over Q_0 .. Q_{C-2}); all-reduced on multi-GPU
+    # ---- stage 3: boundary-separator system (block tridiagonal over Q_0 .. Q_{C-2}): every rank adds the Schur
+    # complements of ITS cells into a zeroed copy; multi-GPU exchange 2: all-reduce; then solved on every rank
     nq = C - 1
     xQ = np.zeros((max(nq, 0), w))
     if nq:
         G = np.zeros((nq*w, nq*w)); gq = np.zeros(nq*w)
-        for c, cs in enumerate(cellsys):
+        for c, cs in cellsys.items():
             if c > 0:
                 G[(c - 1)*w:c*w, (c - 1)*w:c*w] += cs['Saa']; gq[(c - 1)*w:c*w] += cs['ga']
             if c < C - 1:
                 G[c*w:(c + 1)*w, c*w:(c + 1)*w] += cs['Sbb']; gq[c*w:(c + 1)*w] += cs['gb']
             if 0 < c < C - 1:
                 G[c*w:(c + 1)*w, (c - 1)*w:c*w] += cs['Sba']; G[(c - 1)*w:c*w, c*w:(c + 1)*w] += cs['Sba'].T
+        if world > 1:
+            import torch
+            comm.all_reduce(torch.from_numpy(G.reshape(-1))); comm.all_reduce(torch.from_numpy(gq))
         xQ = np.linalg.solve(G, gq).reshape(nq, w)
 
-    # ---- stage 4: back-substitution
+    # ---- stage 4: back-substitution of this rank's cells; multi-GPU exchange 3: all-reduce of the zero-padded solution
     x = np.zeros(n)
-    for c, cell in enumerate(L.cells):
+    for c in mine:
+        cell = L.cells[c]
         A, Bc = chains[c]; cs = cellsys[c]
         xa = xQ[c - 1] if cell['has_qa'] else np.zeros(w)
         xb = xQ[c] if cell['has_qb'] else np.zeros(w)
@@ -216,6 +240,9 @@ def cell_solve(S, g, WB, C):
         x[m0 + w:b1] = Bc.backward(xM[::-1].reshape(WB, T), xb[::-1].reshape(WB, T)).ravel()[::-1]
         if cell['has_qb']:
             x[b1:b1 + w] = xb
+    if world > 1:
+        import torch
+        comm.all_reduce(torch.from_numpy(x))
     return x
 
 
