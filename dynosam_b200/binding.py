@@ -24,7 +24,7 @@ REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.
 EXPORTS = [
     "dynoba_version", "dynoba_status_string", "dynoba_last_error", "dynoba_create", "dynoba_destroy",
     "dynoba_lm_default_params", "dynoba_set_variables", "dynoba_set_aux_poses", "dynoba_set_calibration",
-    "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_set_reduce", "dynoba_set_partition", "dynoba_set_tuning", "dynoba_fp64_rate", "dynoba_finalize", "dynoba_error",
+    "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_set_reduce", "dynoba_set_partition", "dynoba_set_tuning", "dynoba_fp64_rate", "dynoba_add_linear_prior", "dynoba_marginal", "dynoba_finalize", "dynoba_error",
     "dynoba_optimize", "dynoba_get_variables", "dynoba_get_keys", "dynoba_num_variables", "dynoba_problem_info",
     "dynoba_linearize", "dynoba_linearize_block", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
     "dynoba_get_reduced_system", "dynoba_retract",
@@ -82,6 +82,8 @@ def load():
         L.dynoba_set_partition.argtypes = [C.c_void_p, C.c_int]
         L.dynoba_set_tuning.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.dynoba_fp64_rate.argtypes = [C.c_void_p, c_dp]
+        L.dynoba_add_linear_prior.argtypes = [C.c_void_p, C.c_int32, c_ip, c_dp, c_dp, c_dp, C.c_double]
+        L.dynoba_marginal.argtypes = [C.c_void_p, C.c_int32, c_ip, c_dp, c_dp]
         L.dynoba_finalize.argtypes = [C.c_void_p]
         L.dynoba_error.argtypes = [C.c_void_p, c_dp]
         L.dynoba_optimize.argtypes = [C.c_void_p, C.POINTER(LmParams), C.POINTER(LmStats)]
@@ -162,11 +164,27 @@ class Solver:
             self.add_factors(b)
         if p.pose_order is not None:
             self._ck(L.dynoba_set_pose_order(self.h, p.n_pose, _ip(p.pose_order)))
+        for pr in getattr(p, "linear_priors", []):
+            self.add_linear_prior(pr["idx"], pr["lin"], pr["G"], pr["g"], pr.get("f", 0.0))
 
     def add_factors(self, b):
         self._ck(self.lib.dynoba_add_factors(self.h, b.type, b.n, _ip(b.idx), _dp(b.meas) if b.meas is not None else C.cast(None, c_dp),
                                              _dp(b.sigma), b.sigma_dim, 1 if b.sigma_bcast else b.n, float(b.robust_k),
                                              _ip(b.aux_idx) if b.aux_idx is not None else C.cast(None, c_ip)))
+
+    def add_linear_prior(self, idx, lin, G, g, f=0.0):
+        """gtsam::LinearContainerFactor(HessianFactor): error = 1/2 d^T G d - g^T d + 1/2 f, d = localCoordinates(lin, x)"""
+        idx = np.ascontiguousarray(idx, dtype=np.int32); lin = np.ascontiguousarray(lin, dtype=np.float64).reshape(-1, 12)
+        G = np.ascontiguousarray(G, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)
+        assert G.shape == (6*idx.size, 6*idx.size) and g.shape == (6*idx.size,)
+        self._ck(self.lib.dynoba_add_linear_prior(self.h, idx.size, _ip(idx), _dp(lin), _dp(G), _dp(g), float(f)))
+
+    def marginal(self, keep_idx):
+        """(G, g): marginal information of the pose-like variables keep_idx (the last ones in frame order) at the current values"""
+        keep = np.ascontiguousarray(keep_idx, dtype=np.int32); k = keep.size
+        G = np.zeros((6*k, 6*k)); g = np.zeros(6*k)
+        self._ck(self.lib.dynoba_marginal(self.h, k, _ip(keep), _dp(G), _dp(g)))
+        return G, g
 
     def set_shard(self, rank, world, allreduce, min_bandwidth=0):
         """allreduce(dev_ptr:int, n:int, stream:int) -> None sums n doubles in place across ranks."""

@@ -48,6 +48,11 @@ struct HostBlock {
   DevWindows win{}; bool use_window = false; bool all_window = false;   // all_window: no group left for the per-landmark atomics kernel
 };
 
+struct HostPrior {      // gtsam::LinearContainerFactor(HessianFactor) over pose-like variables
+  std::vector<int32_t> idx; std::vector<double> lin, G, g; double f = 0;
+  DevPrior dev{}; int part_off = 0, bs_off = 0;
+};
+
 }  // namespace
 
 struct dynoba_solver {
@@ -56,6 +61,7 @@ struct dynoba_solver {
   double calib[6] = { 721.5377, 721.5377, 0.0, 609.5593, 172.854, 0.5372 };
   std::vector<int32_t> hint;
   std::vector<HostBlock> blocks;
+  std::vector<HostPrior> priors;
   bool finalized = false, linearized = false, supported = true;
   std::vector<int32_t> pos, pt_new, fl_new;
   DevVars cur{}, cand{}; BandPlan plan{}; DevBand& band = plan.band; int ncell_request = 0;
@@ -284,6 +290,18 @@ int dynoba_add_factors(dynoba_handle h, int type, int64_t n, const int32_t* idx,
   return DYNOBA_OK;
 }
 
+int dynoba_add_linear_prior(dynoba_handle h, int32_t n, const int32_t* pose_idx, const double* lin_poses, const double* G, const double* g, double f) {
+  ARG(h, "null handle"); ARG(n > 0 && n <= 512 && pose_idx && lin_poses && G && g, "bad prior");
+  HostPrior P; P.idx.assign(pose_idx, pose_idx + n); P.lin.assign(lin_poses, lin_poses + (size_t)12*n);
+  P.G.assign(G, G + (size_t)36*n*n); P.g.assign(g, g + (size_t)6*n); P.f = f;
+  { std::vector<int32_t> srt = P.idx; std::sort(srt.begin(), srt.end()); ARG(std::adjacent_find(srt.begin(), srt.end()) == srt.end(), "a prior lists a variable twice"); }
+  for (int r = 0; r < 6*n; r++) for (int c = 0; c < r; c++)
+    ARG(std::fabs(P.G[(size_t)r*6*n + c] - P.G[(size_t)c*6*n + r]) <= 1e-9*(std::fabs(P.G[(size_t)r*6*n + r]) + std::fabs(P.G[(size_t)c*6*n + c]) + 1e-300), "prior information matrix is not symmetric");
+  h->priors.push_back(std::move(P));
+  if (h->finalized) free_device(h);
+  return DYNOBA_OK;
+}
+
 int dynoba_set_pose_order(dynoba_handle h, int64_t n, const int32_t* rank) {
   ARG(h, "null handle"); ARG(n >= 0 && (n == 0 || rank), "null rank");
   h->hint.assign(rank, rank + n);
@@ -408,6 +426,11 @@ static int finalize_impl(dynoba_solver* h) {
     spread = std::max(spread, bspread); pos_lo = std::min(pos_lo, blo); pos_hi = std::max(pos_hi, bhi);
   }
   for (int64_t g = 0; g < nl; g++) if (gmax[g] >= 0) spread = std::max(spread, gmax[g] - gmin[g]);
+  for (auto& P : h->priors) {       // a prior couples all of its variables
+    int lo = INT32_MAX, hi = -1;
+    for (int32_t ix : P.idx) { ARG(ix >= 0 && ix < np, "prior variable out of range"); lo = std::min(lo, h->pos[ix]); hi = std::max(hi, h->pos[ix]); }
+    spread = std::max(spread, hi - lo); pos_lo = std::min(pos_lo, lo); pos_hi = std::max(pos_hi, hi);
+  }
   // group rank: by first pose position, then root id
   std::vector<int32_t> gorder; gorder.reserve(nl);
   for (int64_t g = 0; g < nl; g++) if (root[g] == g) gorder.push_back((int32_t)g);
@@ -804,6 +827,18 @@ static int finalize_impl(dynoba_solver* h) {
     if ((rc = dalloc(h, &dgnl, gnl.size()))) return rc; CK(cudaMemcpy(dgnl, gnl.data(), gnl.size()*4, cudaMemcpyHostToDevice));
     h->gen.n_groups = (int)gl0.size(); h->gen.blocks = dblk; h->gen.gptr = dgptr; h->gen.refs = drefs; h->gen.gl0 = dgl0; h->gen.gnl = dgnl;
   }
+  for (auto& P : h->priors) {
+    const int n = (int)P.idx.size(); std::vector<int32_t> ppos(n);
+    for (int i = 0; i < n; i++) ppos[i] = h->pos[P.idx[i]];
+    int* dpos; double *dlin, *dG, *dg, *dd, *dgc; int rc;
+    if ((rc = dalloc(h, &dpos, (size_t)n, false))) return rc; CK(cudaMemcpy(dpos, ppos.data(), (size_t)n*4, cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &dlin, (size_t)12*n, false))) return rc; CK(cudaMemcpy(dlin, P.lin.data(), (size_t)12*n*8, cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &dG, (size_t)36*n*n, false))) return rc; CK(cudaMemcpy(dG, P.G.data(), (size_t)36*n*n*8, cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &dg, (size_t)6*n, false))) return rc; CK(cudaMemcpy(dg, P.g.data(), (size_t)6*n*8, cudaMemcpyHostToDevice));
+    if ((rc = dalloc(h, &dd, (size_t)6*n))) return rc; if ((rc = dalloc(h, &dgc, (size_t)6*n))) return rc;
+    P.dev = DevPrior{ n, dpos, dlin, dG, dg, P.f, dd, dgc };
+    P.part_off = part; part += 1; P.bs_off = bs; bs += 1;
+  }
   h->gen_bs_off = bs; bs += general_grid(h->gen.n_groups);
   h->n_lin_partials = part; h->n_bs_partials = bs + pose_norm_grid(B.n);
   h->n_partials = std::max(std::max(h->n_lin_partials, h->n_bs_partials), 1);
@@ -841,6 +876,7 @@ static int allreduce_dev(dynoba_solver* h, double* p, size_t n) {
 // graph.error(values) on the given variable set -> scalars[slot]
 static int eval_error(dynoba_solver* h, const DevVars& v, int slot) {
   for (auto& b : h->blocks) h->launches += launch_error(b.dev, v, h->partials + b.part_off, nullptr, h->stream);
+  for (auto& P : h->priors) h->launches += launch_prior_eval(P.dev, v, h->partials + P.part_off, 0, h->stream);
   h->launches += launch_sum(h->partials, h->n_lin_partials, h->scalars + slot, h->stream);
   return DYNOBA_OK;
 }
@@ -853,6 +889,7 @@ static int do_linearize(dynoba_solver* h) {
     h->launches += launch_linearize(b.dev, h->cur, h->partials + b.part_off, h->stream2);
   for (auto& b : h->blocks) if (numeric_grid(b.type, (int)b.n) == 0)
     h->launches += launch_linearize(b.dev, h->cur, h->partials + b.part_off, h->stream);
+  for (auto& P : h->priors) h->launches += launch_prior_eval(P.dev, h->cur, h->partials + P.part_off, 1, h->stream);   // error(0) of the relinearised Hessian factor
   if (side) { cudaEventRecord(h->ev_join, h->stream2); cudaStreamWaitEvent(h->stream, h->ev_join, 0); }
   h->launches += launch_sum(h->partials, h->n_lin_partials, h->scalars + 0, h->stream);
   h->linearized = true;
@@ -873,6 +910,7 @@ static int build_reduced(dynoba_solver* h, double lambda, bool full_sum = false)
     }
   }
   h->launches += launch_schur_general(h->gen, h->band, lambda, h->fail, h->stream);
+  for (auto& P : h->priors) h->launches += launch_prior_accum(P.dev, h->band, h->stream);
   if (h->world <= 1) return DYNOBA_OK;
   if (full_sum || !h->reduce || h->band.ncell == 0) return allreduce_dev(h, h->band.acc, h->band.acc_count);
   for (auto& r : h->plan.reduce_ranges)
@@ -892,6 +930,7 @@ static int solve_step(dynoba_solver* h, double lambda) {
     else { h->launches += launch_backsub_simple(b.dev, h->band, lambda, h->dl_point, h->cur.nl_stride, h->dl_flow, h->cur.nf_stride, h->partials + b.bs_off, h->stream);
            used = std::max(used, b.bs_off + backsub_grid(b.dev.n_groups)); }
   }
+  for (auto& P : h->priors) { h->launches += launch_prior_model(P.dev, h->band, h->partials + P.bs_off, h->stream); used = std::max(used, P.bs_off + 1); }
   if (h->gen.n_groups) {
     h->launches += launch_backsub_general(h->gen, h->band, lambda, h->dl_point, h->cur.nl_stride, h->partials + h->gen_bs_off, h->stream);
     used = std::max(used, h->gen_bs_off + general_grid(h->gen.n_groups));
@@ -1098,6 +1137,84 @@ int dynoba_retract(dynoba_handle h, const double* delta) {
   CK(cudaStreamSynchronize(h->stream));
   std::swap(h->cur, h->cand);
   h->linearized = false;
+  return DYNOBA_OK;
+}
+
+// Marginal information of the LAST n_keep pose-like variables (solver order) at the current values: every landmark and
+// every other pose-like variable eliminated.  The band Cholesky already leaves a Schur complement in the columns it does
+// not factor, so this is one plain band factorisation that stops at the tile holding the first kept variable; the few
+// scalars of that tile that precede the kept block are eliminated on the host.
+int dynoba_marginal(dynoba_handle h, int32_t n_keep, const int32_t* keep_pose_idx, double* G, double* g) {
+  int rc = check_ready(h, true); if (rc) return rc;
+  ARG(n_keep > 0 && keep_pose_idx && G && g, "bad arguments");
+  const int64_t np = h->cur.np;
+  ARG(n_keep <= np, "more variables than there are");
+  if (h->world > 1) { h->err = "dynoba_marginal is a single-GPU entry point"; return DYNOBA_ERR_UNSUPPORTED; }
+  std::vector<int> slot(n_keep, -1);                    // kept variable k sits at solver position np - n_keep + slot
+  for (int k = 0; k < n_keep; k++) {
+    ARG(keep_pose_idx[k] >= 0 && keep_pose_idx[k] < np, "variable out of range");
+    const int p = h->pos[keep_pose_idx[k]] - (int)(np - n_keep);
+    if (p < 0) { h->err = "the kept variables must be the last ones of the elimination order (most recent frames)"; return DYNOBA_ERR_UNSUPPORTED; }
+    slot[k] = p;
+  }
+  { std::vector<int> srt = slot; std::sort(srt.begin(), srt.end()); ARG(std::adjacent_find(srt.begin(), srt.end()) == srt.end(), "a variable is listed twice"); }
+  if (!h->linearized) do_linearize(h);
+  // a second, plain layout whose factorisation stops before the kept block
+  BandPlan mp{}; mp.outer_weight = 0;
+  if (band_plan_layout(mp, h->band.n, h->band.bw, -1, 0, 1)) { h->err = "band layout failed"; return DYNOBA_ERR_BAD_ARG; }
+  const int p0 = 6*(int)(np - n_keep), K0 = p0/TILE, NT = mp.band.NT, WBm = mp.band.WB;
+  if (NT - K0 > WBm + 1) { h->err = "the kept block is wider than the band of the reduced system"; return DYNOBA_ERR_UNSUPPORTED; }
+  mp.chains[0].Kend = K0;
+  double* dbuf; int* ibuf; char* desc;
+  if ((rc = dalloc(h, &dbuf, mp.n_doubles, false))) return rc;
+  if ((rc = dalloc(h, &ibuf, mp.n_ints, false))) return rc;
+  if ((rc = dalloc(h, &desc, mp.n_desc_bytes))) return rc;
+  band_plan_bind(mp, dbuf, ibuf, desc, nullptr);
+  std::swap(h->plan, mp);                               // (h->band refers to h->plan.band)
+  rc = build_reduced(h, 0.0);
+  if (!rc) h->launches += launch_band_factor(h->plan, h->fail, h->stream);
+  const BandProb ch = h->plan.chains[0];
+  const int m = (NT - K0)*TILE, W1 = WBm + 1;
+  std::vector<double> tiles((size_t)(NT - K0)*W1*TILE2), rhs((size_t)m);
+  int failed = 0;
+  if (!rc) {
+    CK(cudaMemcpyAsync(tiles.data(), ch.tiles + (size_t)K0*W1*TILE2, tiles.size()*8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(rhs.data(), ch.rhs + (size_t)K0*TILE, rhs.size()*8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&failed, h->fail, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  std::swap(h->plan, mp);
+  for (void* q : { (void*)dbuf, (void*)ibuf, (void*)desc }) {
+    auto it = std::find_if(h->allocs.begin(), h->allocs.end(), [&](const std::pair<void*, size_t>& a) { return a.first == q; });
+    if (it != h->allocs.end()) { g_devcache.give(h->device, it->first, it->second); h->allocs.erase(it); }
+  }
+  if (rc) return rc;
+  if (failed) { h->err = "the eliminated block is not positive definite"; return DYNOBA_ERR_INDETERMINATE; }
+  // dense symmetric copy of the trailing block: local scalar q <-> solver position K0*32 + q
+  std::vector<double> M((size_t)m*m, 0.0);
+  for (int j = 0; j < m; j++) for (int i = j; i < m; i++) {
+    const int I = i >> 5, J = j >> 5; if (I - J > WBm) continue;
+    const double v = tiles[((size_t)J*W1 + (I - J))*TILE2 + (size_t)(j & 31)*TILE + (i & 31)];
+    M[(size_t)i*m + j] = v; M[(size_t)j*m + i] = v;
+  }
+  // eliminate the e = p0 - K0*32 scalars in front of the kept block (symmetric Gaussian elimination, e < 32)
+  const int e = p0 - K0*TILE;
+  for (int k = 0; k < e; k++) {
+    const double piv = M[(size_t)k*m + k];
+    if (!(piv > 0.0)) { h->err = "the eliminated block is not positive definite"; return DYNOBA_ERR_INDETERMINATE; }
+    for (int i = k + 1; i < m; i++) {
+      const double l = M[(size_t)i*m + k]/piv;
+      if (l == 0.0) continue;
+      for (int j = k + 1; j < m; j++) M[(size_t)i*m + j] -= l*M[(size_t)k*m + j];
+      rhs[i] -= l*rhs[k];
+    }
+  }
+  const int dim = 6*n_keep;
+  for (int a = 0; a < n_keep; a++) for (int r = 0; r < 6; r++) {
+    const int qi = e + 6*slot[a] + r;
+    g[6*a + r] = rhs[qi];
+    for (int b = 0; b < n_keep; b++) for (int c = 0; c < 6; c++) G[(size_t)(6*a + r)*dim + 6*b + c] = M[(size_t)qi*m + e + 6*slot[b] + c];
+  }
   return DYNOBA_OK;
 }
 

@@ -213,6 +213,17 @@ struct DevWindows {
   double* slots;                 // [n*npose_slots][WIN_SLOT_DOUBLES] staged slots in factor order (HBM scratch)
 };
 
+// Dense quadratic prior over n pose-like variables (kernels_prior.cu): gtsam::LinearContainerFactor(HessianFactor)
+struct DevPrior {
+  int n; const int* pos;          // solver positions of the variables
+  const double* lin;              // [n][12] linearisation point
+  const double* G; const double* g; double f;   // [6n][6n] row-major information, [6n] linear term, constant
+  double* delta; double* gcur;    // [6n] local coordinates / g - G delta at the current linearisation
+};
+int launch_prior_eval(const DevPrior& P, const DevVars& v, double* partial, int store, cudaStream_t s);
+int launch_prior_accum(const DevPrior& P, const DevBand& B, cudaStream_t s);
+int launch_prior_model(const DevPrior& P, const DevBand& B, double* partial, cudaStream_t s);
+
 // ---- launchers (each returns the number of kernels it launched)
 int launch_linearize(const DevBlock& blk, const DevVars& v, double* partials, cudaStream_t s);
 int launch_error(const DevBlock& blk, const DevVars& v, double* partials, double* per_factor, cudaStream_t s);

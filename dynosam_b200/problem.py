@@ -79,6 +79,9 @@ class Problem:
     pose_keys: Optional[np.ndarray] = None    # uint64 gtsam keys, opaque round-trip
     point_keys: Optional[np.ndarray] = None
     meta: dict = field(default_factory=dict)
+    # gtsam::LinearContainerFactor(HessianFactor) priors over pose-like variables (sliding-window marginals): dicts with
+    # idx int32[n], lin [n,12], G [6n,6n], g [6n], f
+    linear_priors: list = field(default_factory=list)
 
     def __post_init__(self):
         self.pose = np.ascontiguousarray(self.pose, dtype=np.float64).reshape(-1, 12)

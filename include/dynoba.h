@@ -106,6 +106,23 @@ int dynoba_set_calibration(dynoba_handle h, const double calib[6]);
 int dynoba_add_factors(dynoba_handle h, int type, int64_t n, const int32_t* idx, const double* meas,
                        const double* sigma, int sigma_dim, int64_t sigma_count, double robust_k,
                        const int32_t* aux_idx);
+/* gtsam::LinearContainerFactor holding a HessianFactor over n pose-like variables -- the form in which the reference's
+ * sliding-window optimiser hands the information of the marginalised variables to the next window
+ * (dynosam_opt/src/SlidingWindowOptimization.cc:67-121,165-190).  lin_poses[n][12] = linearisation point, G[6n][6n]
+ * (row-major, symmetric) and g[6n] = information matrix / vector in the tangent space at the linearisation point
+ * ([omega; v] per pose), f = constant:  error(x) = 1/2 d^T G d - g^T d + 1/2 f  with d_i = Logmap(lin_i^-1 x_i);
+ * linearising at x gives HessianFactor(G, g - G d, ...) as GTSAM does.  A variable may appear once per prior.  With
+ * several ranks, give a prior to exactly one of them. */
+int dynoba_add_linear_prior(dynoba_handle h, int32_t n, const int32_t* pose_idx, const double* lin_poses,
+                            const double* G, const double* g, double f);
+/* Marginal information (G[6k][6k], g[6k]) of the k pose-like variables keep_pose_idx at the current values, every other
+ * variable -- all landmarks and the older pose-like variables -- eliminated: what SlidingWindowOptimization::
+ * CalculateMarginalFactors computes with eliminatePartialMultifrontal (:165-190), ready to be passed to
+ * dynoba_add_linear_prior of the next window together with the current values of the kept variables as linearisation
+ * point.  The kept variables must be the last ones of the elimination order (the most recent frames) and span no more
+ * than the band of the reduced system (else DYNOBA_ERR_UNSUPPORTED).  Difference from the reference: it retains recent
+ * LANDMARKS as well; here every landmark is eliminated into the prior.  Single GPU. */
+int dynoba_marginal(dynoba_handle h, int32_t n_keep, const int32_t* keep_pose_idx, double* G, double* g);
 /* Optional elimination-order hint for pose-like variables (e.g. the frame id encoded in the key):
  * variables are ordered by (rank, index).  Without it the given order is used. */
 int dynoba_set_pose_order(dynoba_handle h, int64_t n, const int32_t* rank);
