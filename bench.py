@@ -98,7 +98,17 @@ def shard_problem(p: Problem, rank: int, world: int) -> Problem:
         if ls and ps:
             np.minimum.at(first, group[b.idx[:, ls[0]]], pos[b.idx[:, ps]].min(1))
     first[first == np.iinfo(np.int64).max] = 0
-    owner_of_pos = lambda q: np.minimum(q*world//max(p.n_pose, 1), world - 1)
+    # slices of the pose axis: the library's own cut of the reduced system into per-rank cells when it is there (so that a
+    # rank's landmarks contribute to the cells it owns), else uniform
+    try:
+        from dynosam_b200.binding import plan_partition
+        bounds = plan_partition(p.n_pose, problem_bandwidth(p), world).astype(np.int64)
+    except Exception:
+        bounds = None
+    if bounds is not None and (np.diff(bounds) > 0).all():
+        owner_of_pos = lambda q: np.clip(np.searchsorted(bounds, q, side="right") - 1, 0, world - 1)
+    else:
+        owner_of_pos = lambda q: np.minimum(q*world//max(p.n_pose, 1), world - 1)
     keep_pt = owner_of_pos(first)[group] == rank
     new_idx = np.cumsum(keep_pt) - 1
     blocks = []

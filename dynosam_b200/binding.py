@@ -24,7 +24,7 @@ REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.
 EXPORTS = [
     "dynoba_version", "dynoba_status_string", "dynoba_last_error", "dynoba_create", "dynoba_destroy",
     "dynoba_lm_default_params", "dynoba_set_variables", "dynoba_set_aux_poses", "dynoba_set_calibration",
-    "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_set_reduce", "dynoba_set_partition", "dynoba_set_tuning", "dynoba_fp64_rate", "dynoba_add_linear_prior", "dynoba_marginal", "dynoba_finalize", "dynoba_error",
+    "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_set_reduce", "dynoba_set_partition", "dynoba_plan_partition", "dynoba_set_tuning", "dynoba_fp64_rate", "dynoba_add_linear_prior", "dynoba_marginal", "dynoba_finalize", "dynoba_error",
     "dynoba_optimize", "dynoba_get_variables", "dynoba_get_keys", "dynoba_num_variables", "dynoba_problem_info",
     "dynoba_linearize", "dynoba_linearize_block", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
     "dynoba_get_reduced_system", "dynoba_retract",
@@ -80,6 +80,7 @@ def load():
         L.dynoba_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p, C.c_int]
         L.dynoba_set_reduce.argtypes = [C.c_void_p, REDUCE_FN, C.c_void_p]
         L.dynoba_set_partition.argtypes = [C.c_void_p, C.c_int]
+        L.dynoba_plan_partition.argtypes = [C.c_int32, C.c_int32, C.c_int32, c_ip]
         L.dynoba_set_tuning.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.dynoba_fp64_rate.argtypes = [C.c_void_p, c_dp]
         L.dynoba_add_linear_prior.argtypes = [C.c_void_p, C.c_int32, c_ip, c_dp, c_dp, c_dp, C.c_double]
@@ -108,6 +109,15 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(c_ip) if a is not None and a.size else C.cast(None, c_ip)
+
+
+def plan_partition(n_poses, bandwidth, world):
+    """first pose position (elimination order) of every rank's cells, [world + 1] (pure host computation, no GPU needed)"""
+    out = np.zeros(world + 1, np.int32)
+    st = load().dynoba_plan_partition(int(n_poses), int(bandwidth), int(world), _ip(out))
+    if st != OK:
+        raise DynobaError(st, "dynoba_plan_partition")
+    return out
 
 
 def default_params(**kw) -> LmParams:

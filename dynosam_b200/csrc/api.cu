@@ -322,6 +322,14 @@ int dynoba_set_tuning(dynoba_handle h, const char* name, double value) {
   else ARG(false, "unknown tuning parameter");
   return DYNOBA_OK;
 }
+int dynoba_plan_partition(int32_t n_poses, int32_t bandwidth, int32_t world, int32_t* first_position) {
+  if (n_poses <= 0 || world < 1 || !first_position) return DYNOBA_ERR_BAD_ARG;
+  std::vector<int> b(world + 1);
+  if (band_plan_partition(6*n_poses, bandwidth, world, b.data()) < 0) return DYNOBA_ERR_BAD_ARG;
+  for (int r = 0; r <= world; r++) first_position[r] = std::min(b[r]/6, n_poses);
+  first_position[world] = n_poses;
+  return DYNOBA_OK;
+}
 int dynoba_set_partition(dynoba_handle h, int ncells) {
   ARG(h, "null handle"); ARG(ncells >= -1 && ncells <= MAX_CELLS, "ncells out of range");
   h->ncell_request = ncells;

@@ -262,6 +262,7 @@ struct BandPlan {
   std::vector<Range> reduce_ranges; double* rhs_region; size_t rhs_count;
 };
 int band_plan_layout(BandPlan& P, int n, int bw, int ncell_request, int rank, int world);   // 0 = ok
+int band_plan_partition(int n, int bw, int world, int* bounds);   // returns the number of cells
 void band_plan_bind(BandPlan& P, double* dbase, int* ibase, void* desc_base, double* dp);
 void band_plan_trim(BandPlan& P, const int* lo, const int* hi);   // [world] scalar position ranges the ranks' factors touch -> reduce_ranges
 void band_set_tuning(int band_ctas_per_chain);

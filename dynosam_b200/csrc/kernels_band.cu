@@ -1249,8 +1249,13 @@ int band_plan_layout(BandPlan& P, int n, int bw, int ncell_request, int rank, in
     P.chains.push_back(p);
   } else {
     const long long free_tiles = (long long)NT - (long long)(2*C - 1)*WB;
-    const double outer_weight = P.outer_weight > 0 ? P.outer_weight : ((C >= 2 && world == 1) ? 4.5 : 1.0);
-    std::vector<double> wgt(2*C, 1.0); wgt[0] = wgt[2*C - 1] = outer_weight;
+    // relative chain lengths.  One GPU: plain end chains 4.5x the spiked ones.  Several GPUs (one cell per rank): a rank in
+    // the middle runs two spiked chains (weight 0.5 each); an end rank runs its plain chain at the spine's pace
+    // (10.4 us per column against the ~12.9 us a middle rank needs per spiked column: weight 1.24) and, with the worker
+    // CTAs that leaves for the spike pool, a shorter spiked chain (0.6) -- measured rates of C5, see DESIGN.md section 6.
+    std::vector<double> wgt(2*C, 1.0);
+    if (P.outer_weight > 0 || world == 1 || C != world) { wgt[0] = wgt[2*C - 1] = P.outer_weight > 0 ? P.outer_weight : (C >= 2 ? 4.5 : 1.0); }
+    else { for (auto& x : wgt) x = 0.5; wgt[0] = wgt[2*C - 1] = 1.24; wgt[1] = wgt[2*C - 2] = 0.6; }
     double wsum = 0; for (double x : wgt) wsum += x;
     std::vector<int> len(2*C);
     long long used = 0;
@@ -1308,6 +1313,19 @@ int band_plan_layout(BandPlan& P, int n, int bw, int ncell_request, int rank, in
   P.n_ints = ni;
   P.n_desc_bytes = align_up(sizeof(BandProb)*(size_t)(2*P.nchain + 2*P.ncs + 1) + sizeof(CellGeom)*(size_t)std::max(C, 1) + sizeof(int)*(size_t)std::max(C, 1), 256) + 1024;
   return 0;
+}
+
+// first scalar position of the cells owned by each rank (bounds[world] = n_pad): what the host needs to shard landmarks
+// so that a rank's contribution stays inside its own cells
+int band_plan_partition(int n, int bw, int world, int* bounds) {
+  BandPlan P{}; P.outer_weight = 0;
+  if (band_plan_layout(P, n, bw, 0, 0, world)) return -1;
+  const int C = P.band.ncell;
+  for (int r = 0; r <= world; r++) bounds[r] = P.band.n_pad;
+  bounds[0] = 0;
+  for (int c = C - 1; c >= 0; c--) { const int owner = c*world/C; bounds[owner] = c == 0 ? 0 : P.cells[c].q0; }
+  for (int r = world - 1; r > 0; r--) if (bounds[r] > bounds[r + 1]) bounds[r] = bounds[r + 1];     // ranks without a cell
+  return C;
 }
 
 void band_plan_bind(BandPlan& P, double* dbase, int* ibase, void* desc_base, double* dp) {

@@ -139,6 +139,12 @@ int dynoba_set_reduce(dynoba_handle h, dynoba_reduce_fn fn, void* ctx);
  * band factorisation.  The request is clamped to what the system's length allows.  GTSAM equivalent: the elimination
  * ordering of LevenbergMarquardtParams (RegularBackendModule.cc:405-419 leaves it at COLAMD). */
 int dynoba_set_partition(dynoba_handle h, int ncells);
+/* The cells' extent on the pose axis for a reduced system of n_poses pose-like variables and the given scalar
+ * half-bandwidth, cut for `world` ranks: first_position[r] = first pose position (in elimination order) of rank r's cells,
+ * first_position[world] = n_poses.  A host that shards landmarks by the position of their first pose along these bounds
+ * keeps every rank's contribution inside its own cells (plus a halo one co-visibility window wide).  Needs no handle
+ * and no device. */
+int dynoba_plan_partition(int32_t n_poses, int32_t bandwidth, int32_t world, int32_t* first_position);
 /* Performance parameters of the reduced solve (results do not depend on them): "outer_weight" = relative length of the
  * two end chains, which carry no spike (default 4.5 on one GPU, 1 otherwise); "band_ctas_per_chain" = worker CTAs that
  * serve the band tiles of one chain (the others stream the spike updates; process-wide). */
