@@ -246,7 +246,7 @@ def cpu_oracle_leg(cfg_name, formulation, seed, scale, iters):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant Jacobian-build kernel, from an `ncu --set full`
 # capture of this very launch (a counter value cannot be measured inside a timed run); the capture is named next to it.
 # Only valid for the exact launch that was profiled: C5 at full scale on one GPU; anything else reports null.
-NCU_TRAFFIC = {("C5", "hybrid", 5, 11376204): (577.77e6 + 4309.57e6, "profiles/r01_final.md (ncu --set full of the same launch)")}
+NCU_TRAFFIC = {("C5", "hybrid", 5, 11376204): (576.973e6 + 4550.677e6, "profiles/r02_final.md section 3 (ncu --set full of the same launch)")}
 
 
 def ncu_traffic(args, world, blk):
