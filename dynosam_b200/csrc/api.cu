@@ -708,7 +708,7 @@ static int finalize_impl(dynoba_solver* h) {
       // ---- window decomposition (kernels_window.cu) for the 3-dof landmark types
       const bool win_type = b.type == F_POSE2POINT3 || b.type == F_STEREO3 || b.type == F_HYBRID3 || b.type == F_HYBRID_STEREO3;
       b.use_window = false; b.all_window = false; b.win = DevWindows{};
-      if (win_type && !gl.empty() && !getenv("DYNOBA_NO_WINDOW")) {
+      if (win_type && !gl.empty()) {
         const int ng = (int)gl.size(), NPs = ti.npose;
         std::vector<unsigned char> gwin(ng, 0);
         std::vector<unsigned char, NoInitAlloc<unsigned char>> lvar((size_t)NPs*stride);   // only read for window-path factors
@@ -716,7 +716,6 @@ static int finalize_impl(dynoba_solver* h) {
         int pose_slot[2] = {0, 0}; { int c = 0; for (int k = 0; k < ti.arity; k++) if (ti.cls[k] == VC_POSE && c < 2) pose_slot[c++] = k; }
         // window size: one 512-thread CTA holds 16 tiles of 8x4 blocks; NLOC 24 -> 12 tiles (one stripe), NLOC 40 -> 30 (two)
         int cap = NPs == 1 ? 24 : 40;
-        if (const char* e = getenv(NPs == 1 ? "DYNOBA_WIN_CAP1" : "DYNOBA_WIN_CAP2")) cap = std::max(2, std::min(WIN_NLOC_MAX, atoi(e)));
         // greedy chunking, independently inside parallel segments of the group list (a chunk never crosses a segment)
         const int nseg = std::max(1, std::min<int>(omp_get_max_threads(), ng/4096 + 1));
         struct SegOut { std::vector<int32_t> g0, nloc, cv, b0; std::vector<int4> bat; };   // b0: first batch of each chunk (+ end)
