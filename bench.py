@@ -3,11 +3,16 @@
 
 One "step" = one outer Levenberg-Marquardt iteration (1 materialising linearize + >= 1 damped Schur solve +
 >= 1 chi^2 sweep) on the synthetic 10k-key-frame / 100-object / 2M-landmark dynamic graph (BASELINE.json
-configs[4]; it fits one B200, so it is also the N=1 workload).  Landmarks are sharded over the N ranks; the
-reduced system is summed with one NCCL all-reduce per damped solve (strong scaling: total work fixed).
+configs[4]; it fits one B200, so it is also the N=1 workload).  N > 1: landmarks are sharded in time over the ranks and
+the reduced solve is distributed (one cell of the banded system per rank: a reduce per cell, an all-reduce of the small
+boundary-separator system and of the pose update); strong scaling: total work fixed.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config C5|C3|C2|C1] [--scale s]
-    python bench.py --impl reference ...    # CPU arm: the oracle port timed on the host cores
+    python bench.py --impl reference ...    # CPU arm: the oracle port on the host cores, same config at full size
+
+The JSON line carries `roofline` (Jacobian-build kernel vs measured HBM bandwidth), `reduced_solve` (vs the fp64 rate
+measured on the box), `e2e` (through the C ABI from host arrays), `cpu_baseline` + `parity_check` (one full-size LM
+iteration of the oracle port, compared with the GPU's first iteration) and `configs` (C2, C3, front-end C4).
 """
 from __future__ import annotations
 

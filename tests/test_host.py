@@ -307,3 +307,17 @@ def test_distributed_cell_solve_gloo(tmp_path):
                        capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("cells ok") == 2
+
+
+def test_plan_partition_is_a_pure_host_function():
+    """dynoba_plan_partition needs neither a handle nor a device: monotone bounds covering the pose axis; with one cell per
+    rank the end ranks (plain chain + short spiked chain) get more of the axis than the middle ranks (two spiked chains)."""
+    from dynosam_b200.binding import plan_partition
+    for world in (1, 2, 4, 8):
+        b = plan_partition(60027, 959, world)
+        assert b[0] == 0 and b[-1] == 60027 and (np.diff(b) > 0).all(), (world, b)
+    b = np.diff(plan_partition(60027, 959, 8))
+    assert b[0] > 1.5*b[3] and b[-1] > 1.5*b[3] and abs(int(b[2]) - int(b[4])) <= 64
+    # a system too short for eight cells still yields valid bounds (ranks without a cell own an empty slice)
+    b = plan_partition(300, 959, 8)
+    assert b[0] == 0 and b[-1] == 300 and (np.diff(b) >= 0).all()
