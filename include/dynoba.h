@@ -184,6 +184,42 @@ int dynoba_get_reduced_system(dynoba_handle h, double lambda, double* S, double*
 /* values.retract(delta), same layout as dynoba_solve */
 int dynoba_retract(dynoba_handle h, const double* delta);
 
+/* ---- graph construction straight into SoA blocks: what Formulation<MAP>::updateStaticObservations /
+ * updateDynamicObservations + the hybrid formulation's callbacks do with the Map
+ * (dynosam/include/dynosam/backend/Formulation-impl.hpp:552-897, src/backend/rgbd/HybridEstimator.cc:573-830), without
+ * allocating a factor object per observation: feed frames and observations, get the variable arrays and one homogeneous
+ * block per factor type (read them back, or hand them to a solver handle with dynoba_builder_emit).  Host code only. */
+typedef struct dynoba_builder* dynoba_builder_handle;
+typedef struct {
+  int32_t min_static_obs, min_dynamic_obs;   /* min_static_observations (2), min_dynamic_observations (3) */
+  int32_t keyframe_gap;                      /* new object key-frame once unseen for more than this many frames (2) */
+  double sigma_static, sigma_dynamic;        /* isotropic point noise (0.2) */
+  double huber_k;                            /* 1e-4; <= 0: Gaussian */
+  double odometry_sigma[6], smoothing_sigma[6];
+  double prior_sigma;                        /* 1e-6 */
+} dynoba_builder_params;
+void dynoba_builder_default_params(dynoba_builder_params* p);
+int dynoba_builder_create(const dynoba_builder_params* p, dynoba_builder_handle* out);
+int dynoba_builder_destroy(dynoba_builder_handle b);
+const char* dynoba_builder_last_error(dynoba_builder_handle b);
+/* camera pose estimate X[12] of a frame and (NULL for the first frame) the odometry measurement from the previous frame */
+int dynoba_builder_add_frame(dynoba_builder_handle b, int32_t frame, const double* X, const double* odom_from_prev);
+/* point measurements in the camera frame, z[n][3]; object ids start at 1 */
+int dynoba_builder_add_static(dynoba_builder_handle b, int32_t frame, int64_t n, const int64_t* tracklet, const double* z);
+int dynoba_builder_add_dynamic(dynoba_builder_handle b, int32_t frame, int64_t n, const int64_t* tracklet, const int32_t* object, const double* z);
+/* initial value of the cumulative motion e_H_k (front-end estimate; identity at key-frames) / fixed key-frame pose L_e
+ * (default: centroid of the key-frame's points, identity rotation) */
+int dynoba_builder_set_motion_init(dynoba_builder_handle b, int32_t object, int32_t frame, const double* H);
+int dynoba_builder_set_keyframe_pose(dynoba_builder_handle b, int32_t object, int32_t keyframe, const double* L_e);
+int dynoba_builder_finalize(dynoba_builder_handle b);
+int dynoba_builder_counts(dynoba_builder_handle b, int64_t* n_pose, int64_t* n_point, int64_t* n_aux, int32_t* n_blocks);
+int dynoba_builder_get_variables(dynoba_builder_handle b, double* pose, double* point, double* aux, int32_t* pose_order,
+                                 uint64_t* pose_keys, uint64_t* point_keys);
+int dynoba_builder_block_info(dynoba_builder_handle b, int32_t block, int32_t* type, int64_t* n, int32_t* sigma_dim,
+                              int64_t* sigma_count, double* robust_k, int32_t* has_aux);
+int dynoba_builder_get_block(dynoba_builder_handle b, int32_t block, int32_t* idx, double* meas, double* sigma, int32_t* aux_idx);
+int dynoba_builder_emit(dynoba_builder_handle b, dynoba_handle h);
+
 #ifdef __cplusplus
 }
 #endif
