@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdynofront.so")
 EXPORTS = ["dynofront_create", "dynofront_destroy", "dynofront_last_error", "dynofront_set_frame", "dynofront_track_dynamic",
            "dynofront_sample_candidates", "dynofront_propagate_mask", "dynofront_klt_track", "dynofront_klt_track_fb",
-           "dynofront_klt_last_min_eig", "dynofront_track_static_flow", "dynofront_next_frame", "dynofront_pin_host", "dynofront_unpin_host",
+           "dynofront_klt_last_min_eig", "dynofront_stereo_track", "dynofront_track_static_flow", "dynofront_next_frame", "dynofront_pin_host", "dynofront_unpin_host",
            "dynofront_get_motion_mask", "dynofront_get_pyramid_level"]
 
 
@@ -59,6 +59,8 @@ def load():
                                           C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double, C.POINTER(C.c_float)]
         L.dynofront_klt_track_fb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(KltFbParamsC), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        L.dynofront_stereo_track.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.dynofront_klt_last_min_eig.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.dynofront_track_static_flow.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                                   C.POINTER(C.c_int64)] + [C.c_void_p]*8 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -190,6 +192,15 @@ class FeatureTrackerGPU:
                                                  C.byref(ns), C.byref(nk), C.byref(ms)))
         self.last_ms = ms.value; self.last_counts = (ns.value, nk.value)
         return nxt, st, back, (keep if check else None)
+
+    def stereo_track(self, left_gray, right_gray, left_pts, fx, baseline):
+        """FeatureTracker::stereoTrack without its RANSAC: (right_pts, status, depth, valid)"""
+        lg = np.ascontiguousarray(left_gray, dtype=np.uint8); rg = np.ascontiguousarray(right_gray, dtype=np.uint8)
+        p0 = np.ascontiguousarray(left_pts, dtype=np.float32).reshape(-1, 2); n = p0.shape[0]
+        rp = np.zeros((n, 2), np.float32); st = np.zeros(n, np.uint8); depth = np.zeros(n); valid = np.zeros(n, np.uint8); ms = C.c_float()
+        self._ck(self.lib.dynofront_stereo_track(self.h, _p(lg), _p(rg), n, _p(p0), _p(rp), _p(st), float(fx), float(baseline), _p(depth), _p(valid), C.byref(ms)))
+        self.last_ms = ms.value
+        return rp, st, depth, valid
 
     def klt_last_min_eig(self, n):
         out = np.zeros((n, 2), np.float32)

@@ -36,6 +36,7 @@ struct dynofront_ctx {
   std::vector<uint8_t*> pyr[2]; std::vector<short*> der; std::vector<int> lw, lh;
   float *k_prev = nullptr, *k_next = nullptr, *k_err = nullptr; uint8_t* k_st = nullptr; int k_cap = 0;
   float *k_back = nullptr, *k_eig = nullptr; uint8_t *k_st2 = nullptr, *k_keep = nullptr; int32_t* k_age = nullptr; int* k_count = nullptr;   // forward-backward tracker
+  double* st_depth = nullptr; int st_cap = 0;     // stereoTrack
   std::vector<short*> der2;                       // Scharr derivatives of the CURRENT image (backward pass)
   // external-flow static tracker scratch
   int sf_cap = 0, sf_cells = 0; double* sf_kp = nullptr; int32_t* sf_age = nullptr; uint8_t* sf_use = nullptr; int32_t* sf_det = nullptr;
@@ -831,6 +832,54 @@ int dynofront_klt_track_fb(dynofront_handle h, const uint8_t* prev_gray, const u
   FCK(cudaStreamSynchronize(h->s));
   FCK(cudaGetLastError());
   if (n_status) *n_status = counts[0]; if (n_keep) *n_keep = counts[1];
+  if (ms_device) FCK(cudaEventElapsedTime(ms_device, h->e0, h->e1));
+  return 0;
+}
+
+// FeatureTracker::stereoTrack (FeatureTracker.cc:194-337): left -> right LK (21x21, 5 levels, OpenCV default criteria), then per
+// matched point disparity = uL - uR, rejected when <= 1 px or uR < 0, depth = fx * baseline / disparity.  (The reference also
+// runs the right -> left pass but its round-trip filter is commented out, :240-253, and a fundamental-matrix RANSAC sits between
+// the LK status and the disparity test: host code outside section 8 -- final = status & ransac_mask & valid.)
+__global__ void stereo_post_kernel(int n, const float* __restrict__ left, const float* __restrict__ right, const uint8_t* __restrict__ st, double fx,
+                                   double baseline, double* __restrict__ depth, uint8_t* __restrict__ valid) {
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double uL = (double)left[2*i], uR = (double)right[2*i];
+  const double disparity = uL - uR;
+  const bool ok = st[i] && !(disparity <= 1.0 || right[2*i] < 0.0f);
+  valid[i] = ok ? 1 : 0;
+  depth[i] = ok ? fx*baseline/disparity : 0.0;
+}
+int dynofront_stereo_track(dynofront_handle h, const uint8_t* left_gray, const uint8_t* right_gray, int32_t n, const float* left_pts, float* right_pts,
+                           uint8_t* status, double fx, double baseline, double* depth, uint8_t* valid, float* ms_device) {
+  if (!h || !left_gray || !right_gray || n < 0 || !left_pts || !right_pts || !status || !depth || !valid) return -1;
+  cudaSetDevice(h->dev);
+  const int win = 21, max_level = 5;
+  int levels = 0; { int w = h->W, hh = h->H; for (int l = 0; l <= max_level && l < 8; l++) { levels = l; if (l < max_level) { const int w2 = (w + 1)/2, h2 = (hh + 1)/2; if (w2 <= win || h2 <= win) break; w = w2; hh = h2; } } }
+  if (n > h->k_cap) { if (klt_scratch(h, std::max(n, 4096))) return -3; }
+  double* d_depth = nullptr;
+  if (n > h->st_cap) { if (falloc(h, &h->st_depth, (size_t)std::max(n, 4096))) return -3; h->st_cap = std::max(n, 4096); }
+  d_depth = h->st_depth;
+  FCK(cudaEventRecord(h->e0, h->s));
+  if (build_pyramid(h, 0, left_gray, levels, win, true)) return -3;
+  if (build_pyramid(h, 1, right_gray, levels, win, false)) return -3;
+  h->have_pyr = h->have_pyr_cur = false;
+  FCK(cudaMemcpyAsync(h->k_prev, left_pts, 2*(size_t)n*4, cudaMemcpyHostToDevice, h->s));
+  FCK(cudaMemcpyAsync(h->k_next, left_pts, 2*(size_t)n*4, cudaMemcpyHostToDevice, h->s));
+  KltLevels L; L.nlev = levels + 1;
+  for (int l = 0; l <= levels; l++) { L.I[l] = h->pyr[0][l]; L.J[l] = h->pyr[1][l]; L.D[l] = h->der[l]; L.w[l] = h->lw[l]; L.h[l] = h->lh[l]; }
+  if (n > 0) {
+    klt_kernel<<<(n + KLT_WARPS - 1)/KLT_WARPS, KLT_WARPS*32, (size_t)KLT_WARPS*win*win*3*sizeof(short), h->s>>>(L, n, h->k_prev, h->k_next, h->k_st, h->k_err, win, 30, 0.01f*0.01f,
+                                                                                                                0, 1e-4f, h->k_eig);
+    stereo_post_kernel<<<(n + 255)/256, 256, 0, h->s>>>(n, h->k_prev, h->k_next, h->k_st, fx, baseline, d_depth, h->k_keep);
+  }
+  FCK(cudaMemcpyAsync(right_pts, h->k_next, 2*(size_t)n*4, cudaMemcpyDeviceToHost, h->s));
+  FCK(cudaMemcpyAsync(status, h->k_st, n, cudaMemcpyDeviceToHost, h->s));
+  FCK(cudaMemcpyAsync(depth, d_depth, (size_t)n*8, cudaMemcpyDeviceToHost, h->s));
+  FCK(cudaMemcpyAsync(valid, h->k_keep, n, cudaMemcpyDeviceToHost, h->s));
+  FCK(cudaEventRecord(h->e1, h->s));
+  FCK(cudaStreamSynchronize(h->s));
+  FCK(cudaGetLastError());
   if (ms_device) FCK(cudaEventElapsedTime(ms_device, h->e0, h->e1));
   return 0;
 }

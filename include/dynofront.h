@@ -8,6 +8,7 @@
  *   dynofront_propagate_mask    FeatureTracker::propogateMask       FeatureTracker.cc:1212-1359
  *   dynofront_track_static_flow ExternalFlowFeatureTracker::trackStatic / constructStaticFeature  StaticFeatureTracker.cc:70-220
  *   dynofront_klt_track_fb      KltFeatureTracker::trackPoints: forward + backward LK, round-trip test, label / border / age checks (:486-592)
+ *   dynofront_stereo_track      FeatureTracker::stereoTrack: left -> right LK + disparity / depth test  FeatureTracker.cc:194-337
  *   dynofront_klt_track         cv::calcOpticalFlowPyrLK as called by KltFeatureTracker::trackPoints
  *                               (StaticFeatureTracker.cc:420-625) and FeatureTracker::trackDynamicKLT (FeatureTracker.cc:500-862)
  * Images are row-major, tightly packed: flow float32[H][W][2] (CV_32FC2), masks int32[H][W] (CV_32S, ObjectId),
@@ -96,6 +97,12 @@ typedef struct {
 int dynofront_klt_track_fb(dynofront_handle h, const uint8_t* prev_gray, const uint8_t* cur_gray, int32_t n, const float* prev_pts,
                            float* next_pts, uint8_t* status, float* back_pts, const dynofront_klt_fb_params* prm,
                            const int32_t* prev_age, uint8_t* keep, int32_t* n_status, int32_t* n_keep, float* ms_device);
+/* FeatureTracker::stereoTrack (FeatureTracker.cc:194-337): LK from the left to the right image (21x21, 5 levels, OpenCV default
+ * criteria) and the per-point disparity test: valid[i] = status[i] && !(uL - uR <= 1 || uR < 0), depth[i] = fx * baseline /
+ * (uL - uR) (0 where invalid).  The fundamental-matrix RANSAC the reference runs between the two is host code:
+ * final = status & ransac_mask & valid. */
+int dynofront_stereo_track(dynofront_handle h, const uint8_t* left_gray, const uint8_t* right_gray, int32_t n, const float* left_pts,
+                           float* right_pts, uint8_t* status, double fx, double baseline, double* depth, uint8_t* valid, float* ms_device);
 /* parity hook: (min eigenvalue, trace/(2 win^2)) of the level-0 spatial gradient matrix of the last forward pass, [n][2] */
 int dynofront_klt_last_min_eig(dynofront_handle h, int32_t n, float* out);
 

@@ -241,3 +241,22 @@ def klt_track_fb(prev_gray, cur_gray, prev_pts, motion_mask=None, prev_age=None,
                 continue
             keep[i] = 1
     return nxt, status, back, keep
+
+
+def stereo_track(left_gray, right_gray, left_pts, fx, baseline):
+    """FeatureTracker::stereoTrack (FeatureTracker.cc:194-337) without the fundamental-matrix RANSAC: cv2 LK left -> right
+    (21x21, maxLevel 5, default criteria), then disparity = uL - uR, rejected when <= 1 or uR < 0, depth = fx b / disparity."""
+    import cv2
+    p0 = np.ascontiguousarray(left_pts, dtype=np.float32).reshape(-1, 1, 2)
+    rp, st, _ = cv2.calcOpticalFlowPyrLK(left_gray, right_gray, p0, None, winSize=(21, 21), maxLevel=5)
+    rp = rp.reshape(-1, 2); st = st.reshape(-1)
+    n = len(st); depth = np.zeros(n); valid = np.zeros(n, np.uint8)
+    for i in range(n):
+        if not st[i]:
+            continue
+        uL = float(p0[i, 0, 0]); uR = float(rp[i, 0])
+        disparity = uL - uR
+        if disparity <= 1.0 or rp[i, 0] < np.float32(0.0):
+            continue
+        valid[i] = 1; depth[i] = fx*baseline/disparity
+    return rp, st, depth, valid

@@ -315,3 +315,30 @@ def test_streaming_mode_equals_call_by_call():
         for x, y in zip(ka, kb):
             assert np.array_equal(x, y), k
     a.unpin(frames[1][0]); a.unpin(frames[1][1]); a.unpin(frames[1][2])
+
+
+@pytest.mark.gpu
+def test_stereo_track_matches_opencv():
+    """FeatureTracker::stereoTrack: left -> right LK, disparity / depth test (the RANSAC in between is host code)."""
+    from dynosam_b200.frontend import FeatureTrackerGPU
+    from oracle import frontend_oracle as FO
+    rng = np.random.default_rng(17)
+    left, _, _ = SyntheticStream(n_objects=6, seed=3).frame(5)
+    right = np.empty_like(left)                                     # a fronto-parallel scene: constant disparity of 9 px, except for
+    right[:, :-9] = left[:, 9:]; right[:, -9:] = left[:, -9:]        # the bottom 70 rows, which are infinitely far away (zero disparity)
+    right[H - 70:] = left[H - 70:]
+    n = 600
+    pts = np.stack([rng.uniform(15, W - 15, n), rng.uniform(15, H - 15, n)], 1).astype(np.float32)
+    t = FeatureTrackerGPU(W, H)
+    rp, st, depth, valid = t.stereo_track(left, right, pts, 721.5377, 0.5372)
+    orp, ost, odepth, ovalid = FO.stereo_track(left, right, pts, 721.5377, 0.5372)
+    agree = st == ost
+    assert agree.mean() >= 0.99, agree.mean()
+    both = (st == 1) & (ost == 1)
+    assert np.percentile(np.abs(rp[both] - orp[both]).max(axis=1), 99) < 1e-2
+    # the disparity test is a threshold on uL - uR: identical wherever the disparities are not within 1e-2 px of it
+    clear = both & (np.abs((pts[:, 0] - orp[:, 0]) - 1.0) > 2e-2) & (np.abs(orp[:, 0]) > 2e-2)
+    assert np.array_equal(valid[clear], ovalid[clear]) and valid[clear].sum() > 300 and (valid[clear] == 0).sum() > 0
+    ok = clear & (valid == 1)
+    assert np.abs(depth[ok] - odepth[ok]).max() <= 2e-3*np.abs(odepth[ok]).max()
+    assert abs(np.median(depth[ok]) - 721.5377*0.5372/9.0) < 0.05
