@@ -706,7 +706,12 @@ static int group_process(const orc_problem* P, const schur_ws* W, int g, double 
   }
   /* mode 0: Wh = W L^-T  (6*ngp x nvl), S_local = sum A^T A - Wh Wh^T, g_local = sum A^T b - Wh y */
   int np6 = 6*ngp;
-  double* Wm = calloc((size_t)np6*nvl + (size_t)np6*np6 + np6 + 1, sizeof(double));
+  /* per-thread scratch, grown on demand and zeroed per group (a calloc/free pair of several hundred KB per landmark goes
+   * through mmap/munmap and dominated the elimination) */
+  static __thread double* tl_buf = NULL; static __thread size_t tl_cap = 0;
+  const size_t need = (size_t)np6*nvl + (size_t)np6*np6 + np6 + 1;
+  if (need > tl_cap) { free(tl_buf); tl_cap = need + need/2; tl_buf = (double*)malloc(tl_cap*sizeof(double)); if (!tl_buf) { tl_cap = 0; return 2; } }
+  double* Wm = tl_buf; memset(Wm, 0, need*sizeof(double));
   double* Sl = Wm + (size_t)np6*nvl; double* gloc = Sl + (size_t)np6*np6;
   for (int q = 0; q < nf; q++) {
     fref f = W->g_fac[W->g_fptr[g]+q]; const orc_block* b = &P->blocks[f.blk];
@@ -744,7 +749,6 @@ static int group_process(const orc_problem* P, const schur_ws* W, int g, double 
         int li = 6*a + r, lj = 6*c + e; double v = li >= lj ? Sl[(size_t)li*np6+lj] : Sl[(size_t)lj*np6+li];
         band_add(AB, W->ld, gi, gj, v);
       } } }
-  free(Wm);
   return 0;
 }
 
