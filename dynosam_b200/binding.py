@@ -27,7 +27,7 @@ EXPORTS = [
     "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_set_reduce", "dynoba_set_partition", "dynoba_plan_partition", "dynoba_set_tuning", "dynoba_fp64_rate", "dynoba_add_linear_prior", "dynoba_marginal", "dynoba_finalize", "dynoba_error",
     "dynoba_optimize", "dynoba_get_variables", "dynoba_get_keys", "dynoba_num_variables", "dynoba_problem_info",
     "dynoba_linearize", "dynoba_linearize_block", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
-    "dynoba_get_reduced_system", "dynoba_retract",
+    "dynoba_get_reduced_system", "dynoba_retract", "dynoba_flow_pose_batch",
 ]
 
 
@@ -99,6 +99,8 @@ def load():
         L.dynoba_solve.argtypes = [C.c_void_p, C.c_double, c_dp]
         L.dynoba_get_reduced_system.argtypes = [C.c_void_p, C.c_double, c_dp, c_dp]
         L.dynoba_retract.argtypes = [C.c_void_p, c_dp]
+        L.dynoba_flow_pose_batch.argtypes = [C.c_int, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_double, C.c_double,
+                                             C.POINTER(LmParams), c_dp, c_dp, c_dp, c_dp, c_ip, c_ip]
         _LIB = L
     return _LIB
 
@@ -308,3 +310,26 @@ class Solver:
         if p.n_flow:
             self._ck(self.lib.dynoba_get_variables(self.h, FLOW2, p.n_flow, _dp(flow)))
         return pose, point, flow
+
+
+def flow_pose_batch(problems, flow_sigma, flow_prior_sigma, huber_k, device: int = 0, params: LmParams | None = None, **kw):
+    """All joint optical-flow + pose refinements of a frame in ONE launch (dynoba_flow_pose_batch; the reference runs
+    OpticalFlowAndPoseOptimizer::optimize per object, MotionSolver-inl.hpp:88-260).  problems: dicts with pose_init[12],
+    pose_prev[12], calib[5], kp_prev[n,2], depth[n], flow[n,2].  Returns one dict per problem."""
+    L = load()
+    npb = len(problems)
+    cnt = [len(np.asarray(q["depth"]).reshape(-1)) for q in problems]
+    off = np.zeros(npb + 1, dtype=np.int32); off[1:] = np.cumsum(cnt)
+    cat = lambda k, w: np.ascontiguousarray(np.concatenate([np.asarray(q[k], dtype=np.float64).reshape(-1, w) for q in problems], 0)) if npb else np.zeros((0, w))
+    pose0, prev, cal = cat("pose_init", 12), cat("pose_prev", 12), cat("calib", 5)
+    kp, depth, flow = cat("kp_prev", 2), cat("depth", 1), cat("flow", 2)
+    total = int(off[-1])
+    pose_out = np.zeros((npb, 12)); flow_out = np.zeros((max(total, 1), 2)); e0 = np.zeros(npb); e1 = np.zeros(npb)
+    it = np.zeros(npb, dtype=np.int32); inner = np.zeros(npb, dtype=np.int32)
+    prm = params if params is not None else default_params(**kw)
+    rc = L.dynoba_flow_pose_batch(device, npb, _ip(off), _dp(pose0), _dp(prev), _dp(cal), _dp(kp), _dp(depth), _dp(flow), float(flow_sigma),
+                                  float(flow_prior_sigma), float(huber_k), C.byref(prm), _dp(pose_out), _dp(flow_out), _dp(e0), _dp(e1), _ip(it), _ip(inner))
+    if rc != 0:
+        raise DynobaError(rc, L.dynoba_status_string(rc).decode())
+    return [dict(pose=pose_out[i].copy(), flow=flow_out[off[i]:off[i + 1]].copy(), error_initial=float(e0[i]), error_final=float(e1[i]),
+                 iterations=int(it[i]), inner_iterations=int(inner[i])) for i in range(npb)]

@@ -220,6 +220,26 @@ int dynoba_builder_block_info(dynoba_builder_handle b, int32_t block, int32_t* t
 int dynoba_builder_get_block(dynoba_builder_handle b, int32_t block, int32_t* idx, double* meas, double* sigma, int32_t* aux_idx);
 int dynoba_builder_emit(dynoba_builder_handle b, dynoba_handle h);
 
+/* ---- batched star problems --------------------------------------------------------------------------
+ * Replaces, for ALL objects of a frame (or many frames) at once, the per-object
+ * OpticalFlowAndPoseOptimizer::optimize / MotionOnlyRefinementOptimizer loop of the front end
+ * (dynosam/include/dynosam/frontend/vision/MotionSolver-inl.hpp:88-260): problem p has one Pose3 unknown and one Point2
+ * flow unknown per feature i in [offsets[p], offsets[p+1]); every feature contributes
+ *   Pose3FlowProjectionFactor(flow_i, pose; kp_prev_i, depth_i, pose_prev_p, K_p)   noise Robust(Huber(huber_k), Isotropic(flow_sigma))
+ *   PriorFactor<Point2>(flow_i, flow_i^0)                                            noise Isotropic(flow_prior_sigma)
+ * and each problem runs its own Levenberg-Marquardt (GTSAM tryLambda semantics, prm as for dynoba_optimize; NULL =
+ * defaults; the reference uses max_iterations 10) -- one CTA per problem, the whole loop on the device, one launch.
+ * Poses are 12 doubles (row-major R, then t), calib5 = fx fy s u0 v0.  flow holds the measured flows: initial value
+ * and prior mean.  huber_k <= 0: Gaussian.  All pointers are HOST memory; outputs: refined pose[12] per problem,
+ * refined flow per feature, total error before/after, LM iterations and inner (lambda) iterations per problem.
+ * The reference's outlier rounds (determineFactorOutliers + re-run on the inliers) stay with the caller: call again
+ * with the inlier subset. */
+int dynoba_flow_pose_batch(int device, int32_t n_problems, const int32_t* offsets, const double* pose_init,
+                           const double* pose_prev, const double* calib5, const double* kp_prev, const double* depth,
+                           const double* flow, double flow_sigma, double flow_prior_sigma, double huber_k,
+                           const dynoba_lm_params* prm, double* pose_out, double* flow_out, double* err_before,
+                           double* err_after, int32_t* iterations, int32_t* inner_iterations);
+
 #ifdef __cplusplus
 }
 #endif
