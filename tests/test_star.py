@@ -80,6 +80,7 @@ def test_star_batch_matches_oracle(sig):
         if o["error_final"] < 1e-12*o["error_initial"]:
             # exact fit (<= 3 features: 4N residuals, 6 + 2N unknowns): the last steps act on rounding noise; same minimum, no step-by-step claim
             assert r["error_final"] < 1e-10*o["error_initial"] and r["iterations"] >= 1
+            moved += 1
             continue
         assert (r["iterations"], r["inner_iterations"]) == (o["iterations"], o["inner_iterations"]), (len(q["depth"]), r, o)
         assert abs(r["error_final"] - o["error_final"]) <= 1e-9*max(o["error_final"], 1e-12) + 1e-12
@@ -97,6 +98,8 @@ def test_star_batch_empty_and_large():
     probs = [make_problem(rng, 0)] + [make_problem(rng, int(n)) for n in rng.integers(30, 300, 400)]
     out = binding.flow_pose_batch(probs, 1.0, 0.5, 1.0, max_iterations=10)
     assert out[0]["iterations"] == 0 and np.array_equal(out[0]["pose"], np.asarray(probs[0]["pose_init"]))
+    closer = 0
     for q, r in zip(probs[1:], out[1:]):
         assert r["error_final"] < r["error_initial"] and r["iterations"] >= 1
-        assert np.abs(r["pose"][9:] - q["gt"][9:]).max() < np.abs(np.asarray(q["pose_init"])[9:] - q["gt"][9:]).max() + 1e-3
+        closer += np.abs(r["pose"][9:] - q["gt"][9:]).max() < np.abs(np.asarray(q["pose_init"])[9:] - q["gt"][9:]).max()
+    assert closer >= 0.9*(len(probs) - 1)
