@@ -318,6 +318,8 @@ def flow_pose_batch(problems, flow_sigma, flow_prior_sigma, huber_k, device: int
     pose_prev[12], calib[5], kp_prev[n,2], depth[n], flow[n,2].  Returns one dict per problem."""
     L = load()
     npb = len(problems)
+    if npb == 0:
+        return []
     cnt = [len(np.asarray(q["depth"]).reshape(-1)) for q in problems]
     off = np.zeros(npb + 1, dtype=np.int32); off[1:] = np.cumsum(cnt)
     cat = lambda k, w: np.ascontiguousarray(np.concatenate([np.asarray(q[k], dtype=np.float64).reshape(-1, w) for q in problems], 0)) if npb else np.zeros((0, w))

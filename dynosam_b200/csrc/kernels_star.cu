@@ -206,9 +206,9 @@ extern "C" int dynoba_flow_pose_batch(int device, int32_t n_problems, const int3
                                       const double* calib5, const double* kp_prev, const double* depth, const double* flow, double flow_sigma,
                                       double flow_prior_sigma, double huber_k, const dynoba_lm_params* prm, double* pose_out, double* flow_out,
                                       double* err_before, double* err_after, int32_t* iterations, int32_t* inner_iterations) {
+  if (n_problems == 0) return DYNOBA_OK;
   if (n_problems < 0 || !offsets || !pose_init || !pose_prev || !calib5 || !pose_out || !err_before || !err_after || !iterations || !inner_iterations ||
       !(flow_sigma > 0) || !(flow_prior_sigma > 0)) return DYNOBA_ERR_BAD_ARG;
-  if (n_problems == 0) return DYNOBA_OK;
   const int total = offsets[n_problems];
   if (total < 0 || (total > 0 && (!kp_prev || !depth || !flow || !flow_out))) return DYNOBA_ERR_BAD_ARG;
   for (int p = 0; p < n_problems; p++) if (offsets[p + 1] < offsets[p]) return DYNOBA_ERR_BAD_ARG;

@@ -2,7 +2,9 @@
 C ABI with host buffers (allocation, H2D, the single launch, D2H inside the timed region).  Prints one JSON line."""
 import json, sys, time
 import numpy as np
-sys.path.insert(0, "tests")
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_star import make_problem                                    # noqa: E402
 from dynosam_b200 import binding                                      # noqa: E402
 
