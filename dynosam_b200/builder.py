@@ -15,7 +15,10 @@ c_i64p = C.POINTER(C.c_int64)
 class BuilderParams(C.Structure):
     _fields_ = [("min_static_obs", C.c_int32), ("min_dynamic_obs", C.c_int32), ("keyframe_gap", C.c_int32),
                 ("sigma_static", C.c_double), ("sigma_dynamic", C.c_double), ("huber_k", C.c_double),
-                ("odometry_sigma", C.c_double*6), ("smoothing_sigma", C.c_double*6), ("prior_sigma", C.c_double)]
+                ("odometry_sigma", C.c_double*6), ("smoothing_sigma", C.c_double*6), ("prior_sigma", C.c_double),
+                ("formulation", C.c_int32), ("sigma_motion", C.c_double)]
+
+FORMULATIONS = {"hybrid": 0, "wcme": 1, "wcpe": 2}
 
 
 def _dp(a):
@@ -46,6 +49,8 @@ class GraphBuilder:
             if k in ("odometry_sigma", "smoothing_sigma"):
                 for i in range(6):
                     getattr(prm, k)[i] = float(v[i])
+            elif k == "formulation":
+                prm.formulation = FORMULATIONS[v] if isinstance(v, str) else int(v)
             else:
                 setattr(prm, k, v)
         self.h = C.c_void_p()

@@ -14,8 +14,17 @@
 //     initialised by HybridObjectMotion::projectToObject3 at its first observation; HybridMotionFactor(X_k, e_H_k, m_L; z, L_e);
 //     PriorFactor(H_e = I, 1e-6) at the key-frame (:744-746); three-motion HybridSmoothingFactor inside a segment (:800-802);
 //     L_e = centroid of the key-frame's points with identity rotation unless given (:867-875).
+//   * WCME (formulation 1; WorldMotionEstimator.cc:151-351): one point per (tracklet, frame) initialised X_k z, a PoseToPointFactor
+//     per observation, LandmarkMotionTernaryFactor(m_prev, m_k, H_k) between consecutive observations of a tracklet, a motion
+//     variable H_k per (object, frame that closes a pair) initialised with the front end's translation and IDENTITY rotation
+//     (:297-303), BetweenFactor(H_k-1, H_k, I) smoothing between consecutive frames (:309-349).
+//   * WCPE (formulation 2; WorldPoseEstimator.cc:89-315): the same points, LandmarkMotionPoseFactor(m_prev, m_k, L_prev, L_k), an
+//     object pose L_k per (object, frame) initialised motion * L_k-1 when the front end gave a motion and L_k-1 exists, else the
+//     centroid of the object's points at k with identity rotation (:205-232), LandmarkPoseSmoothingFactor over three consecutive
+//     frames (:259-306); no prior on the object poses.
 // Host code only (no kernel): it lives in libdynoba.so because its output is the library's input.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -64,6 +73,7 @@ void dynoba_builder_default_params(dynoba_builder_params* p) {
   const double od[6] = {0.02, 0.02, 0.02, 0.01, 0.01, 0.01}, sm[6] = {0.01, 0.01, 0.01, 0.1, 0.1, 0.1};
   for (int i = 0; i < 6; i++) { p->odometry_sigma[i] = od[i]; p->smoothing_sigma[i] = sm[i]; }
   p->prior_sigma = 1e-6;
+  p->formulation = DYNOBA_FORMULATION_HYBRID; p->sigma_motion = 0.01;         // motion_ternary_factor_noise_sigma
 }
 int dynoba_builder_create(const dynoba_builder_params* p, dynoba_builder_handle* out) {
   if (!out) return DYNOBA_ERR_BAD_ARG;
@@ -131,6 +141,69 @@ int dynoba_builder_finalize(dynoba_builder_handle b) {
     }
     if (blk.n()) b->blocks.push_back(std::move(blk));
   }
+  if (P.formulation != DYNOBA_FORMULATION_HYBRID) {
+    // ---- world-centric formulations: a point per (tracklet, observation), chained by motion factors
+    BARG(P.formulation == DYNOBA_FORMULATION_WCME || P.formulation == DYNOBA_FORMULATION_WCPE, "unknown formulation");
+    const bool wcpe = P.formulation == DYNOBA_FORMULATION_WCPE;
+    const int32_t n_cam = (int32_t)cam_index.size();
+    std::map<std::pair<int32_t, int64_t>, std::vector<size_t>> tracks; std::vector<std::pair<int32_t, int64_t>> first_seen;
+    for (size_t i = 0; i < b->dyn.size(); i++) { BARG(cam(b->dyn[i].frame) >= 0, "dynamic observation in an unknown frame");
+      auto key = std::make_pair(b->dyn[i].object, b->dyn[i].tracklet);
+      auto& t = tracks[key]; if (t.empty()) first_seen.push_back(key); t.push_back(i); }
+    std::stable_sort(first_seen.begin(), first_seen.end(), [](const std::pair<int32_t, int64_t>& a, const std::pair<int32_t, int64_t>& c) { return a.first < c.first; });
+    const int min_obs = std::max(P.min_dynamic_obs, 2);                 // a motion factor needs a pair
+    // (object, frame) -> pose-like variable: WCME the frame that closes a pair, WCPE every observed frame of a kept tracklet
+    std::map<std::pair<int32_t, int32_t>, int32_t> var_index;
+    std::map<std::pair<int32_t, int32_t>, std::pair<std::array<double, 3>, int>> centroid;     // world points of the kept tracklets
+    for (auto& key : first_seen) {
+      auto& t = tracks[key]; if ((int)t.size() < min_obs) continue;
+      for (size_t k = 0; k < t.size(); k++) { const Obs& o = b->dyn[t[k]];
+        if (k > 0) BARG(o.frame > b->dyn[t[k-1]].frame, "a tracklet is observed twice in one frame");
+        if (wcpe || k > 0) var_index[{o.object, o.frame}] = -1;
+        double w[3]; se3_transform_from(b->frames[o.frame].first, o.z, w);
+        auto& c = centroid[{o.object, o.frame}]; for (int a = 0; a < 3; a++) c.first[a] += w[a]; c.second++; }
+    }
+    for (auto& kv : var_index) {                                       // std::map order: object-major, frames ascending
+      const int32_t obj = kv.first.first, fr = kv.first.second;
+      kv.second = (int32_t)(b->pose.size()/12);
+      Pose V = identity_pose();
+      auto mi = b->motion_init.find({obj, fr});
+      if (!wcpe) { if (mi != b->motion_init.end()) for (int a = 0; a < 3; a++) V.t[a] = mi->second.t[a]; }
+      else {
+        auto given = b->keyframe_pose.find({obj, fr}); auto prev = var_index.find({obj, fr - 1});
+        if (given != b->keyframe_pose.end()) V = given->second;
+        else if (mi != b->motion_init.end() && prev != var_index.end() && prev->second >= 0) se3_compose(mi->second, pose_from(&b->pose[(size_t)12*prev->second]), V);
+        else { auto& c = centroid[{obj, fr}]; for (int a = 0; a < 3; a++) V.t[a] = c.first[a]/std::max(c.second, 1); }
+      }
+      double p[12]; pose_to(V, p); b->pose.insert(b->pose.end(), p, p + 12);
+      b->order.push_back(fr); b->pose_keys.push_back(labeled(wcpe ? 'L' : 'H', (uint64_t)('0' + obj), (uint64_t)fr));
+    }
+    Block ptp; ptp.type = DYNOBA_POSE2POINT3; ptp.sigma = { P.sigma_dynamic }; ptp.k = P.huber_k;
+    Block mot; mot.type = wcpe ? DYNOBA_MOTIONPOSE3 : DYNOBA_TERNARY3; mot.sigma = { P.sigma_motion }; mot.k = P.huber_k;
+    for (auto& key : first_seen) {
+      auto& t = tracks[key]; if ((int)t.size() < min_obs) continue;
+      for (size_t k = 0; k < t.size(); k++) { const Obs& o = b->dyn[t[k]];
+        const int32_t pi = (int32_t)(b->point.size()/3);
+        double w[3]; se3_transform_from(b->frames[o.frame].first, o.z, w);                 // X_k z (dynamicPointUpdateCallback)
+        b->point.insert(b->point.end(), w, w + 3); b->point_keys.push_back(sym('m', cantor((uint64_t)o.tracklet, (uint64_t)o.frame)));
+        ptp.idx.push_back(cam(o.frame)); ptp.idx.push_back(pi); ptp.meas.insert(ptp.meas.end(), o.z, o.z + 3);
+        if (k > 0) { mot.idx.push_back(pi - 1); mot.idx.push_back(pi);
+          if (wcpe) mot.idx.push_back(var_index[{o.object, b->dyn[t[k-1]].frame}]);
+          mot.idx.push_back(var_index[{o.object, o.frame}]); }
+      }
+    }
+    if (ptp.n()) b->blocks.push_back(std::move(ptp));
+    if (mot.n()) b->blocks.push_back(std::move(mot));
+    Block sm; sm.type = wcpe ? DYNOBA_SMOOTH_POSE6 : DYNOBA_BETWEEN6; sm.sigma.assign(P.smoothing_sigma, P.smoothing_sigma + 6); sm.sigma_dim = 6;
+    const Pose I = identity_pose(); double pi12[12]; pose_to(I, pi12);
+    for (auto& kv : var_index) {
+      const int32_t obj = kv.first.first, fr = kv.first.second;
+      auto p1 = var_index.find({obj, fr - 1}), p2 = var_index.find({obj, fr - 2});
+      if (!wcpe) { if (p1 != var_index.end()) { sm.idx.push_back(p1->second); sm.idx.push_back(kv.second); sm.meas.insert(sm.meas.end(), pi12, pi12 + 12); } }
+      else if (p1 != var_index.end() && p2 != var_index.end()) { sm.idx.push_back(p2->second); sm.idx.push_back(p1->second); sm.idx.push_back(kv.second); }
+    }
+    if (sm.n()) b->blocks.push_back(std::move(sm));
+  } else {
   // ---- dynamic: objects -> visibility segments (key-frames) -> motion variables
   const int32_t n_cam = (int32_t)cam_index.size();
   std::map<int32_t, std::vector<int32_t>> obj_frames;                  // object -> sorted frames it is observed in
@@ -197,6 +270,7 @@ int dynoba_builder_finalize(dynoba_builder_handle b) {
     }
     if (pr.n()) b->blocks.push_back(std::move(pr));
     if (sm.n()) b->blocks.push_back(std::move(sm));
+  }
   }
   // ---- camera chain
   {

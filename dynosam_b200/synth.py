@@ -96,6 +96,7 @@ def make_problem(n_frames=20, n_objects=1, n_static=700, n_dynamic=300, formulat
     pose_keys = [camera_pose_key(np.arange(N))]
     aux = np.zeros((0, 12))
     gt_motion = None
+    dyn_obs = None
     n_pt_static = ns
     if J:
         if object_span is None:
@@ -145,6 +146,7 @@ def make_problem(n_frames=20, n_objects=1, n_static=700, n_dynamic=300, formulat
         mW = lie.transform_from(E_k, lie.transform_from(L_e[tobj[tid]], mL[tid]))
         z = lie.transform_to(X_gt[fr], mW) + rng.normal(0, meas_noise, (tid.shape[0], 3))
         hidx = hstart[tobj[tid]] + (fr - s[tobj[tid]]) - skip                    # motion var of (object, frame)
+        dyn_obs = dict(frame=fr, tracklet=tid + ns, object=tobj[tid] + 1)        # per dynamic observation, in block order
         if formulation == "hybrid":
             # m_L init = L_e^-1 * E^-1 * X * z at the first observation (HybridObjectMotion::projectToObject3)
             f0 = start[:-1]
@@ -200,7 +202,7 @@ def make_problem(n_frames=20, n_objects=1, n_static=700, n_dynamic=300, formulat
                    pose_order=np.concatenate(order_hint).astype(np.int32),
                    pose_keys=np.concatenate(pose_keys), point_keys=np.concatenate(pt_keys))
     prob.meta = dict(n_frames=N, n_objects=J, n_static=ns, n_dynamic=nd, formulation=formulation, seed=seed,
-                     gt_camera=X_gt, gt_motion=gt_motion)
+                     gt_camera=X_gt, gt_motion=gt_motion, dyn_obs=dyn_obs)
     return prob
 
 

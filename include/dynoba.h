@@ -190,6 +190,11 @@ int dynoba_retract(dynoba_handle h, const double* delta);
  * allocating a factor object per observation: feed frames and observations, get the variable arrays and one homogeneous
  * block per factor type (read them back, or hand them to a solver handle with dynoba_builder_emit).  Host code only. */
 typedef struct dynoba_builder* dynoba_builder_handle;
+/* HYBRID: HybridEstimator.cc:573-830.  WCME: WorldMotionEstimator.cc:151-351 (point per (tracklet, frame), ternary motion factors,
+ * motion variables initialised with the front-end translation and identity rotation).  WCPE: WorldPoseEstimator.cc:89-315 (object
+ * POSE variables L_k, initialised motion * L_k-1 or centroid; dynoba_builder_set_keyframe_pose(object, frame, L) overrides the
+ * initial value of L at that frame). */
+enum { DYNOBA_FORMULATION_HYBRID = 0, DYNOBA_FORMULATION_WCME = 1, DYNOBA_FORMULATION_WCPE = 2 };
 typedef struct {
   int32_t min_static_obs, min_dynamic_obs;   /* min_static_observations (2), min_dynamic_observations (3) */
   int32_t keyframe_gap;                      /* new object key-frame once unseen for more than this many frames (2) */
@@ -197,6 +202,8 @@ typedef struct {
   double huber_k;                            /* 1e-4; <= 0: Gaussian */
   double odometry_sigma[6], smoothing_sigma[6];
   double prior_sigma;                        /* 1e-6 */
+  int32_t formulation;                       /* DYNOBA_FORMULATION_* (hybrid) */
+  double sigma_motion;                       /* motion_ternary_factor_noise_sigma (0.01): TERNARY3 / MOTIONPOSE3 of the world-centric formulations */
 } dynoba_builder_params;
 void dynoba_builder_default_params(dynoba_builder_params* p);
 int dynoba_builder_create(const dynoba_builder_params* p, dynoba_builder_handle* out);

@@ -103,3 +103,87 @@ def test_builder_emit_into_the_solver():
     assert a["iterations"] == r["iterations"] and a["inner_iterations"] == r["inner_iterations"]
     assert abs(a["error_final"] - r["error_final"]) <= 1e-9*r["error_final"]
     s.close(); ref.close(); b.close()
+
+
+def _feed_world_centric(p, b):
+    """replay a synthetic WCME / WCPE problem as per-frame observations (tracklet / object ids from the generator's table)"""
+    N = p.meta["n_frames"]; d = p.meta["dyn_obs"]
+    ptp = [x for x in p.blocks if x.type == POSE2POINT3]
+    odo = [x for x in p.blocks if x.type == BETWEEN6][-1]
+    rel = {int(i[1]): m for i, m in zip(odo.idx, odo.meas)}
+    for k in range(N):
+        b.add_frame(k, p.pose[k], rel.get(k))
+        sel = np.flatnonzero(ptp[0].idx[:, 0] == k)
+        sel = sel[np.argsort(ptp[0].idx[sel, 1], kind="stable")]
+        b.add_static(k, ptp[0].idx[sel, 1], ptp[0].meas[sel])
+        sel = np.flatnonzero(d["frame"] == k)
+        sel = sel[np.argsort(d["tracklet"][sel], kind="stable")]
+        b.add_dynamic(k, d["tracklet"][sel], d["object"][sel], ptp[1].meas[sel])
+
+
+@pytest.mark.parametrize("formulation", ["wcme", "wcpe"])
+@pytest.mark.parametrize("cfg", [dict(n_frames=20, n_objects=1, n_static=300, n_dynamic=300, seed=42),
+                                 dict(n_frames=40, n_objects=3, n_static=200, n_dynamic=600, seed=7, object_span=(12, 25))])
+def test_builder_world_centric_formulations(formulation, cfg):
+    """WCME (WorldMotionEstimator.cc:151-351) and WCPE (WorldPoseEstimator.cc:89-315) topology: point per (tracklet, frame),
+    motion factor chains, smoothing, keys -- block by block against the independent numpy generator; initial values of the
+    pose-like variables by the reference's own rules."""
+    from dynosam_b200.builder import GraphBuilder
+    from dynosam_b200.problem import MOTIONPOSE3, SMOOTH_POSE6, TERNARY3
+    from oracle import oracle as O
+    p = synth.make_problem(formulation=formulation, **cfg)
+    N = p.meta["n_frames"]
+    b = GraphBuilder(formulation=formulation)
+    if formulation == "wcme":
+        keys = p.pose_keys[N:]
+        for m in range(N, p.n_pose):                               # front-end motions k-1 -> k
+            b.set_motion_init(int((int(p.pose_keys[m]) >> 48) & 0xff) - ord('0'), int(p.pose_order[m]), p.pose[m])
+    _feed_world_centric(p, b)
+    q = b.problem()
+    assert q.n_pose == p.n_pose and q.n_point == p.n_point and q.aux_pose.shape[0] == 0
+    assert np.array_equal(q.pose_order, p.pose_order) and np.array_equal(q.pose_keys, p.pose_keys) and np.array_equal(q.point_keys, p.point_keys)
+    assert np.array_equal(q.pose[:N], p.pose[:N])
+    assert np.abs(q.point - p.point).max() <= 1e-12*max(np.abs(p.point).max(), 1.0)       # X_k z
+    want = [POSE2POINT3, POSE2POINT3, TERNARY3, BETWEEN6, PRIOR6, BETWEEN6] if formulation == "wcme" else \
+           [POSE2POINT3, POSE2POINT3, MOTIONPOSE3, SMOOTH_POSE6, PRIOR6, BETWEEN6]
+    assert [x.type for x in q.blocks] == [x.type for x in p.blocks] == want
+    for x, y in zip(q.blocks, p.blocks):
+        assert np.array_equal(x.idx, y.idx), x.type
+        assert (x.meas is None and y.meas is None) or np.array_equal(x.meas, y.meas), x.type
+        assert np.array_equal(np.ravel(x.sigma), np.ravel(y.sigma)) and x.robust_k == y.robust_k, x.type
+    if formulation == "wcme":
+        # WorldMotionEstimator.cc:297-303: the front end's translation, identity rotation
+        assert np.array_equal(q.pose[N:, 9:], p.pose[N:, 9:]) and np.array_equal(q.pose[N:, :9], np.tile(np.eye(3).ravel(), (p.n_pose - N, 1)))
+    else:
+        # WorldPoseEstimator.cc:205-232 without front-end motions: centroid of the object's points at that frame, identity rotation
+        d = p.meta["dyn_obs"]; npt_s = p.meta["n_static"]
+        for m in range(N, p.n_pose):
+            obj = int((int(p.pose_keys[m]) >> 48) & 0xff) - ord('0'); fr = int(p.pose_order[m])
+            sel = np.flatnonzero((d["object"] == obj) & (d["frame"] == fr))
+            assert np.allclose(q.pose[m, 9:], q.point[npt_s + sel].mean(0), rtol=0, atol=1e-12) and np.array_equal(q.pose[m, :9], np.eye(3).ravel())
+    q.pose[N:] = p.pose[N:]                                          # same initial values -> same graph error
+    q.calib = p.calib
+    assert abs(O.OracleProblem(q).error() - O.OracleProblem(p).error()) <= 1e-12*O.OracleProblem(p).error()
+    b.close()
+
+
+def test_builder_wcpe_pose_propagation():
+    """WCPE initial object poses: L_k = motion(k-1 -> k) * L_k-1 when the front end gave a motion and L_k-1 exists
+    (WorldPoseEstimator.cc:205-215), a given pose overrides, else the centroid."""
+    from dynosam_b200.builder import GraphBuilder
+    I = lie.identity()[0]
+    b = GraphBuilder(formulation="wcpe")
+    for k in range(4):
+        b.add_frame(k, I, None if k == 0 else I)
+        b.add_dynamic(k, [1, 2], [1, 1], [[1.0 + k, 0.0, 5.0], [3.0 + k, 0.0, 5.0]])
+    H = lie.se3_exp(np.array([[0.0, 0.1, 0.0, 1.0, 0.0, 0.0]]))[0]
+    L1 = lie.se3_exp(np.array([[0.0, 0.2, 0.0, 3.0, 0.0, 5.0]]))[0]
+    b.set_keyframe_pose(1, 1, L1); b.set_motion_init(1, 2, H)
+    q = b.problem()
+    assert q.n_pose == 4 + 4 and q.n_point == 8
+    assert np.allclose(q.pose[4][9:], [2.0, 0.0, 5.0])                       # frame 0: centroid
+    assert np.array_equal(q.pose[5], L1)                                     # frame 1: given
+    assert np.allclose(q.pose[6], lie.compose(H[None], L1[None])[0], atol=1e-15)     # frame 2: propagated
+    assert np.allclose(q.pose[7][9:], [5.0, 0.0, 5.0])                       # frame 3: no motion -> centroid
+    assert q.blocks[1].n == 6 and q.blocks[2].n == 2                         # 6 pose-motion factors, 2 smoothing triples
+    b.close()
