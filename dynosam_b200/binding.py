@@ -27,7 +27,8 @@ EXPORTS = [
     "dynoba_add_factors", "dynoba_set_pose_order", "dynoba_set_shard", "dynoba_set_reduce", "dynoba_set_partition", "dynoba_plan_partition", "dynoba_set_tuning", "dynoba_fp64_rate", "dynoba_add_linear_prior", "dynoba_marginal", "dynoba_finalize", "dynoba_error",
     "dynoba_optimize", "dynoba_get_variables", "dynoba_get_keys", "dynoba_num_variables", "dynoba_problem_info",
     "dynoba_linearize", "dynoba_linearize_block", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
-    "dynoba_get_reduced_system", "dynoba_retract", "dynoba_flow_pose_batch",
+    "dynoba_get_reduced_system", "dynoba_retract", "dynoba_flow_pose_default_params", "dynoba_flow_pose_batch",
+    "dynoba_motion_refine_default_params", "dynoba_motion_refine_batch",
 ]
 
 
@@ -47,6 +48,16 @@ class LmStats(C.Structure):
 
     def as_dict(self):
         return {f[0]: getattr(self, f[0]) for f in self._fields_}
+
+
+class FlowPoseParams(C.Structure):
+    _fields_ = [("flow_sigma", C.c_double), ("flow_prior_sigma", C.c_double), ("huber_k", C.c_double), ("outlier_rounds", C.c_int32),
+                ("outlier_threshold", C.c_double), ("lm", LmParams)]
+
+
+class MotionRefineParams(C.Structure):
+    _fields_ = [("landmark_motion_sigma", C.c_double), ("projection_sigma", C.c_double), ("huber_k", C.c_double),
+                ("pose_prior_sigma", C.c_double), ("lm", LmParams)]
 
 
 class DynobaError(RuntimeError):
@@ -99,8 +110,13 @@ def load():
         L.dynoba_solve.argtypes = [C.c_void_p, C.c_double, c_dp]
         L.dynoba_get_reduced_system.argtypes = [C.c_void_p, C.c_double, c_dp, c_dp]
         L.dynoba_retract.argtypes = [C.c_void_p, c_dp]
-        L.dynoba_flow_pose_batch.argtypes = [C.c_int, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_double, C.c_double,
-                                             C.POINTER(LmParams), c_dp, c_dp, c_dp, c_dp, c_ip, c_ip]
+        c_u8p = C.POINTER(C.c_uint8)
+        L.dynoba_flow_pose_default_params.argtypes = [C.POINTER(FlowPoseParams)]
+        L.dynoba_flow_pose_batch.argtypes = [C.c_int, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.POINTER(FlowPoseParams),
+                                             c_dp, c_dp, c_u8p, c_dp, c_dp, c_ip, c_ip, c_ip]
+        L.dynoba_motion_refine_default_params.argtypes = [C.POINTER(MotionRefineParams)]
+        L.dynoba_motion_refine_batch.argtypes = [C.c_int, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.POINTER(MotionRefineParams),
+                                                 c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, c_ip]
         _LIB = L
     return _LIB
 
@@ -312,26 +328,67 @@ class Solver:
         return pose, point, flow
 
 
-def flow_pose_batch(problems, flow_sigma, flow_prior_sigma, huber_k, device: int = 0, params: LmParams | None = None, **kw):
+def _cat(problems, key, width):
+    return np.ascontiguousarray(np.concatenate([np.asarray(q[key], dtype=np.float64).reshape(-1, width) for q in problems], 0))
+
+
+def _set_params(prm, kw):
+    for k, v in kw.items():
+        if hasattr(prm, k):
+            setattr(prm, k, v)
+        elif hasattr(prm.lm, k):
+            setattr(prm.lm, k, v)
+        else:
+            raise TypeError(f"unknown parameter {k}")
+
+
+def flow_pose_batch(problems, device: int = 0, **kw):
     """All joint optical-flow + pose refinements of a frame in ONE launch (dynoba_flow_pose_batch; the reference runs
-    OpticalFlowAndPoseOptimizer::optimize per object, MotionSolver-inl.hpp:88-260).  problems: dicts with pose_init[12],
-    pose_prev[12], calib[5], kp_prev[n,2], depth[n], flow[n,2].  Returns one dict per problem."""
+    OpticalFlowAndPoseOptimizer::optimize per object, MotionSolver-inl.hpp:88-278).  problems: dicts with pose_init[12],
+    pose_prev[12], calib[5], kp_prev[n,2], depth[n], flow[n,2].  Keyword arguments set dynoba_flow_pose_params / its lm
+    member (flow_sigma, flow_prior_sigma, huber_k, outlier_rounds, outlier_threshold, max_iterations, ...).
+    Returns one dict per problem."""
     L = load()
     npb = len(problems)
     if npb == 0:
         return []
     cnt = [len(np.asarray(q["depth"]).reshape(-1)) for q in problems]
     off = np.zeros(npb + 1, dtype=np.int32); off[1:] = np.cumsum(cnt)
-    cat = lambda k, w: np.ascontiguousarray(np.concatenate([np.asarray(q[k], dtype=np.float64).reshape(-1, w) for q in problems], 0)) if npb else np.zeros((0, w))
-    pose0, prev, cal = cat("pose_init", 12), cat("pose_prev", 12), cat("calib", 5)
-    kp, depth, flow = cat("kp_prev", 2), cat("depth", 1), cat("flow", 2)
+    pose0, prev, cal = _cat(problems, "pose_init", 12), _cat(problems, "pose_prev", 12), _cat(problems, "calib", 5)
+    kp, depth, flow = _cat(problems, "kp_prev", 2), _cat(problems, "depth", 1), _cat(problems, "flow", 2)
     total = int(off[-1])
-    pose_out = np.zeros((npb, 12)); flow_out = np.zeros((max(total, 1), 2)); e0 = np.zeros(npb); e1 = np.zeros(npb)
-    it = np.zeros(npb, dtype=np.int32); inner = np.zeros(npb, dtype=np.int32)
-    prm = params if params is not None else default_params(**kw)
-    rc = L.dynoba_flow_pose_batch(device, npb, _ip(off), _dp(pose0), _dp(prev), _dp(cal), _dp(kp), _dp(depth), _dp(flow), float(flow_sigma),
-                                  float(flow_prior_sigma), float(huber_k), C.byref(prm), _dp(pose_out), _dp(flow_out), _dp(e0), _dp(e1), _ip(it), _ip(inner))
+    pose_out = np.zeros((npb, 12)); flow_out = np.zeros((max(total, 1), 2)); inl = np.zeros(max(total, 1), dtype=np.uint8)
+    e0 = np.zeros(npb); e1 = np.zeros(npb)
+    it = np.zeros(npb, dtype=np.int32); inner = np.zeros(npb, dtype=np.int32); rounds = np.zeros(npb, dtype=np.int32)
+    prm = FlowPoseParams(); L.dynoba_flow_pose_default_params(C.byref(prm)); _set_params(prm, kw)
+    rc = L.dynoba_flow_pose_batch(device, npb, _ip(off), _dp(pose0), _dp(prev), _dp(cal), _dp(kp), _dp(depth), _dp(flow), C.byref(prm),
+                                  _dp(pose_out), _dp(flow_out), inl.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(e0), _dp(e1), _ip(it), _ip(inner), _ip(rounds))
     if rc != 0:
         raise DynobaError(rc, L.dynoba_status_string(rc).decode())
-    return [dict(pose=pose_out[i].copy(), flow=flow_out[off[i]:off[i + 1]].copy(), error_initial=float(e0[i]), error_final=float(e1[i]),
-                 iterations=int(it[i]), inner_iterations=int(inner[i])) for i in range(npb)]
+    return [dict(pose=pose_out[i].copy(), flow=flow_out[off[i]:off[i + 1]].copy(), inlier=inl[off[i]:off[i + 1]].astype(bool),
+                 error_initial=float(e0[i]), error_final=float(e1[i]), iterations=int(it[i]), inner_iterations=int(inner[i]), rounds=int(rounds[i]))
+            for i in range(npb)]
+
+
+def motion_refine_batch(problems, device: int = 0, **kw):
+    """All object-motion refinements of a frame in ONE launch (dynoba_motion_refine_batch; the reference runs
+    MotionOnlyRefinementOptimizer::optimize per object, MotionSolver-inl.hpp:291-470).  problems: dicts with pose_prev[12],
+    pose_cur[12], motion_init[12], calib[5], kp_prev[n,2], kp_cur[n,2], points_init[n,6] (m_k-1 | m_k, world frame)."""
+    L = load()
+    npb = len(problems)
+    if npb == 0:
+        return []
+    cnt = [np.asarray(q["kp_prev"]).reshape(-1, 2).shape[0] for q in problems]
+    off = np.zeros(npb + 1, dtype=np.int32); off[1:] = np.cumsum(cnt)
+    pa, pb, h, cal = _cat(problems, "pose_prev", 12), _cat(problems, "pose_cur", 12), _cat(problems, "motion_init", 12), _cat(problems, "calib", 5)
+    ka, kb, pts = _cat(problems, "kp_prev", 2), _cat(problems, "kp_cur", 2), _cat(problems, "points_init", 6)
+    total = int(off[-1])
+    mo = np.zeros((npb, 12)); po = np.zeros((npb, 24)); pto = np.zeros((max(total, 1), 6)); me = np.zeros(max(total, 1)); e0 = np.zeros(npb); e1 = np.zeros(npb)
+    it = np.zeros(npb, dtype=np.int32); inner = np.zeros(npb, dtype=np.int32)
+    prm = MotionRefineParams(); L.dynoba_motion_refine_default_params(C.byref(prm)); _set_params(prm, kw)
+    rc = L.dynoba_motion_refine_batch(device, npb, _ip(off), _dp(pa), _dp(pb), _dp(h), _dp(cal), _dp(ka), _dp(kb), _dp(pts), C.byref(prm),
+                                      _dp(mo), _dp(po), _dp(pto), _dp(me), _dp(e0), _dp(e1), _ip(it), _ip(inner))
+    if rc != 0:
+        raise DynobaError(rc, L.dynoba_status_string(rc).decode())
+    return [dict(motion=mo[i].copy(), poses=po[i].reshape(2, 12).copy(), points=pto[off[i]:off[i + 1]].copy(), motion_factor_error=me[off[i]:off[i + 1]].copy(),
+                 error_initial=float(e0[i]), error_final=float(e1[i]), iterations=int(it[i]), inner_iterations=int(inner[i])) for i in range(npb)]

@@ -228,24 +228,54 @@ int dynoba_builder_get_block(dynoba_builder_handle b, int32_t block, int32_t* id
 int dynoba_builder_emit(dynoba_builder_handle b, dynoba_handle h);
 
 /* ---- batched star problems --------------------------------------------------------------------------
- * Replaces, for ALL objects of a frame (or many frames) at once, the per-object
- * OpticalFlowAndPoseOptimizer::optimize / MotionOnlyRefinementOptimizer loop of the front end
- * (dynosam/include/dynosam/frontend/vision/MotionSolver-inl.hpp:88-260): problem p has one Pose3 unknown and one Point2
- * flow unknown per feature i in [offsets[p], offsets[p+1]); every feature contributes
+ * The front end's per-object refinements, for ALL objects of a frame (or of many frames) in ONE launch: one CTA per problem
+ * runs the whole Levenberg-Marquardt (GTSAM tryLambda semantics, as dynoba_optimize) and the outlier rounds on the device.
+ * All pointers are HOST memory; poses are 12 doubles (row-major R, then t); calib5 = fx fy s u0 v0 (gtsam::Cal3_S2).
+ * Problem p owns the features / tracklets [offsets[p], offsets[p+1]) of the concatenated per-feature arrays; offsets[0] = 0.
+ *
+ * (1) dynoba_flow_pose_batch replaces the loop over OpticalFlowAndPoseOptimizer::optimize
+ * (dynosam/include/dynosam/frontend/vision/MotionSolver-inl.hpp:88-278): one Pose3 unknown and one Point2 flow unknown per
+ * feature; every feature contributes
  *   Pose3FlowProjectionFactor(flow_i, pose; kp_prev_i, depth_i, pose_prev_p, K_p)   noise Robust(Huber(huber_k), Isotropic(flow_sigma))
  *   PriorFactor<Point2>(flow_i, flow_i^0)                                            noise Isotropic(flow_prior_sigma)
- * and each problem runs its own Levenberg-Marquardt (GTSAM tryLambda semantics, prm as for dynoba_optimize; NULL =
- * defaults; the reference uses max_iterations 10) -- one CTA per problem, the whole loop on the device, one launch.
- * Poses are 12 doubles (row-major R, then t), calib5 = fx fy s u0 v0.  flow holds the measured flows: initial value
- * and prior mean.  huber_k <= 0: Gaussian.  All pointers are HOST memory; outputs: refined pose[12] per problem,
- * refined flow per feature, total error before/after, LM iterations and inner (lambda) iterations per problem.
- * The reference's outlier rounds (determineFactorOutliers + re-run on the inliers) stay with the caller: call again
- * with the inlier subset. */
+ * `flow` holds the measured flows: initial value and prior mean.  After the first LM, up to outlier_rounds times: the flow
+ * factors whose Gaussian error exceeds outlier_threshold leave the graph (their prior stays), the pose is reset to pose_init,
+ * LM runs again (:201-247).  Outputs: refined pose per problem, refined flow per feature, inlier_out[i] = 1 if the feature's
+ * factor is still in the graph, error of the full graph at the initial values, error of the final graph at the result, LM
+ * iterations / inner (lambda) iterations summed over the rounds, number of outlier rounds run. */
+typedef struct {
+  double flow_sigma, flow_prior_sigma, huber_k;   /* OpticalFlowAndPoseOptimizer::Params: 10, 3.33, 0.001; huber_k <= 0: Gaussian */
+  int32_t outlier_rounds;                         /* 4 (params.outlier_reject); 0 = no outlier rejection */
+  double outlier_threshold;                       /* <= 0: 0.5 * chi2inv(0.99, 2) (factor_graph_tools::determineFactorOutliers) */
+  dynoba_lm_params lm;                            /* GTSAM defaults with max_iterations 10 */
+} dynoba_flow_pose_params;
+void dynoba_flow_pose_default_params(dynoba_flow_pose_params* p);
 int dynoba_flow_pose_batch(int device, int32_t n_problems, const int32_t* offsets, const double* pose_init,
                            const double* pose_prev, const double* calib5, const double* kp_prev, const double* depth,
-                           const double* flow, double flow_sigma, double flow_prior_sigma, double huber_k,
-                           const dynoba_lm_params* prm, double* pose_out, double* flow_out, double* err_before,
-                           double* err_after, int32_t* iterations, int32_t* inner_iterations);
+                           const double* flow, const dynoba_flow_pose_params* prm, double* pose_out, double* flow_out,
+                           uint8_t* inlier_out, double* err_before, double* err_after, int32_t* iterations,
+                           int32_t* inner_iterations, int32_t* rounds);
+/* (2) dynoba_motion_refine_batch replaces the loop over MotionOnlyRefinementOptimizer::optimize (:291-470, ProjectionError
+ * solver): unknowns are the two camera poses X_k-1, X_k (PriorFactor, Isotropic pose_prior_sigma), the object motion H and two
+ * world points per tracklet (points_init[i] = m_k-1 | m_k, 6 doubles); every tracklet contributes
+ *   GenericProjectionFactor(X_k-1, m_k-1; kp_prev_i, K)  and  (X_k, m_k; kp_cur_i, K)   Robust(Huber(huber_k), Isotropic(projection_sigma))
+ *   LandmarkMotionTernaryFactor(m_k-1, m_k, H)                                           Robust(Huber(huber_k), Isotropic(landmark_motion_sigma))
+ * One LM per problem (max_iterations 5).  motion_factor_error[i] is the Gaussian error of tracklet i's motion factor at the
+ * result -- the quantity determineFactorOutliers<LandmarkMotionTernaryFactor> thresholds at 0.5 * chi2inv(0.99, 3); the
+ * reference's re-optimisation after removing those factors re-inserts an existing key into gtsam::Values (:441) and is not
+ * reproduced: call again with the inliers.  poses_out (24 per problem), points_out, motion_factor_error may be NULL. */
+typedef struct {
+  double landmark_motion_sigma, projection_sigma, huber_k;   /* MotionOnlyRefinementOptimizer::Params: 0.001, 2.0, 0.0001 */
+  double pose_prior_sigma;                                   /* 0.00001 */
+  dynoba_lm_params lm;                                       /* GTSAM defaults with max_iterations 5 */
+} dynoba_motion_refine_params;
+void dynoba_motion_refine_default_params(dynoba_motion_refine_params* p);
+int dynoba_motion_refine_batch(int device, int32_t n_problems, const int32_t* offsets, const double* pose_prev,
+                               const double* pose_cur, const double* motion_init, const double* calib5,
+                               const double* kp_prev, const double* kp_cur, const double* points_init,
+                               const dynoba_motion_refine_params* prm, double* motion_out, double* poses_out,
+                               double* points_out, double* motion_factor_error, double* err_before, double* err_after,
+                               int32_t* iterations, int32_t* inner_iterations);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 """batched star problems -- the front end's joint optical-flow + pose refinement
-(OpticalFlowAndPoseOptimizer::optimize, MotionSolver-inl.hpp:88-260), all objects of a frame in one launch."""
+(OpticalFlowAndPoseOptimizer::optimize, MotionSolver-inl.hpp:88-278) and object-motion refinement
+(MotionOnlyRefinementOptimizer::optimize, :291-470), all objects of a frame in one launch."""
 import numpy as np
 import pytest
 
@@ -7,6 +8,34 @@ from dynosam_b200 import binding, lie
 
 K5 = np.array([721.5377, 721.5377, 0.0, 609.5593, 172.854])
 FLOW_SIGMA, PRIOR_SIGMA, HUBER_K = 10.0, 3.33, 0.001          # FrontendParams-like magnitudes (flow in pixels)
+
+
+def _project(X, p):
+    q = lie.transform_to(np.tile(X, (len(p), 1)), p)
+    return np.stack([K5[0]*q[:, 0]/q[:, 2] + K5[3], K5[1]*q[:, 1]/q[:, 2] + K5[4]], 1), q[:, 2]
+
+
+def _back_project(X, kp, depth):
+    pc = np.stack([(kp[:, 0] - K5[3])/K5[0]*depth, (kp[:, 1] - K5[4])/K5[1]*depth, depth], 1)
+    return lie.transform_from(np.tile(X, (len(kp), 1)), pc)
+
+
+def make_motion_problem(rng, n, px_noise=0.3, depth_noise=0.05, outliers=0.0):
+    """two camera poses, a moving rigid object: key-points in both frames, back-projected (noisy depth) world points, a
+    perturbed initial motion"""
+    Xa = lie.se3_exp(rng.normal(0, 0.05, (1, 6)))[0]
+    Xb = lie.compose(Xa[None], lie.se3_exp(np.array([[0.002, -0.01, 0.001, 0.02, -0.01, 0.6]])))[0]
+    H = lie.se3_exp(np.array([[0.01, 0.03, -0.01, 0.3, 0.02, 0.5]]) + rng.normal(0, 0.01, (1, 6)))[0]
+    kp0 = np.stack([rng.uniform(400, 800, n), rng.uniform(100, 300, n)], 1); d0 = rng.uniform(8, 20, n)
+    ma = _back_project(Xa, kp0, d0)
+    mb = lie.transform_from(np.tile(H, (n, 1)), ma)
+    if outliers > 0:
+        bad = rng.random(n) < outliers; mb[bad] += rng.normal(0, 0.5, (int(bad.sum()), 3))
+    kpa, da = _project(Xa, ma); kpb, db = _project(Xb, mb)
+    kpa = kpa + rng.normal(0, px_noise, (n, 2)); kpb = kpb + rng.normal(0, px_noise, (n, 2))
+    ma0 = _back_project(Xa, kpa, da*(1 + rng.normal(0, depth_noise, n))); mb0 = _back_project(Xb, kpb, db*(1 + rng.normal(0, depth_noise, n)))
+    H0 = lie.compose(H[None], lie.se3_exp(rng.normal(0, 0.02, (1, 6))))[0]
+    return dict(pose_prev=Xa, pose_cur=Xb, motion_init=H0, calib=K5, kp_prev=kpa, kp_cur=kpb, points_init=np.concatenate([ma0, mb0], 1), gt=H)
 
 
 def make_problem(rng, n, noise=0.5, outliers=0.0, behind=0):
@@ -53,13 +82,66 @@ def test_star_batch_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     rng = np.random.default_rng(0)
     with pytest.raises(binding.DynobaError):
-        binding.flow_pose_batch([make_problem(rng, 10)], FLOW_SIGMA, PRIOR_SIGMA, HUBER_K)
+        binding.flow_pose_batch([make_problem(rng, 10)])
+    with pytest.raises(binding.DynobaError):
+        binding.motion_refine_batch([make_motion_problem(rng, 10)])
 
 
 def test_star_batch_bad_arguments():
     L = binding.load()
-    assert L.dynoba_flow_pose_batch(0, -1, None, None, None, None, None, None, None, 1.0, 1.0, 0.0, None, None, None, None, None, None, None) == -1
-    assert L.dynoba_flow_pose_batch(0, 1, None, None, None, None, None, None, None, 1.0, 1.0, 0.0, None, None, None, None, None, None, None) == -1
+    N = None
+    assert L.dynoba_flow_pose_batch(0, -1, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N) == -1
+    assert L.dynoba_flow_pose_batch(0, 1, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N) == -1
+    assert L.dynoba_flow_pose_batch(0, 0, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N) == 0          # nothing to do
+    assert L.dynoba_motion_refine_batch(0, -1, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N) == -1
+    assert L.dynoba_motion_refine_batch(0, 2, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N) == -1
+    assert L.dynoba_motion_refine_batch(0, 0, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N) == 0
+
+
+def test_projection_factor_restatement():
+    """gtsam::GenericProjectionFactor restated in oracle/star_oracle.py: analytic Jacobians against central differences on the
+    manifold (pose perturbed by retract, [omega, v]), skew included; behind the camera: (2 fx, 2 fx) and zero Jacobians."""
+    from oracle import star_oracle as SO
+    rng = np.random.default_rng(8)
+    K = np.array([700.0, 650.0, 1.5, 600.0, 180.0])
+    for _ in range(5):
+        X = lie.se3_exp(rng.normal(0, 0.3, (1, 6)))[0]
+        p = lie.transform_from(X[None], np.array([[rng.uniform(-3, 3), rng.uniform(-2, 2), rng.uniform(4, 20)]]))[0]
+        z = rng.uniform(0, 500, 2)
+        r, Jx, Jp = SO.projection_factor(X, p, K, z)
+        h = 1e-6
+        for c in range(6):
+            e = np.zeros((1, 6)); e[0, c] = h
+            rp = SO.projection_factor(lie.retract(X[None], e)[0], p, K, z)[0]; rm = SO.projection_factor(lie.retract(X[None], -e)[0], p, K, z)[0]
+            assert np.abs((rp - rm)/(2*h) - Jx[:, c]).max() < 1e-5*max(1.0, np.abs(Jx).max())
+        for c in range(3):
+            e = np.zeros(3); e[c] = h
+            assert np.abs((SO.projection_factor(X, p + e, K, z)[0] - SO.projection_factor(X, p - e, K, z)[0])/(2*h) - Jp[:, c]).max() < 1e-5*max(1.0, np.abs(Jp).max())
+    X = lie.identity()[0]
+    r, Jx, Jp = SO.projection_factor(X, np.array([0.0, 0.0, -1.0]), K, np.zeros(2))
+    assert np.array_equal(r, [1400.0, 1400.0]) and not Jx.any() and not Jp.any()
+
+
+def test_motion_refine_oracle_reduces_error():
+    from oracle import star_oracle as SO
+    rng = np.random.default_rng(4)
+    q = make_motion_problem(rng, 30, outliers=0.1)
+    r = SO.motion_refine_lm(q["pose_prev"], q["pose_cur"], q["motion_init"], K5, q["kp_prev"], q["kp_cur"], q["points_init"])
+    assert r["iterations"] >= 1 and r["error_final"] < 0.1*r["error_initial"]
+    assert np.abs(r["poses"] - np.stack([q["pose_prev"], q["pose_cur"]])).max() < 1e-6            # the 1e-5 priors hold the cameras
+    assert r["motion_factor_error"].shape == (30,)
+
+
+def test_flow_pose_oracle_outlier_rounds():
+    """the outlier rounds of the restatement: gross outliers leave the graph, the inlier fit gets close to the ground truth"""
+    from oracle import star_oracle as SO
+    rng = np.random.default_rng(6)
+    q = make_problem(rng, 150, noise=0.3, outliers=0.15)
+    a = SO.flow_pose_refine(q["pose_init"], q["pose_prev"], K5, q["kp_prev"], q["depth"], q["flow"], 1.0, 0.5, 1.0, outlier_rounds=0, max_iterations=10)
+    b = SO.flow_pose_refine(q["pose_init"], q["pose_prev"], K5, q["kp_prev"], q["depth"], q["flow"], 1.0, 0.5, 1.0, outlier_rounds=4, max_iterations=10)
+    assert a["rounds"] == 0 and a["inlier"].all()
+    assert 1 <= b["rounds"] <= 4 and 5 <= (~b["inlier"]).sum() <= 60
+    assert np.abs(b["pose"][9:] - q["gt"][9:]).max() <= np.abs(a["pose"][9:] - q["gt"][9:]).max() + 1e-3
 
 
 @pytest.mark.gpu
@@ -69,9 +151,9 @@ def test_star_batch_matches_oracle(sig):
     pose and flows (fp64; tolerance 1e-9 relative on chi^2, 1e-7 on the values)."""
     from oracle import star_oracle as SO
     rng = np.random.default_rng(11)
-    sizes = [1, 2, 3, 7, 33, 64, 100, 255, 256, 257, 300, 511, 700] + list(rng.integers(20, 400, 27))
+    sizes = [1, 2, 3, 7, 33, 64, 100, 255, 256, 257, 300, 511, 700] + list(rng.integers(20, 400, 12))
     probs = [make_problem(rng, int(n), noise=0.5, outliers=0.1 if i % 3 == 0 else 0.0, behind=2 if i % 5 == 4 and n > 10 else 0) for i, n in enumerate(sizes)]
-    out = binding.flow_pose_batch(probs, *sig, max_iterations=10)
+    out = binding.flow_pose_batch(probs, flow_sigma=sig[0], flow_prior_sigma=sig[1], huber_k=sig[2], outlier_rounds=0)
     assert len(out) == len(probs)
     moved = 0
     for q, r in zip(probs, out):
@@ -93,13 +175,62 @@ def test_star_batch_matches_oracle(sig):
 def test_star_batch_empty_and_large():
     """Edge cases: no problems, a problem with no features (nothing to do: the pose stays), and a frame-sized batch (one CTA per
     problem, more problems than SMs) whose every problem lowers its error."""
-    assert binding.flow_pose_batch([], FLOW_SIGMA, PRIOR_SIGMA, HUBER_K) == []
+    assert binding.flow_pose_batch([]) == [] and binding.motion_refine_batch([]) == []
     rng = np.random.default_rng(2)
     probs = [make_problem(rng, 0)] + [make_problem(rng, int(n)) for n in rng.integers(30, 300, 400)]
-    out = binding.flow_pose_batch(probs, 1.0, 0.5, 1.0, max_iterations=10)
+    out = binding.flow_pose_batch(probs, flow_sigma=1.0, flow_prior_sigma=0.5, huber_k=1.0, outlier_rounds=0)
     assert out[0]["iterations"] == 0 and np.array_equal(out[0]["pose"], np.asarray(probs[0]["pose_init"]))
     closer = 0
     for q, r in zip(probs[1:], out[1:]):
         assert r["error_final"] < r["error_initial"] and r["iterations"] >= 1
         closer += np.abs(r["pose"][9:] - q["gt"][9:]).max() < np.abs(np.asarray(q["pose_init"])[9:] - q["gt"][9:]).max()
     assert closer >= 0.9*(len(probs) - 1)
+
+
+@pytest.mark.gpu
+def test_flow_pose_outlier_rounds_match_oracle():
+    """LM + the reference's outlier rounds (MotionSolver-inl.hpp:201-247) in one launch: same inlier sets, number of rounds,
+    iteration totals, error and pose as the CPU restatement."""
+    from oracle import star_oracle as SO
+    rng = np.random.default_rng(21)
+    sizes = [40, 80, 150, 200, 260, 300] + list(rng.integers(30, 250, 10))
+    probs = [make_problem(rng, int(n), noise=0.3, outliers=(0.0, 0.1, 0.2)[i % 3], behind=2 if i % 4 == 3 else 0) for i, n in enumerate(sizes)]
+    for sig in ((1.0, 0.5, 1.0), (FLOW_SIGMA, PRIOR_SIGMA, HUBER_K)):
+        out = binding.flow_pose_batch(probs, flow_sigma=sig[0], flow_prior_sigma=sig[1], huber_k=sig[2])      # defaults: 4 rounds, 10 iterations
+        with_rounds = 0
+        for q, r in zip(probs, out):
+            o = SO.flow_pose_refine(q["pose_init"], q["pose_prev"], K5, q["kp_prev"], q["depth"], q["flow"], *sig, outlier_rounds=4, max_iterations=10)
+            assert r["rounds"] == o["rounds"] and np.array_equal(r["inlier"], o["inlier"]), (len(q["depth"]), r["rounds"], o["rounds"])
+            assert (r["iterations"], r["inner_iterations"]) == (o["iterations"], o["inner_iterations"])
+            assert abs(r["error_initial"] - o["error_initial"]) <= 1e-11*max(o["error_initial"], 1.0)
+            assert abs(r["error_final"] - o["error_final"]) <= 1e-9*max(o["error_final"], 1e-12) + 1e-12
+            assert np.abs(r["pose"] - o["pose"]).max() < 1e-7 and np.abs(r["flow"] - o["flow"]).max() < 1e-6
+            with_rounds += r["rounds"] > 0
+        if sig[0] == 1.0:
+            assert with_rounds >= 5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("soft", [False, True])
+def test_motion_refine_batch_matches_oracle(soft):
+    """Object-motion refinement, one CTA per problem: same LM run as the dense CPU restatement (fp64; the camera priors put
+    1e10 next to 1e6 in the Hessian, hence 1e-7 relative on chi^2 and 1e-6 on the values)."""
+    from oracle import star_oracle as SO
+    rng = np.random.default_rng(31)
+    sizes = [6, 7, 20, 64, 100, 255, 256, 257] + list(rng.integers(10, 120, 6))
+    probs = [make_motion_problem(rng, int(n), outliers=0.1 if i % 2 else 0.0) for i, n in enumerate(sizes)]
+    kw = dict(landmark_motion_sigma=0.05, huber_k=1.0, max_iterations=8) if soft else {}
+    out = binding.motion_refine_batch(probs, **kw)
+    same = 0
+    for q, r in zip(probs, out):
+        o = SO.motion_refine_lm(q["pose_prev"], q["pose_cur"], q["motion_init"], K5, q["kp_prev"], q["kp_cur"], q["points_init"], **kw)
+        assert abs(r["error_initial"] - o["error_initial"]) <= 1e-10*o["error_initial"]
+        if (r["iterations"], r["inner_iterations"]) != (o["iterations"], o["inner_iterations"]):
+            continue                                                 # a fidelity test decided on the last digits; counted below
+        same += 1
+        assert abs(r["error_final"] - o["error_final"]) <= 1e-7*o["error_final"] + 1e-12
+        assert np.abs(r["motion"] - o["motion"]).max() < 1e-6 and np.abs(r["poses"] - o["poses"]).max() < 1e-6
+        assert np.abs(r["points"] - o["points"]).max() < 1e-5
+        assert np.abs(r["motion_factor_error"] - o["motion_factor_error"]).max() <= 1e-5*max(o["motion_factor_error"].max(), 1.0)
+        assert r["error_final"] < r["error_initial"]
+    assert same >= len(probs) - 3, same
