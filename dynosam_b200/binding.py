@@ -28,7 +28,7 @@ EXPORTS = [
     "dynoba_optimize", "dynoba_get_variables", "dynoba_get_keys", "dynoba_num_variables", "dynoba_problem_info",
     "dynoba_linearize", "dynoba_linearize_block", "dynoba_get_linearization", "dynoba_get_factor_errors", "dynoba_solve",
     "dynoba_get_reduced_system", "dynoba_retract", "dynoba_flow_pose_default_params", "dynoba_flow_pose_batch",
-    "dynoba_motion_refine_default_params", "dynoba_motion_refine_batch",
+    "dynoba_motion_refine_default_params", "dynoba_motion_refine_batch", "dynoba_batch_release",
 ]
 
 

@@ -16,6 +16,7 @@
 // control loop of api.cu::dynoba_optimize.
 #include <cfloat>
 #include <algorithm>
+#include <mutex>
 #include <vector>
 #include "../../include/dynoba.h"
 #include "internal.cuh"
@@ -146,7 +147,7 @@ __device__ __forceinline__ void flow_factor(const FlowPoseBatch& S, int i, bool 
 
 struct FlowPoseProblem {
   const FlowPoseBatch& S; int f0, f1; Pose Xp; double K6[6];
-  double* red; double* sums; double* sh_dp; Pose* sh_cur; Pose* sh_cand; int* sh_ok;
+  double* red; double* sums; double* sh_dp; double* sh_L; Pose* sh_cur; Pose* sh_cand; int* sh_ok;
 
   __device__ double error_at(const Pose& X, const double* flows) {
     double e[1] = { 0.0 };
@@ -183,7 +184,7 @@ struct FlowPoseProblem {
     }
     block_sum<28>(acc, red, sums);
     if (threadIdx.x == 0) {
-      double L[36]; int e = 0;
+      double* L = sh_L; int e = 0;
       for (int r = 0; r < 6; r++) for (int c = 0; c <= r; c++, e++) L[r*6 + c] = sums[e] + (r == c ? lambda : 0.0);
       const bool ok = chol_lower<6>(L);
       if (ok) { chol_solve<6>(L, sums + 21, sh_dp); Pose cand; se3_retract(*sh_cur, sh_dp, cand); *sh_cand = cand; }
@@ -240,11 +241,11 @@ struct FlowPoseProblem {
 __global__ void __launch_bounds__(STAR_THREADS) flow_pose_kernel(FlowPoseBatch S) {
   __shared__ double red[28*STAR_WARPS];
   __shared__ double sums[28];
-  __shared__ double sh_dp[6];
+  __shared__ double sh_dp[6], sh_L[36];
   __shared__ Pose sh_cur, sh_cand;
   __shared__ int sh_ok;
   const int pb = blockIdx.x;
-  FlowPoseProblem Q{ S, S.off[pb], S.off[pb + 1], Pose{}, {0, 0, 0, 0, 0, 0}, red, sums, sh_dp, &sh_cur, &sh_cand, &sh_ok };
+  FlowPoseProblem Q{ S, S.off[pb], S.off[pb + 1], Pose{}, {0, 0, 0, 0, 0, 0}, red, sums, sh_dp, sh_L, &sh_cur, &sh_cand, &sh_ok };
   Pose X0;
   for (int k = 0; k < 9; k++) { Q.Xp.R[k] = S.pose_prev[12*pb + k]; X0.R[k] = S.pose0[12*pb + k]; }
   for (int k = 0; k < 3; k++) { Q.Xp.t[k] = S.pose_prev[12*pb + 9 + k]; X0.t[k] = S.pose0[12*pb + 9 + k]; }
@@ -543,19 +544,33 @@ __global__ void __launch_bounds__(STAR_THREADS) motion_refine_kernel(MotionBatch
   }
 }
 
-// a bump allocator over one device block, 16-byte granules; with base == nullptr it only measures
+// Per-device state kept between calls (these entry points run every frame): one stream and one grow-only workspace, so a call
+// costs copies + one launch -- no cudaMalloc / cudaFree / stream creation on the per-frame path.  Calls on one device serialise.
+struct StarContext { std::mutex mu; cudaStream_t stream = nullptr; char* base = nullptr; size_t cap = 0; };
+static StarContext g_star[64];
+// a bump allocator over the workspace, 16-byte granules; with base == nullptr it only measures
 struct DeviceBlock {
   char* base = nullptr; size_t used = 0;
   template <class T> T* take(size_t count) { T* p = base ? (T*)(base + used) : nullptr; used += (count*sizeof(T) + 15) & ~(size_t)15; return p; }
-  bool allocate() { const size_t need = used + 256; used = 0; return cudaMalloc((void**)&base, need) == cudaSuccess; }
-  ~DeviceBlock() { if (base) cudaFree(base); }
+  bool allocate(StarContext& c) {
+    const size_t need = used + 256; used = 0;
+    if (need > c.cap) {
+      if (c.base) { cudaFree(c.base); c.base = nullptr; c.cap = 0; }
+      const size_t cap = need + need/2;
+      if (cudaMalloc((void**)&c.base, cap) != cudaSuccess) { c.base = nullptr; return false; }
+      c.cap = cap;
+    }
+    base = c.base; return true;
+  }
 };
 static int star_device_ready(int device) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return DYNOBA_ERR_CUDA;     // no CPU fallback
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return DYNOBA_ERR_CUDA;
-  if (cudaSetDevice(device) != cudaSuccess) return DYNOBA_ERR_CUDA;
+  if (device >= 64 || cudaSetDevice(device) != cudaSuccess) return DYNOBA_ERR_CUDA;
+  StarContext& c = g_star[device];
+  if (!c.stream && cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) { c.stream = nullptr; return DYNOBA_ERR_CUDA; }
   return DYNOBA_OK;
 }
 
@@ -583,7 +598,10 @@ int dynoba_flow_pose_batch(int device, int32_t n_problems, const int32_t* offset
   const int total = offsets[n_problems];
   if (offsets[0] != 0 || total < 0 || (total > 0 && (!kp_prev || !depth || !flow || !flow_out))) return DYNOBA_ERR_BAD_ARG;
   for (int p = 0; p < n_problems; p++) if (offsets[p + 1] < offsets[p]) return DYNOBA_ERR_BAD_ARG;
+  if (device < 0 || device >= 64) return DYNOBA_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(g_star[device].mu);
   int rc = star_device_ready(device); if (rc) return rc;
+  StarContext& ctx = g_star[device];
   const size_t np = (size_t)n_problems, nt = (size_t)std::max(total, 1);
   DeviceBlock blk; FlowPoseBatch S{};
   int* d_off; double *d_pose0, *d_prev, *d_cal, *d_kp, *d_depth, *d_flow0;
@@ -597,10 +615,10 @@ int dynoba_flow_pose_batch(int device, int32_t n_problems, const int32_t* offset
     S.iterations = blk.take<int>(np); S.inner = blk.take<int>(np); S.rounds = blk.take<int>(np);
   };
   layout();
-  if (!blk.allocate()) { cudaGetLastError(); return DYNOBA_ERR_CUDA; }
+  if (!blk.allocate(ctx)) { cudaGetLastError(); return DYNOBA_ERR_CUDA; }
   layout();
   S.nprob = n_problems;
-  cudaStream_t s; if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return DYNOBA_ERR_CUDA;
+  cudaStream_t s = ctx.stream;
   cudaMemcpyAsync(d_off, offsets, (np + 1)*4, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_pose0, pose_init, 96*np, cudaMemcpyHostToDevice, s); cudaMemcpyAsync(d_prev, pose_prev, 96*np, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_cal, calib5, 40*np, cudaMemcpyHostToDevice, s);
@@ -619,7 +637,6 @@ int dynoba_flow_pose_batch(int device, int32_t n_problems, const int32_t* offset
   cudaMemcpyAsync(iterations, S.iterations, 4*np, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(inner_iterations, S.inner, 4*np, cudaMemcpyDeviceToHost, s);
   if (rounds) cudaMemcpyAsync(rounds, S.rounds, 4*np, cudaMemcpyDeviceToHost, s);
   const cudaError_t e1 = cudaStreamSynchronize(s), e2 = cudaGetLastError();
-  cudaStreamDestroy(s);
   return (e1 == cudaSuccess && e2 == cudaSuccess) ? DYNOBA_OK : DYNOBA_ERR_CUDA;
 }
 
@@ -642,7 +659,10 @@ int dynoba_motion_refine_batch(int device, int32_t n_problems, const int32_t* of
   const int total = offsets[n_problems];
   if (offsets[0] != 0 || total < 0 || (total > 0 && (!kp_prev || !kp_cur || !points_init))) return DYNOBA_ERR_BAD_ARG;
   for (int p = 0; p < n_problems; p++) if (offsets[p + 1] < offsets[p]) return DYNOBA_ERR_BAD_ARG;
+  if (device < 0 || device >= 64) return DYNOBA_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(g_star[device].mu);
   int rc = star_device_ready(device); if (rc) return rc;
+  StarContext& ctx = g_star[device];
   const size_t np = (size_t)n_problems, nt = (size_t)std::max(total, 1);
   DeviceBlock blk; MotionBatch S{};
   int* d_off; double *d_pa, *d_pb, *d_h, *d_cal, *d_ka, *d_kb, *d_pt0;
@@ -655,10 +675,10 @@ int dynoba_motion_refine_batch(int device, int32_t n_problems, const int32_t* of
     S.iterations = blk.take<int>(np); S.inner = blk.take<int>(np);
   };
   layout();
-  if (!blk.allocate()) { cudaGetLastError(); return DYNOBA_ERR_CUDA; }
+  if (!blk.allocate(ctx)) { cudaGetLastError(); return DYNOBA_ERR_CUDA; }
   layout();
   S.nprob = n_problems;
-  cudaStream_t s; if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return DYNOBA_ERR_CUDA;
+  cudaStream_t s = ctx.stream;
   cudaMemcpyAsync(d_off, offsets, (np + 1)*4, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_pa, pose_prev, 96*np, cudaMemcpyHostToDevice, s); cudaMemcpyAsync(d_pb, pose_cur, 96*np, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_h, motion_init, 96*np, cudaMemcpyHostToDevice, s); cudaMemcpyAsync(d_cal, calib5, 40*np, cudaMemcpyHostToDevice, s);
@@ -675,8 +695,19 @@ int dynoba_motion_refine_batch(int device, int32_t n_problems, const int32_t* of
   cudaMemcpyAsync(err_before, S.err_before, 8*np, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(err_after, S.err_after, 8*np, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(iterations, S.iterations, 4*np, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(inner_iterations, S.inner, 4*np, cudaMemcpyDeviceToHost, s);
   const cudaError_t e1 = cudaStreamSynchronize(s), e2 = cudaGetLastError();
-  cudaStreamDestroy(s);
   return (e1 == cudaSuccess && e2 == cudaSuccess) ? DYNOBA_OK : DYNOBA_ERR_CUDA;
+}
+
+// frees the per-device workspace and stream the two batch entry points keep between calls
+int dynoba_batch_release(int device) {
+  if (device < 0 || device >= 64) return DYNOBA_ERR_BAD_ARG;
+  StarContext& c = g_star[device];
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (!c.base && !c.stream) return DYNOBA_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return DYNOBA_ERR_CUDA;
+  if (c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); c.stream = nullptr; }
+  if (c.base) { cudaFree(c.base); c.base = nullptr; c.cap = 0; }
+  return DYNOBA_OK;
 }
 
 }  // extern "C"

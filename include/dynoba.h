@@ -270,6 +270,9 @@ typedef struct {
   dynoba_lm_params lm;                                       /* GTSAM defaults with max_iterations 5 */
 } dynoba_motion_refine_params;
 void dynoba_motion_refine_default_params(dynoba_motion_refine_params* p);
+/* Both batch entry points keep one stream and one grow-only device workspace per device between calls (they run every frame:
+ * no allocation on that path; calls on one device serialise).  dynoba_batch_release frees them. */
+int dynoba_batch_release(int device);
 int dynoba_motion_refine_batch(int device, int32_t n_problems, const int32_t* offsets, const double* pose_prev,
                                const double* pose_cur, const double* motion_init, const double* calib5,
                                const double* kp_prev, const double* kp_cur, const double* points_init,
