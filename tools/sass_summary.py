@@ -6,10 +6,11 @@ tensor core), DFMA, UBLKCP / LDGSTS (bulk and per-thread async copies), SYNCS (m
 """
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIBS = {"libdynoba.so": ["linearize_kernel<5", "schur_accum_kernel<2", "schur_stage_kernel<2", "band_cholesky_dataflow_kernel_v3", "band_backward_cluster_kernel"],
+LIBS = {"libdynoba.so": ["linearize_kernel<5", "schur_accum_kernel<2", "schur_stage_kernel<2", "band_cholesky_dataflow_kernel_v3", "band_backward_cluster_kernel",
+                        "flow_pose_kernel", "motion_refine_kernel"],
         "libdynofront.so": ["klt_kernel", "sc_count_kernel", "pm_warp_kernel"]}
 KEYS = ["DMMA", "DFMA", "DADD", "DMUL", "MUFU", "UBLKCP", "LDGSTS", "SYNCS", "RED", "ATOM", "LDG.E.64", "LDG.E.128", "LDG.E.U8", "LDG.E ", "STG.E.64", "STG.E.128",
-        "STG.E ", "LDS", "STS", "BAR", "SHFL", "UTMALDG", "UTCMMA"]
+        "STG.E ", "LDS", "STS", "LDL", "STL", "BAR", "SHFL", "UTMALDG", "UTCMMA"]
 
 def demangle(n):
     try:
