@@ -235,6 +235,18 @@ def test_gtsam_adapter_compiles_against_api_stubs():
         assert t in src
 
 
+def test_motion_solver_adapter_compiles_against_api_stubs():
+    """include/dynoba_motion_solver_adapter.hpp (the binding of the batched per-object refinements, MotionSolver.cc:673-713) is
+    real code over gtsam value types: it must compile against the same API stubs."""
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Wno-pragma-once-outside-header", "-I", os.path.join(ROOT, "tests", "stubs"),
+                        "-I", os.path.join(ROOT, "include"), "-x", "c++", os.path.join(ROOT, "include", "dynoba_motion_solver_adapter.hpp")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    src = open(os.path.join(ROOT, "include", "dynoba_motion_solver_adapter.hpp")).read()
+    for t in ("dynoba_flow_pose_batch", "dynoba_motion_refine_batch", "OpticalFlowAndPoseBatch", "MotionOnlyRefinementBatch"):
+        assert t in src
+
+
 def _build_capi_smoke(tmp_path):
     exe = str(tmp_path / "capi_smoke")
     libdir = os.path.join(ROOT, "dynosam_b200")
