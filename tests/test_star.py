@@ -6,55 +6,8 @@ import pytest
 
 from dynosam_b200 import binding, lie
 
-K5 = np.array([721.5377, 721.5377, 0.0, 609.5593, 172.854])
-FLOW_SIGMA, PRIOR_SIGMA, HUBER_K = 10.0, 3.33, 0.001          # FrontendParams-like magnitudes (flow in pixels)
-
-
-def _project(X, p):
-    q = lie.transform_to(np.tile(X, (len(p), 1)), p)
-    return np.stack([K5[0]*q[:, 0]/q[:, 2] + K5[3], K5[1]*q[:, 1]/q[:, 2] + K5[4]], 1), q[:, 2]
-
-
-def _back_project(X, kp, depth):
-    pc = np.stack([(kp[:, 0] - K5[3])/K5[0]*depth, (kp[:, 1] - K5[4])/K5[1]*depth, depth], 1)
-    return lie.transform_from(np.tile(X, (len(kp), 1)), pc)
-
-
-def make_motion_problem(rng, n, px_noise=0.3, depth_noise=0.05, outliers=0.0):
-    """two camera poses, a moving rigid object: key-points in both frames, back-projected (noisy depth) world points, a
-    perturbed initial motion"""
-    Xa = lie.se3_exp(rng.normal(0, 0.05, (1, 6)))[0]
-    Xb = lie.compose(Xa[None], lie.se3_exp(np.array([[0.002, -0.01, 0.001, 0.02, -0.01, 0.6]])))[0]
-    H = lie.se3_exp(np.array([[0.01, 0.03, -0.01, 0.3, 0.02, 0.5]]) + rng.normal(0, 0.01, (1, 6)))[0]
-    kp0 = np.stack([rng.uniform(400, 800, n), rng.uniform(100, 300, n)], 1); d0 = rng.uniform(8, 20, n)
-    ma = _back_project(Xa, kp0, d0)
-    mb = lie.transform_from(np.tile(H, (n, 1)), ma)
-    if outliers > 0:
-        bad = rng.random(n) < outliers; mb[bad] += rng.normal(0, 0.5, (int(bad.sum()), 3))
-    kpa, da = _project(Xa, ma); kpb, db = _project(Xb, mb)
-    kpa = kpa + rng.normal(0, px_noise, (n, 2)); kpb = kpb + rng.normal(0, px_noise, (n, 2))
-    ma0 = _back_project(Xa, kpa, da*(1 + rng.normal(0, depth_noise, n))); mb0 = _back_project(Xb, kpb, db*(1 + rng.normal(0, depth_noise, n)))
-    H0 = lie.compose(H[None], lie.se3_exp(rng.normal(0, 0.02, (1, 6))))[0]
-    return dict(pose_prev=Xa, pose_cur=Xb, motion_init=H0, calib=K5, kp_prev=kpa, kp_cur=kpb, points_init=np.concatenate([ma0, mb0], 1), gt=H)
-
-
-def make_problem(rng, n, noise=0.5, outliers=0.0, behind=0):
-    X_prev = lie.se3_exp(rng.normal(0, 0.05, (1, 6)))[0]
-    step = lie.se3_exp(np.array([[0.01, -0.02, 0.005, 0.05, -0.02, 0.9]]) + rng.normal(0, 0.01, (1, 6)))[0]
-    X_gt = lie.compose(X_prev[None], step[None])[0]
-    kp = np.stack([rng.uniform(50, 1190, n), rng.uniform(30, 340, n)], 1); depth = rng.uniform(5, 40, n)
-    pc = np.stack([(kp[:, 0] - K5[3])/K5[0]*depth, (kp[:, 1] - K5[4])/K5[1]*depth, depth], 1)
-    pw = lie.transform_from(np.tile(X_prev, (n, 1)), pc) if n else np.zeros((0, 3))
-    q = lie.transform_to(np.tile(X_gt, (n, 1)), pw) if n else np.zeros((0, 3))
-    proj = np.stack([K5[0]*q[:, 0]/q[:, 2] + K5[3], K5[1]*q[:, 1]/q[:, 2] + K5[4]], 1)
-    flow = proj - kp + rng.normal(0, noise, (n, 2))
-    if outliers > 0 and n:
-        bad = rng.random(n) < outliers
-        flow[bad] += rng.normal(0, 40.0, (int(bad.sum()), 2))
-    if behind and n:
-        depth[:behind] = 0.2                                     # points that end up behind the camera: cheirality branch
-    init = lie.compose(X_gt[None], lie.se3_exp(rng.normal(0, 0.02, (1, 6))))[0]
-    return dict(pose_init=init, pose_prev=X_prev, calib=K5, kp_prev=kp, depth=depth, flow=flow, gt=X_gt)
+from dynosam_b200.synth_star import (FLOW_SIGMA, HUBER_K, K5, PRIOR_SIGMA, flow_parity_set, flow_rounds_set, make_flow_pose_problem as make_problem,
+                                     make_motion_problem, motion_set)
 
 
 def test_star_oracle_is_a_minimiser():
@@ -150,9 +103,7 @@ def test_star_batch_matches_oracle(sig):
     """Every problem of the batch runs the same LM as the CPU restatement: same accepted / rejected steps, same error, same
     pose and flows (fp64; tolerance 1e-9 relative on chi^2, 1e-7 on the values)."""
     from oracle import star_oracle as SO
-    rng = np.random.default_rng(11)
-    sizes = [1, 2, 3, 7, 33, 64, 100, 255, 256, 257, 300, 511, 700] + list(rng.integers(20, 400, 12))
-    probs = [make_problem(rng, int(n), noise=0.5, outliers=0.1 if i % 3 == 0 else 0.0, behind=2 if i % 5 == 4 and n > 10 else 0) for i, n in enumerate(sizes)]
+    probs = flow_parity_set()
     out = binding.flow_pose_batch(probs, flow_sigma=sig[0], flow_prior_sigma=sig[1], huber_k=sig[2], outlier_rounds=0)
     assert len(out) == len(probs)
     moved = 0
@@ -192,9 +143,7 @@ def test_flow_pose_outlier_rounds_match_oracle():
     """LM + the reference's outlier rounds (MotionSolver-inl.hpp:201-247) in one launch: same inlier sets, number of rounds,
     iteration totals, error and pose as the CPU restatement."""
     from oracle import star_oracle as SO
-    rng = np.random.default_rng(21)
-    sizes = [40, 80, 150, 200, 260, 300] + list(rng.integers(30, 250, 10))
-    probs = [make_problem(rng, int(n), noise=0.3, outliers=(0.0, 0.1, 0.2)[i % 3], behind=2 if i % 4 == 3 else 0) for i, n in enumerate(sizes)]
+    probs = flow_rounds_set()
     for sig in ((1.0, 0.5, 1.0), (FLOW_SIGMA, PRIOR_SIGMA, HUBER_K)):
         out = binding.flow_pose_batch(probs, flow_sigma=sig[0], flow_prior_sigma=sig[1], huber_k=sig[2])      # defaults: 4 rounds, 10 iterations
         with_rounds = 0; same = 0
@@ -223,9 +172,7 @@ def test_motion_refine_batch_matches_oracle(soft):
     """Object-motion refinement, one CTA per problem: same LM run as the dense CPU restatement (fp64; the camera priors put
     1e10 next to 1e6 in the Hessian, hence 1e-7 relative on chi^2 and 1e-6 on the values)."""
     from oracle import star_oracle as SO
-    rng = np.random.default_rng(31)
-    sizes = [6, 7, 20, 64, 100, 255, 256, 257] + list(rng.integers(10, 120, 6))
-    probs = [make_motion_problem(rng, int(n), outliers=0.1 if i % 2 else 0.0) for i, n in enumerate(sizes)]
+    probs = motion_set()
     kw = dict(landmark_motion_sigma=0.05, huber_k=1.0, max_iterations=8) if soft else {}
     out = binding.motion_refine_batch(probs, **kw)
     same = 0; worst = dict(chi2=0.0, motion=0.0, points=0.0, factor=0.0)

@@ -3,8 +3,8 @@ through the C ABI with host buffers (H2D, the single launch, D2H inside the time
 import json, os, subprocess, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from test_star import make_motion_problem, make_problem                                    # noqa: E402
+sys.path.insert(0, ROOT)
+from dynosam_b200.synth_star import make_flow_pose_problem as make_problem, make_motion_problem    # noqa: E402
 from dynosam_b200 import binding                                                           # noqa: E402
 
 rng = np.random.default_rng(1)
