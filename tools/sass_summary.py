@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBS = {"libdynoba.so": ["linearize_kernel<5", "schur_accum_kernel<2", "schur_stage_kernel<2", "band_cholesky_dataflow_kernel_v3", "band_backward_cluster_kernel",
                         "flow_pose_kernel", "motion_refine_kernel"],
         "libdynofront.so": ["klt_kernel", "sc_count_kernel", "pm_warp_kernel"]}
+CENSUS_ONLY = ("flow_pose_kernel", "motion_refine_kernel")
 KEYS = ["DMMA", "DFMA", "DADD", "DMUL", "MUFU", "UBLKCP", "LDGSTS", "SYNCS", "RED", "ATOM", "LDG.E.64", "LDG.E.128", "LDG.E.U8", "LDG.E ", "STG.E.64", "STG.E.128",
         "STG.E ", "LDS", "STS", "LDL", "STL", "BAR", "SHFL", "UTMALDG", "UTCMMA"]
 
@@ -41,7 +42,8 @@ def main():
                         ops[k.strip() if not k.endswith(" ") else k.strip() + " (32-bit)"] += 1
             short = re.sub(r"\(.*", "", name).replace("dynoba::", "")
             fn = os.path.join(ROOT, "profiles", "r02_sass_" + re.sub(r"[^A-Za-z0-9]+", "_", short).strip("_") + ".txt")
-            open(fn, "w").write(f"// cuobjdump -sass {lib}, function {name}\n" + b)
+            if not any(w in name for w in CENSUS_ONLY):           # large scalar kernels: census row only, no multi-MB dump in the repo
+                open(fn, "w").write(f"// cuobjdump -sass {lib}, function {name}\n" + b)
             rows.append((lib, short, n_inst, ops))
     print("| kernel | instructions | " + " | ".join(k.strip() for k in KEYS) + " |")
     print("|---|---|" + "---|"*len(KEYS))
