@@ -81,70 +81,3 @@ def test_cuda_reproduces_golden_lm(formulation):
     pose, point, _ = s.values()
     assert np.abs(pose.sum(0) - g["pose_sum"]).max() <= 1e-4 and np.abs(point.sum(0) - g["point_sum"]).max() <= 1e-2
     s.close()
-
-
-# ---- batched star problems: outputs of oracle/star_oracle.py on dynosam_b200/synth_star.py's seeded sets
-STAR_SIGMAS = dict(flow_sigma=1.0, flow_prior_sigma=0.5, huber_k=1.0)
-
-
-def _check_star_flow(g, results, offset=0):
-    """results[i] belongs to problem offset + i of the fixture; exact-fit problems (<= 3 features) are compared at the minimum"""
-    starts = np.concatenate([[0], np.cumsum(g["n"])])
-    same = 0
-    for i, r in enumerate(results):
-        j = offset + i
-        assert len(r["flow"]) == int(g["n"][j])
-        assert abs(r["error_initial"] - g["error_initial"][j]) <= 1e-11*max(g["error_initial"][j], 1.0)
-        assert r["rounds"] == int(g["rounds"][j])
-        assert np.array_equal(np.asarray(r["inlier"], dtype=np.uint8), g["inlier_bits"][starts[j]:starts[j + 1]])
-        if g["error_final"][j] < 1e-12*g["error_initial"][j]:
-            assert r["error_final"] < 1e-10*g["error_initial"][j]
-            same += 1
-            continue
-        if (r["iterations"], r["inner_iterations"]) == (int(g["iterations"][j]), int(g["inner_iterations"][j])):
-            same += 1
-            assert abs(r["error_final"] - g["error_final"][j]) <= 1e-9*max(g["error_final"][j], 1e-12) + 1e-12
-            assert np.abs(r["pose"] - g["pose"][j]).max() < 1e-7
-            assert np.abs(r["flow"].sum(0) - g["flow_sum"][j]).max() < 1e-6*max(len(r["flow"]), 1)
-        else:       # a stopping test fell on the other side in the last digits: same minimum, one iteration more or less
-            assert abs(r["iterations"] - int(g["iterations"][j])) <= 1
-            assert abs(r["error_final"] - g["error_final"][j]) <= 1e-4*g["error_final"][j] and np.abs(r["pose"] - g["pose"][j]).max() < 1e-4
-    assert same >= len(results) - 2, same
-
-
-def _check_star_motion(g, results, offset=0):
-    same = 0
-    for i, r in enumerate(results):
-        j = offset + i
-        assert len(r["points"]) == int(g["n"][j])
-        assert abs(r["error_initial"] - g["error_initial"][j]) <= 1e-10*g["error_initial"][j]
-        if (r["iterations"], r["inner_iterations"]) != (int(g["iterations"][j]), int(g["inner_iterations"][j])):
-            continue
-        same += 1
-        assert abs(r["error_final"] - g["error_final"][j]) <= 1e-3*g["error_final"][j]
-        assert np.abs(r["motion"] - g["motion"][j]).max() < 1e-4 and np.abs(r["poses"] - g["poses"][j]).max() < 1e-6
-        assert abs(r["motion_factor_error"].sum() - g["factor_error_sum"][j]) <= 1e-3*max(g["factor_error_sum"][j], 1.0)
-    assert same >= len(results) - 3, same
-
-
-def test_oracle_reproduces_golden_star():
-    """the dense restatements still give the stored runs (a slice of every set, to keep the CPU suite short)"""
-    from dynosam_b200 import synth_star
-    from oracle import star_oracle as SO
-    sig = (STAR_SIGMAS["flow_sigma"], STAR_SIGMAS["flow_prior_sigma"], STAR_SIGMAS["huber_k"])
-    for name, probs, rounds, lo, hi in (("star_flow_pose_lm.npz", synth_star.flow_parity_set(), 0, 2, 9), ("star_flow_pose_rounds.npz", synth_star.flow_rounds_set(), 4, 0, 4)):
-        rs = [SO.flow_pose_refine(q["pose_init"], q["pose_prev"], synth_star.K5, q["kp_prev"], q["depth"], q["flow"], *sig, outlier_rounds=rounds, max_iterations=10)
-              for q in probs[lo:hi]]
-        _check_star_flow(_load(name), rs, offset=lo)
-    probs = synth_star.motion_set()
-    rs = [SO.motion_refine_lm(q["pose_prev"], q["pose_cur"], q["motion_init"], synth_star.K5, q["kp_prev"], q["kp_cur"], q["points_init"]) for q in probs[:5]]
-    _check_star_motion(_load("star_motion_refine.npz"), rs)
-
-
-@pytest.mark.gpu
-def test_cuda_reproduces_golden_star():
-    """dynoba_flow_pose_batch / dynoba_motion_refine_batch against the stored runs, no oracle at run time"""
-    from dynosam_b200 import binding, synth_star
-    _check_star_flow(_load("star_flow_pose_lm.npz"), binding.flow_pose_batch(synth_star.flow_parity_set(), outlier_rounds=0, **STAR_SIGMAS))
-    _check_star_flow(_load("star_flow_pose_rounds.npz"), binding.flow_pose_batch(synth_star.flow_rounds_set(), **STAR_SIGMAS))
-    _check_star_motion(_load("star_motion_refine.npz"), binding.motion_refine_batch(synth_star.motion_set()))
