@@ -40,6 +40,25 @@ def test_star_batch_fails_loudly_without_gpu():
         binding.motion_refine_batch([make_motion_problem(rng, 10)])
 
 
+def _build_capi_star(tmp_path):
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "capi_star"); libdir = os.path.join(root, "dynosam_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "capi", "capi_star.c"),
+                        "-o", exe, "-L", libdir, "-ldynoba", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+def test_plain_c_program_links_the_star_abi(tmp_path):
+    """tests/capi/capi_star.c: a C99 program links libdynoba.so and calls dynoba_flow_pose_batch; without a GPU it must stop with
+    DYNOBA_ERR_CUDA (exit code 3)"""
+    import subprocess
+    import torch
+    r = subprocess.run([_build_capi_star(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == (0 if torch.cuda.is_available() else 3), r.stdout + r.stderr
+
+
 def test_star_batch_bad_arguments():
     L = binding.load()
     N = None
