@@ -16,7 +16,7 @@ class BuilderParams(C.Structure):
     _fields_ = [("min_static_obs", C.c_int32), ("min_dynamic_obs", C.c_int32), ("keyframe_gap", C.c_int32),
                 ("sigma_static", C.c_double), ("sigma_dynamic", C.c_double), ("huber_k", C.c_double),
                 ("odometry_sigma", C.c_double*6), ("smoothing_sigma", C.c_double*6), ("prior_sigma", C.c_double),
-                ("formulation", C.c_int32), ("sigma_motion", C.c_double)]
+                ("formulation", C.c_int32), ("sigma_motion", C.c_double), ("backtrack", C.c_int32)]
 
 FORMULATIONS = {"hybrid": 0, "wcme": 1, "wcpe": 2}
 

@@ -74,6 +74,7 @@ void dynoba_builder_default_params(dynoba_builder_params* p) {
   for (int i = 0; i < 6; i++) { p->odometry_sigma[i] = od[i]; p->smoothing_sigma[i] = sm[i]; }
   p->prior_sigma = 1e-6;
   p->formulation = DYNOBA_FORMULATION_HYBRID; p->sigma_motion = 0.01;         // motion_ternary_factor_noise_sigma
+  p->backtrack = 1;
 }
 int dynoba_builder_create(const dynoba_builder_params* p, dynoba_builder_handle* out) {
   if (!out) return DYNOBA_ERR_BAD_ARG;
@@ -125,19 +126,34 @@ int dynoba_builder_finalize(dynoba_builder_handle b) {
   auto by_frame = [](const Obs& a, const Obs& c) { return a.frame < c.frame; };
   std::stable_sort(b->stat.begin(), b->stat.end(), by_frame);
   std::stable_sort(b->dyn.begin(), b->dyn.end(), by_frame);
+  // ---- which observations enter the graph.  A tracklet needs min_*_obs observations.  With backtrack (the batch graph of
+  // SURVEY 8d; UpdateObservationParams::do_backtrack = true, ParallelHybridBackendModule.cc:427) all of them are added; without
+  // (RegularBackendModule.cc:139,197) the tracklet enters at the frame its count reaches the minimum and only what that update
+  // adds is kept: static -- that frame's observation on (Formulation-impl.hpp:194-199); dynamic -- the pair (previous, that
+  // frame) on (:703-720), i.e. the first min_dynamic_obs - 2 observations never enter.
+  std::vector<Obs> stat, dyn;
+  {
+    std::map<std::pair<int32_t, int64_t>, int> count, seen;
+    for (auto& o : b->stat) count[{0, o.tracklet}]++;
+    for (auto& o : b->dyn) count[{o.object, o.tracklet}]++;
+    const int min_dyn = P.formulation == DYNOBA_FORMULATION_HYBRID ? P.min_dynamic_obs : std::max(P.min_dynamic_obs, 2);   // a motion factor needs a pair
+    const int start_s = P.backtrack ? 0 : std::max(P.min_static_obs - 1, 0), start_d = P.backtrack ? 0 : std::max(min_dyn - 2, 0);
+    for (auto& o : b->stat) if (count[{0, o.tracklet}] >= P.min_static_obs && seen[{0, o.tracklet}]++ >= start_s) stat.push_back(o);
+    for (auto& o : b->dyn) if (count[{o.object, o.tracklet}] >= min_dyn && seen[{o.object, o.tracklet}]++ >= start_d) dyn.push_back(o);
+  }
+  // ---- static landmarks: tracklets in order of first appearance (frame-major, insertion order inside a frame)
   {
     std::map<int64_t, std::vector<size_t>> tracks; std::vector<int64_t> first_seen;
-    for (size_t i = 0; i < b->stat.size(); i++) { BARG(cam(b->stat[i].frame) >= 0, "static observation in an unknown frame");
-      auto& t = tracks[b->stat[i].tracklet]; if (t.empty()) first_seen.push_back(b->stat[i].tracklet); t.push_back(i); }
+    for (size_t i = 0; i < stat.size(); i++) { BARG(cam(stat[i].frame) >= 0, "static observation in an unknown frame");
+      auto& t = tracks[stat[i].tracklet]; if (t.empty()) first_seen.push_back(stat[i].tracklet); t.push_back(i); }
     Block blk; blk.type = DYNOBA_POSE2POINT3; blk.sigma = { P.sigma_static }; blk.k = P.huber_k;
     for (int64_t tid : first_seen) {
       auto& t = tracks[tid];
-      if ((int)t.size() < P.min_static_obs) continue;
       const int32_t pi = (int32_t)(b->point.size()/3);
-      const Obs& o0 = b->stat[t[0]];
-      double w[3]; se3_transform_from(b->frames[o0.frame].first, o0.z, w);          // initial value: X_k z of the first observation
+      const Obs& o0 = stat[t[0]];
+      double w[3]; se3_transform_from(b->frames[o0.frame].first, o0.z, w);          // initial value: X_k z of the first observation that enters
       b->point.insert(b->point.end(), w, w + 3); b->point_keys.push_back(sym('l', (uint64_t)tid));
-      for (size_t i : t) { const Obs& o = b->stat[i]; blk.idx.push_back(cam(o.frame)); blk.idx.push_back(pi); blk.meas.insert(blk.meas.end(), o.z, o.z + 3); }
+      for (size_t i : t) { const Obs& o = stat[i]; blk.idx.push_back(cam(o.frame)); blk.idx.push_back(pi); blk.meas.insert(blk.meas.end(), o.z, o.z + 3); }
     }
     if (blk.n()) b->blocks.push_back(std::move(blk));
   }
@@ -147,18 +163,17 @@ int dynoba_builder_finalize(dynoba_builder_handle b) {
     const bool wcpe = P.formulation == DYNOBA_FORMULATION_WCPE;
     const int32_t n_cam = (int32_t)cam_index.size();
     std::map<std::pair<int32_t, int64_t>, std::vector<size_t>> tracks; std::vector<std::pair<int32_t, int64_t>> first_seen;
-    for (size_t i = 0; i < b->dyn.size(); i++) { BARG(cam(b->dyn[i].frame) >= 0, "dynamic observation in an unknown frame");
-      auto key = std::make_pair(b->dyn[i].object, b->dyn[i].tracklet);
+    for (size_t i = 0; i < dyn.size(); i++) { BARG(cam(dyn[i].frame) >= 0, "dynamic observation in an unknown frame");
+      auto key = std::make_pair(dyn[i].object, dyn[i].tracklet);
       auto& t = tracks[key]; if (t.empty()) first_seen.push_back(key); t.push_back(i); }
     std::stable_sort(first_seen.begin(), first_seen.end(), [](const std::pair<int32_t, int64_t>& a, const std::pair<int32_t, int64_t>& c) { return a.first < c.first; });
-    const int min_obs = std::max(P.min_dynamic_obs, 2);                 // a motion factor needs a pair
     // (object, frame) -> pose-like variable: WCME the frame that closes a pair, WCPE every observed frame of a kept tracklet
     std::map<std::pair<int32_t, int32_t>, int32_t> var_index;
     std::map<std::pair<int32_t, int32_t>, std::pair<std::array<double, 3>, int>> centroid;     // world points of the kept tracklets
     for (auto& key : first_seen) {
-      auto& t = tracks[key]; if ((int)t.size() < min_obs) continue;
-      for (size_t k = 0; k < t.size(); k++) { const Obs& o = b->dyn[t[k]];
-        if (k > 0) BARG(o.frame > b->dyn[t[k-1]].frame, "a tracklet is observed twice in one frame");
+      auto& t = tracks[key];
+      for (size_t k = 0; k < t.size(); k++) { const Obs& o = dyn[t[k]];
+        if (k > 0) BARG(o.frame > dyn[t[k-1]].frame, "a tracklet is observed twice in one frame");
         if (wcpe || k > 0) var_index[{o.object, o.frame}] = -1;
         double w[3]; se3_transform_from(b->frames[o.frame].first, o.z, w);
         auto& c = centroid[{o.object, o.frame}]; for (int a = 0; a < 3; a++) c.first[a] += w[a]; c.second++; }
@@ -181,14 +196,14 @@ int dynoba_builder_finalize(dynoba_builder_handle b) {
     Block ptp; ptp.type = DYNOBA_POSE2POINT3; ptp.sigma = { P.sigma_dynamic }; ptp.k = P.huber_k;
     Block mot; mot.type = wcpe ? DYNOBA_MOTIONPOSE3 : DYNOBA_TERNARY3; mot.sigma = { P.sigma_motion }; mot.k = P.huber_k;
     for (auto& key : first_seen) {
-      auto& t = tracks[key]; if ((int)t.size() < min_obs) continue;
-      for (size_t k = 0; k < t.size(); k++) { const Obs& o = b->dyn[t[k]];
+      auto& t = tracks[key];
+      for (size_t k = 0; k < t.size(); k++) { const Obs& o = dyn[t[k]];
         const int32_t pi = (int32_t)(b->point.size()/3);
         double w[3]; se3_transform_from(b->frames[o.frame].first, o.z, w);                 // X_k z (dynamicPointUpdateCallback)
         b->point.insert(b->point.end(), w, w + 3); b->point_keys.push_back(sym('m', cantor((uint64_t)o.tracklet, (uint64_t)o.frame)));
         ptp.idx.push_back(cam(o.frame)); ptp.idx.push_back(pi); ptp.meas.insert(ptp.meas.end(), o.z, o.z + 3);
         if (k > 0) { mot.idx.push_back(pi - 1); mot.idx.push_back(pi);
-          if (wcpe) mot.idx.push_back(var_index[{o.object, b->dyn[t[k-1]].frame}]);
+          if (wcpe) mot.idx.push_back(var_index[{o.object, dyn[t[k-1]].frame}]);
           mot.idx.push_back(var_index[{o.object, o.frame}]); }
       }
     }
@@ -207,7 +222,7 @@ int dynoba_builder_finalize(dynoba_builder_handle b) {
   // ---- dynamic: objects -> visibility segments (key-frames) -> motion variables
   const int32_t n_cam = (int32_t)cam_index.size();
   std::map<int32_t, std::vector<int32_t>> obj_frames;                  // object -> sorted frames it is observed in
-  for (auto& o : b->dyn) { BARG(cam(o.frame) >= 0, "dynamic observation in an unknown frame"); obj_frames[o.object].push_back(o.frame); }
+  for (auto& o : dyn) { BARG(cam(o.frame) >= 0, "dynamic observation in an unknown frame"); obj_frames[o.object].push_back(o.frame); }
   struct Seg { int32_t object, keyframe, aux; };
   std::map<std::pair<int32_t, int32_t>, int32_t> motion_index;         // (object, frame) -> pose index
   std::map<std::pair<int32_t, int32_t>, int32_t> seg_of;               // (object, frame) -> segment
@@ -227,7 +242,7 @@ int dynoba_builder_finalize(dynoba_builder_handle b) {
   // ---- dynamic tracklets (object-major, then first appearance), key-frame poses, hybrid factors
   {
     std::map<std::pair<int32_t, int64_t>, std::vector<size_t>> tracks; std::vector<std::pair<int32_t, int64_t>> first_seen;
-    for (size_t i = 0; i < b->dyn.size(); i++) { auto key = std::make_pair(b->dyn[i].object, b->dyn[i].tracklet);
+    for (size_t i = 0; i < dyn.size(); i++) { auto key = std::make_pair(dyn[i].object, dyn[i].tracklet);
       auto& t = tracks[key]; if (t.empty()) first_seen.push_back(key); t.push_back(i); }
     std::stable_sort(first_seen.begin(), first_seen.end(), [](const std::pair<int32_t, int64_t>& a, const std::pair<int32_t, int64_t>& c) { return a.first < c.first; });
     // L_e per segment: given, or the centroid of the key-frame's world points with identity rotation
@@ -236,7 +251,7 @@ int dynoba_builder_finalize(dynoba_builder_handle b) {
       if (it != b->keyframe_pose.end()) Le = it->second;
       else {
         Le = identity_pose(); double c[3] = {0, 0, 0}; int cnt = 0;
-        for (auto& o : b->dyn) if (o.object == segs[s].object && o.frame == segs[s].keyframe) { double w[3]; se3_transform_from(b->frames[o.frame].first, o.z, w); for (int k = 0; k < 3; k++) c[k] += w[k]; cnt++; }
+        for (auto& o : dyn) if (o.object == segs[s].object && o.frame == segs[s].keyframe) { double w[3]; se3_transform_from(b->frames[o.frame].first, o.z, w); for (int k = 0; k < 3; k++) c[k] += w[k]; cnt++; }
         for (int k = 0; k < 3; k++) Le.t[k] = cnt ? c[k]/cnt : 0.0;
       }
       segs[s].aux = (int32_t)(b->aux.size()/12); double p[12]; pose_to(Le, p); b->aux.insert(b->aux.end(), p, p + 12);
@@ -244,18 +259,17 @@ int dynoba_builder_finalize(dynoba_builder_handle b) {
     Block blk; blk.type = DYNOBA_HYBRID3; blk.sigma = { P.sigma_dynamic }; blk.k = P.huber_k; blk.has_aux = true;
     for (auto& key : first_seen) {
       auto& t = tracks[key];
-      if ((int)t.size() < P.min_dynamic_obs) continue;
-      const Obs& o0 = b->dyn[t[0]];
+      const Obs& o0 = dyn[t[0]];
       const int32_t s0 = seg_of[{o0.object, o0.frame}];
       // every observation of a tracklet refers to the key-frame of its FIRST observation (a tracklet does not outlive a segment)
-      bool one_segment = true; for (size_t i : t) one_segment = one_segment && seg_of[{b->dyn[i].object, b->dyn[i].frame}] == s0;
+      bool one_segment = true; for (size_t i : t) one_segment = one_segment && seg_of[{dyn[i].object, dyn[i].frame}] == s0;
       BARG(one_segment, "a dynamic tracklet spans two key-frame segments of its object");
       const int32_t pi = (int32_t)(b->point.size()/3);
       // m_L = L_e^-1 (e_H_k)^-1 X_k z at the first observation (HybridObjectMotion::projectToObject3)
       const Pose Le = pose_from(&b->aux[(size_t)12*segs[s0].aux]); const Pose E = pose_from(&b->pose[(size_t)12*motion_index[{o0.object, o0.frame}]]);
       double w[3], q[3], m[3]; se3_transform_from(b->frames[o0.frame].first, o0.z, w); se3_transform_to(E, w, q); se3_transform_to(Le, q, m);
       b->point.insert(b->point.end(), m, m + 3); b->point_keys.push_back(sym('m', cantor((uint64_t)key.second, 0)));
-      for (size_t i : t) { const Obs& o = b->dyn[i];
+      for (size_t i : t) { const Obs& o = dyn[i];
         blk.idx.push_back(cam(o.frame)); blk.idx.push_back(motion_index[{o.object, o.frame}]); blk.idx.push_back(pi);
         blk.meas.insert(blk.meas.end(), o.z, o.z + 3); blk.aux.push_back(segs[s0].aux); }
     }

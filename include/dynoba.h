@@ -204,6 +204,10 @@ typedef struct {
   double prior_sigma;                        /* 1e-6 */
   int32_t formulation;                       /* DYNOBA_FORMULATION_* (hybrid) */
   double sigma_motion;                       /* motion_ternary_factor_noise_sigma (0.01): TERNARY3 / MOTIONPOSE3 of the world-centric formulations */
+  int32_t backtrack;                         /* UpdateObservationParams::do_backtrack.  1 (default): every observation of a tracklet that reaches
+                                                the minimum count enters the graph (the batch graphs of SURVEY 8d; ParallelHybridBackendModule.cc:427).
+                                                0: RegularBackendModule.cc:139,197 -- a tracklet enters at the frame its count reaches the minimum
+                                                with only what that update adds (static: that observation on; dynamic: the last pair on) */
 } dynoba_builder_params;
 void dynoba_builder_default_params(dynoba_builder_params* p);
 int dynoba_builder_create(const dynoba_builder_params* p, dynoba_builder_handle* out);

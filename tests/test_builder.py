@@ -187,3 +187,50 @@ def test_builder_wcpe_pose_propagation():
     assert np.allclose(q.pose[7][9:], [5.0, 0.0, 5.0])                       # frame 3: no motion -> centroid
     assert q.blocks[1].n == 6 and q.blocks[2].n == 2                         # 6 pose-motion factors, 2 smoothing triples
     b.close()
+
+
+def test_builder_without_backtrack():
+    """UpdateObservationParams::do_backtrack = false (RegularBackendModule.cc:139,197): a tracklet enters the graph at the frame
+    its observation count reaches the minimum, with only what that update adds -- static: that frame's observation on
+    (Formulation-impl.hpp:194-199); dynamic: the pair (previous, that frame) on (:703-720)."""
+    from dynosam_b200.builder import GraphBuilder
+    from dynosam_b200.problem import TERNARY3
+    I = lie.identity()[0]
+    X = [lie.se3_exp(np.array([[0.0, 0.01*k, 0.0, 0.1*k, 0.0, 0.5*k]]))[0] for k in range(6)]
+
+    def feed(b):
+        for k in range(6):
+            b.add_frame(k, X[k], None if k == 0 else I)
+        for k in (2, 3, 4):
+            b.add_static(k, [7], [[0.1*k, 0.0, 4.0]])
+        for k in (4, 5):
+            b.add_static(k, [8], [[1.0, 0.2*k, 6.0]])
+        b.add_static(5, [9], [[0.0, 0.0, 3.0]])                        # seen once: never enters
+        for k in range(5):
+            b.add_dynamic(k, [1, 2], [1, 1], [[1.0 + 0.1*k, 0.0, 5.0], [3.0 + 0.1*k, 0.0, 5.0]])
+        b.add_dynamic(4, [3], [1], [[2.0, 1.0, 5.0]]); b.add_dynamic(5, [3], [1], [[2.1, 1.0, 5.0]])      # two observations: never enters
+
+    b = GraphBuilder(backtrack=0); feed(b); q = b.problem()
+    ptp = q.blocks[0]
+    assert q.n_point == 2 + 2                                          # static 7, 8; dynamic 1, 2
+    assert ptp.idx.tolist() == [[3, 0], [4, 0], [5, 1]]               # 7: frames 3, 4 (2 dropped); 8: frame 5 (4 dropped)
+    assert np.allclose(q.point[0], lie.transform_from(X[3][None], np.array([[0.3, 0.0, 4.0]]))[0])     # X_3 z_3
+    assert np.allclose(q.point[1], lie.transform_from(X[5][None], np.array([[1.0, 1.0, 6.0]]))[0])
+    hyb = q.blocks[1]
+    assert hyb.n == 2*4 and sorted(set(hyb.idx[:, 0].tolist())) == [1, 2, 3, 4]       # frame 0 dropped: the pair (1, 2) opens the tracklet
+    assert q.n_pose == 6 + 4 and q.pose_order[6:].tolist() == [1, 2, 3, 4]            # motions only where factors exist; key-frame = frame 1
+    assert np.allclose(q.aux_pose[0][9:], lie.transform_from(X[1][None], np.array([[2.1, 0.0, 5.0]]))[0])    # centroid of what entered at frame 1
+    # m_L = L_e^-1 (e_H_e = I)^-1 X_1 z_1
+    w = lie.transform_from(X[1][None], np.array([[1.1, 0.0, 5.0]]))[0]
+    assert np.allclose(q.point[2], lie.transform_to(q.aux_pose[0][None], w[None])[0])
+    b.close()
+    # with backtracking (the default) everything of a tracklet that reaches the minimum enters
+    b = GraphBuilder(); feed(b); q = b.problem()
+    assert q.blocks[0].n == 3 + 2 and q.blocks[1].n == 2*5 and q.n_pose == 6 + 5
+    b.close()
+    # world-centric: points from the opening pair on
+    b = GraphBuilder(formulation="wcme", backtrack=0); feed(b); q = b.problem()
+    assert q.n_point == 2 + 2*4 and q.blocks[1].n == 8                # static 7, 8; dynamic points at frames 1..4 of tracklets 1, 2
+    tern = [x for x in q.blocks if x.type == TERNARY3][0]
+    assert tern.n == 2*3 and q.n_pose == 6 + 3 and q.pose_order[6:].tolist() == [2, 3, 4]
+    b.close()
