@@ -292,3 +292,97 @@ def test_simple_optimise_recovers_ground_truth():
     rel_est = O.se3_compose(O.se3_inverse(op.pose[2]), op.pose[3])
     rel_gt = O.se3_compose(O.se3_inverse(pose2), motion2)
     assert np.allclose(rel_est, rel_gt, atol=1e-5)
+
+
+def test_lie_maps_against_scipy():
+    """External pin of the manifold maps the oracle restates from GTSAM 4.2 (SURVEY Appendix A.1): Pose3::Expmap / Logmap with
+    the [omega; v] tangent order are the matrix exponential / logarithm of the 4x4 twist, Rot3::Expmap is Rodrigues -- checked
+    against scipy.linalg.expm / logm, scipy's Rotation and cv2.Rodrigues (none of them shares code with the oracle)."""
+    import cv2
+    from scipy.linalg import expm, logm
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(12)
+    for scale in (1e-9, 1e-3, 0.5, 2.5):
+        for _ in range(5):
+            xi = rng.normal(0, 1, 6)*np.array([scale, scale, scale, 1.0, 1.0, 1.0])
+            w, v = xi[:3], xi[3:]
+            twist = np.zeros((4, 4)); twist[:3, :3] = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]); twist[:3, 3] = v
+            T = expm(twist)
+            P = O.se3_expmap(xi)
+            # GTSAM switches to t = v below theta^2 = DBL_EPSILON (Pose3::Expmap): first-order accurate there
+            ttol = 1e-12 if w @ w > np.finfo(float).eps else np.linalg.norm(w)*np.linalg.norm(v) + 1e-15
+            assert np.abs(P[:9].reshape(3, 3) - T[:3, :3]).max() < 1e-12 and np.abs(P[9:] - T[:3, 3]).max() < ttol
+            assert np.abs(P[:9].reshape(3, 3) - Rotation.from_rotvec(w).as_matrix()).max() < 1e-12
+            assert np.abs(P[:9].reshape(3, 3) - cv2.Rodrigues(w.reshape(3, 1))[0]).max() < 1e-9
+            if np.linalg.norm(w) < 3.0:                                # inside the principal branch of the logarithm
+                L = np.real(logm(T))
+                back = O.se3_logmap(P)
+                ref = np.array([L[2, 1], L[0, 2], L[1, 0], L[0, 3], L[1, 3], L[2, 3]])
+                assert np.abs(back - ref).max() < 1e-8*max(1.0, np.abs(ref).max())
+    # compose / inverse / retract against plain 4x4 algebra
+    def mat(P):
+        M = np.eye(4); M[:3, :3] = np.asarray(P)[:9].reshape(3, 3); M[:3, 3] = np.asarray(P)[9:]; return M
+    a = O.se3_expmap(rng.normal(0, 0.7, 6)); b = O.se3_expmap(rng.normal(0, 0.7, 6)); xi = rng.normal(0, 0.3, 6)
+    assert np.abs(mat(O.se3_compose(a, b)) - mat(a) @ mat(b)).max() < 1e-13
+    assert np.abs(mat(O.se3_inverse(a)) - np.linalg.inv(mat(a))).max() < 1e-12
+    assert np.abs(mat(O.se3_retract(a, xi)) - mat(a) @ mat(O.se3_expmap(xi))).max() < 1e-13      # retract(T, xi) = T Expmap(xi)
+
+
+def test_gtsam_ext_residuals_against_independent_algebra():
+    """External pin of the GTSAM factors the oracle restates (none of them has a test in the reference tree): residuals computed
+    here with plain 4x4 matrices + scipy.linalg.logm, the Huber loss with scipy.special.huber.
+      PriorFactor<Pose3>:    e = -Logmap(x^-1 prior)            BetweenFactor<Pose3>: e = Logmap(measured^-1 (p1^-1 p2))
+      PoseToPointFactor:     e = R^T (p - t) - z                  GenericStereoFactor:  e = (uL, uR, v) - z
+      Robust(Huber(k), Isotropic(sigma)): loss = huber(k, |e| / sigma)"""
+    from scipy.linalg import logm
+    from scipy.special import huber
+    from dynosam_b200.problem import STEREO3
+    rng = np.random.default_rng(13)
+
+    def mat(P):
+        M = np.eye(4); M[:3, :3] = np.asarray(P)[:9].reshape(3, 3); M[:3, 3] = np.asarray(P)[9:]; return M
+
+    def vee(T):
+        L = np.real(logm(T)); return np.array([L[2, 1], L[0, 2], L[1, 0], L[0, 3], L[1, 3], L[2, 3]])
+
+    for _ in range(4):
+        A, B, Mz = (O.se3_expmap(rng.normal(0, 0.4, 6)) for _ in range(3))
+        r, _ = O.OracleProblem(one_factor_problem(PRIOR6, [A], [], meas=B, sigma=np.ones(6))).factor_eval(0, 0)
+        assert np.abs(r + vee(np.linalg.inv(mat(A)) @ mat(B))).max() < 1e-9
+        r, _ = O.OracleProblem(one_factor_problem(BETWEEN6, [A, B], [], meas=Mz, sigma=np.ones(6))).factor_eval(0, 0)
+        assert np.abs(r - vee(np.linalg.inv(mat(Mz)) @ np.linalg.inv(mat(A)) @ mat(B))).max() < 1e-9
+        p = rng.normal(0, 2, 3) + np.array([0, 0, 8.0]); z = rng.normal(0, 1, 3)
+        q = (np.linalg.inv(mat(A)) @ np.append(p, 1.0))[:3]
+        r, _ = O.OracleProblem(one_factor_problem(POSE2POINT3, [A], [p], meas=z, sigma=[1.0])).factor_eval(0, 0)
+        assert np.abs(r - (q - z)).max() < 1e-12
+        K = np.array([700.0, 650.0, 0.0, 600.0, 180.0, 0.5])
+        if q[2] > 0.5:
+            zs = rng.normal(0, 50, 3)
+            r, _ = O.OracleProblem(one_factor_problem(STEREO3, [A], [p], meas=zs, sigma=[1.0], calib=K)).factor_eval(0, 0)
+            proj = np.array([K[3] + K[0]*q[0]/q[2], K[3] + K[0]*(q[0] - K[5])/q[2], K[4] + K[1]*q[1]/q[2]])
+            assert np.abs(r - (proj - zs)).max() < 1e-9
+        # Huber over an isotropic model: the factor error is the scipy Huber loss of the whitened norm
+        for k, sigma in ((1e-4, 0.2), (1.0, 0.2), (5.0, 0.5)):
+            o = O.OracleProblem(one_factor_problem(POSE2POINT3, [A], [p], meas=z, sigma=[sigma], robust_k=k))
+            assert abs(o.error() - huber(k, np.linalg.norm(q - z)/sigma)) <= 1e-12*max(1.0, o.error())
+
+
+def test_lm_minimum_against_scipy_least_squares():
+    """External pin of the LM run as a whole: on a Gaussian (robust off) graph the oracle's Levenberg-Marquardt must end in the
+    least-squares minimum of the whitened residuals -- the same minimum scipy.optimize.least_squares (MINPACK-style trust
+    region, unrelated code) finds from the same initial values through the same retraction."""
+    from scipy.optimize import least_squares
+    from dynosam_b200 import synth
+    p = synth.make_problem(n_frames=6, n_objects=1, n_static=40, n_dynamic=30, formulation="hybrid", seed=3, robust=False, object_span=(6, 6))
+    n = 6*p.n_pose + 3*p.n_point
+
+    def residuals(delta):
+        o = O.OracleProblem(p); o.retract(delta)
+        return -np.concatenate([o.linearize_block(bi)[1].ravel() for bi in range(len(p.blocks))])
+
+    o = O.OracleProblem(p)
+    st = o.optimize(max_iterations=100, rel_tol=1e-12, abs_tol=1e-12)
+    assert abs(0.5*np.sum(residuals(np.zeros(n))**2) - st["error_initial"]) <= 1e-9*st["error_initial"]
+    sol = least_squares(residuals, np.zeros(n), method="trf", xtol=1e-14, ftol=1e-14, gtol=1e-12, max_nfev=200)
+    assert abs(sol.cost - st["error_final"]) <= 1e-7*st["error_final"], (sol.cost, st["error_final"])
+    assert st["error_final"] < 0.5*st["error_initial"]                # it did move: the graph starts well off its minimum
