@@ -94,6 +94,87 @@ def test_projection_factor_restatement():
     assert np.array_equal(r, [1400.0, 1400.0]) and not Jx.any() and not Jp.any()
 
 
+def _flow_pose_objective(q, X, flows, sig):
+    """the objective of OpticalFlowAndPoseOptimizer written independently of oracle/: numpy projection + scipy's Huber loss"""
+    from scipy.special import huber
+    n = len(q["depth"])
+    pc = np.stack([(q["kp_prev"][:, 0] - K5[3])/K5[0]*q["depth"], (q["kp_prev"][:, 1] - K5[4])/K5[1]*q["depth"], q["depth"]], 1)
+    pw = lie.transform_from(np.tile(q["pose_prev"], (n, 1)), pc)
+    c = lie.transform_to(np.tile(X, (n, 1)), pw)
+    with np.errstate(all="ignore"):
+        r = q["kp_prev"] + flows - np.stack([K5[0]*c[:, 0]/c[:, 2] + K5[3], K5[1]*c[:, 1]/c[:, 2] + K5[4]], 1)
+    r[c[:, 2] <= 0] = 2.0*K5[0]                                            # Pose3FlowProjectionFactor.h: behind the camera
+    nrm = np.linalg.norm(r, axis=1)/sig[0]
+    loss = huber(sig[2], nrm) if sig[2] > 0 else 0.5*nrm**2
+    return float(loss.sum() + 0.5*(((flows - q["flow"])/sig[1])**2).sum())
+
+
+def test_flow_pose_oracle_against_independent_objective():
+    """External pin of oracle/star_oracle.py (the reference holds no test of this optimiser): its error equals an objective written
+    from scratch with numpy + scipy.special.huber at arbitrary values, and its LM ends in a stationary point of that objective."""
+    from oracle import star_oracle as SO
+    rng = np.random.default_rng(14)
+    for sig in ((1.0, 0.5, 1.0), (FLOW_SIGMA, PRIOR_SIGMA, 0.0), (2.0, 1.0, 0.3)):
+        q = make_problem(rng, 40, noise=0.4, outliers=0.1, behind=1)
+        m = SO._FlowPose(q["pose_init"], q["pose_prev"], K5, q["kp_prev"], q["depth"], q["flow"], *sig)
+        for _ in range(3):                                                   # (a) same function
+            m.step(rng.normal(0, 0.05, 2*40 + 6))
+            assert abs(m.error() - _flow_pose_objective(q, m.o.pose[0], m.o.flow, sig)) <= 1e-10*max(m.error(), 1.0)
+        r = SO.flow_pose_lm(q["pose_init"], q["pose_prev"], K5, q["kp_prev"], q["depth"], q["flow"], *sig, max_iterations=200,
+                            relative_error_tol=1e-15, absolute_error_tol=1e-15)
+        f0 = _flow_pose_objective(q, r["pose"], r["flow"], sig)
+        assert abs(f0 - r["error_final"]) <= 1e-10*max(f0, 1.0)
+        h = 1e-6; g = []                                                     # (b) stationary: central differences through the retraction
+        for j in range(6):
+            e = np.zeros((1, 6)); e[0, j] = h
+            g.append((_flow_pose_objective(q, lie.retract(r["pose"][None], e)[0], r["flow"], sig) -
+                      _flow_pose_objective(q, lie.retract(r["pose"][None], -e)[0], r["flow"], sig))/(2*h))
+        for i in (0, 7, 23):
+            for a in range(2):
+                fp = r["flow"].copy(); fp[i, a] += h; fm = r["flow"].copy(); fm[i, a] -= h
+                g.append((_flow_pose_objective(q, r["pose"], fp, sig) - _flow_pose_objective(q, r["pose"], fm, sig))/(2*h))
+        assert np.abs(g).max() < 1e-4*max(1.0, f0), (sig, np.abs(g).max(), f0)
+
+
+def _motion_objective(q, poses, H, pts, sig_motion, sig_proj, k, sig_prior):
+    """the objective of MotionOnlyRefinementOptimizer written independently of oracle/: numpy pinhole projection, 4x4 algebra,
+    scipy.linalg.logm for the pose priors, scipy's Huber loss"""
+    from scipy.linalg import logm
+    from scipy.special import huber
+
+    def mat(P):
+        M = np.eye(4); M[:3, :3] = np.asarray(P)[:9].reshape(3, 3); M[:3, 3] = np.asarray(P)[9:]; return M
+
+    def proj_res(X, p, z):
+        c = (np.linalg.inv(mat(X)) @ np.concatenate([p, np.ones((len(p), 1))], 1).T).T[:, :3]
+        with np.errstate(all="ignore"):
+            r = np.stack([K5[0]*c[:, 0]/c[:, 2] + K5[3], K5[1]*c[:, 1]/c[:, 2] + K5[4]], 1) - z
+        r[c[:, 2] <= 0] = 2.0*K5[0]
+        return r
+    total = 0.0
+    for X, p, z in ((poses[0], pts[:, :3], q["kp_prev"]), (poses[1], pts[:, 3:], q["kp_cur"])):
+        total += huber(k, np.linalg.norm(proj_res(X, p, z), axis=1)/sig_proj).sum()
+    back = (np.linalg.inv(mat(H)) @ np.concatenate([pts[:, 3:], np.ones((len(pts), 1))], 1).T).T[:, :3]      # H^-1 m_k
+    total += huber(k, np.linalg.norm(pts[:, :3] - back, axis=1)/sig_motion).sum()
+    for X, prior in ((poses[0], q["pose_prev"]), (poses[1], q["pose_cur"])):
+        L = np.real(logm(np.linalg.inv(mat(X)) @ mat(prior)))
+        xi = np.array([L[2, 1], L[0, 2], L[1, 0], L[0, 3], L[1, 3], L[2, 3]])
+        total += 0.5*((xi/sig_prior)**2).sum()
+    return float(total)
+
+
+def test_motion_refine_oracle_against_independent_objective():
+    from oracle import star_oracle as SO
+    rng = np.random.default_rng(15)
+    q = make_motion_problem(rng, 25, outliers=0.1)
+    args = (0.05, 2.0, 1.0, 1e-3)
+    m = SO._MotionRefine(q["pose_prev"], q["pose_cur"], q["motion_init"], K5, q["kp_prev"], q["kp_cur"], q["points_init"], *args)
+    for _ in range(3):
+        m.step(np.concatenate([rng.normal(0, 0.02, 6*25), rng.normal(0, 1e-4, 12), rng.normal(0, 0.02, 6)]))
+        f = _motion_objective(q, m.o.pose[:2], m.o.pose[2], m.o.point.reshape(25, 6), *args)
+        assert abs(m.error() - f) <= 1e-9*max(f, 1.0), (m.error(), f)
+
+
 def test_motion_refine_oracle_reduces_error():
     from oracle import star_oracle as SO
     rng = np.random.default_rng(4)
